@@ -1,0 +1,90 @@
+"""Pin the CPU oracle (oracle/pbr_oracle.py) against outputs of the UNMODIFIED reference.
+
+The fixtures under tests/golden/ were produced by oracle/make_golden.py from /root/reference
+(PyREMOT 1.0.17, SciPy 1.18.1). RHS-level tolerance 1e-12 relative (pow/T**3 last-bit differences),
+converged solves 1e-8.
+"""
+import numpy as np
+import pytest
+
+from oracle import pbr_oracle as O
+from pyremot_b200 import cases
+
+
+def relerr(a, b, floor=0.0):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.max(np.abs(a - b)/(np.abs(b) + floor))
+
+
+def test_props_known_answers(golden):
+    g = golden("props")
+    sym = list(g["symbols"])
+    assert tuple(sym) == O.COMPONENT_SYMBOLS                      # rmtCom() order
+    Ts = g["Ts"]
+    assert relerr(O.cp(sym, Ts), g["cp_all"]) < 1e-14
+    assert relerr(O.cp_mean(sym, Ts), g["cpmean_all"]) < 1e-14
+    assert relerr(O.viscosity(sym, Ts), g["mu_all"]) < 1e-14
+    comps = cases.MEOH_DME_COMPONENTS
+    S, dH25, sides = O.parse_reactions(cases.MEOH_DME_REACTIONS, comps)
+    assert np.array_equal(S, [[-3, -1, 1, 0, 1, 0], [1, 1, -1, -1, 0, 0], [0, 0, 1, 0, -2, 1]])
+    assert relerr(dH25, g["dH25"]) < 1e-14
+    assert relerr(O.parse_reactions({"R1": "2CH4 <=> C2H4 + 2H2"}, ["CH4", "C2H4", "H2"])[1], g["dH25_ch4"]) < 1e-14
+    assert relerr(O.dH_correction(sides, Ts), g["dHcorr"], floor=1e-9) < 1e-13
+    MW = np.array([O._DB[s][0] for s in comps])
+    mu = O.viscosity(comps, Ts)
+    assert relerr(O.wilke(mu, np.broadcast_to(g["x0"], mu.shape), MW), g["mu_mix"]) < 1e-14
+    # values printed by the reference's own scripts (tests/test_heatCapacity.py, test_viscosity.py)
+    assert np.allclose(dH25, [-49010, -41160, -24520], rtol=1e-12)
+    assert np.allclose(O.cp_mean(comps, 523.0), [28.605201550287504, 41.085448574875535, 34.750290853275004,
+                                                 29.62105503875, 53.714055370462724, 79.34119544325], rtol=1e-14)
+    assert np.allclose(O.wilke(O.viscosity(comps, 523.0), g["x0"], MW), 2.5105175291507334e-05, rtol=1e-13)
+
+
+@pytest.mark.parametrize("tag,pt", [("noniso", "non-iso-thermal"), ("iso", "iso-thermal")])
+def test_n1_rhs_vs_reference(golden, tag, pt):
+    g = golden("n1_rhs")
+    Y, F = g[f"y_{tag}"], g[f"f_{tag}"]
+    ens = O.Ensemble(cases.readme_case("N1", pt), N=len(Y))
+    assert np.allclose(ens.iv_n1()[0], Y[0], rtol=1e-15)
+    f = ens.rhs_n1(Y)
+    assert relerr(f, F, floor=1e-300) < 1e-11
+    # scalar (non-vectorised) rate evaluation agrees with the numpy rebinding
+    e1 = O.Ensemble(cases.readme_case("N1", pt), N=4)
+    r_v = O.rates(e1.rate_expr, [523.0]*4, [5e6]*4, e1.x0, e1.C0)
+    r_s = O.rates(e1.rate_expr, [523.0]*4, [5e6]*4, e1.x0, e1.C0, vectorised=False)
+    assert relerr(r_v, r_s) < 1e-13
+    if tag == "noniso":  # SURVEY.md §8c inlet values
+        assert np.allclose(r_s[0], [85.04367720386661, -159.23189212928682, 236.7358718211693], rtol=1e-10)
+        assert np.allclose(f[0], [-3.6040866831177381, -2.1246841259261795, 4.183788727621879, 1.3849828473304004,
+                                  -3.3785079247956205, 2.0591046016956995, -1.8090067614742154e-03,
+                                  2.6597909560060318], rtol=1e-10)
+
+
+def test_n1_rhs_sweep_vs_reference(golden):
+    g = golden("n1_rhs")
+    rows = cases.ensemble_rows(24)
+    ens = O.Ensemble(cases.readme_case("N1"), {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]})
+    for k in range(2):
+        assert relerr(ens.rhs_n1(g["y_sweep"][:, k]), g["f_sweep"][:, k], floor=1e-300) < 1e-11
+    assert np.allclose(ens.iv_n1(), g["y_sweep"][:, 0], rtol=1e-15)
+
+
+@pytest.mark.parametrize("tag,mk,zNo", [
+    ("readme_z5", lambda: cases.readme_case("N2"), 5),
+    ("readme_z12", lambda: cases.readme_case("N2"), 12),
+    ("readme_iso_z8", lambda: cases.readme_case("N2", "iso-thermal"), 8),
+    ("dme_z20", cases.dme_n2_case, 20),
+    ("ch4_z10", cases.ch4_n2_case, 10),
+])
+def test_n2_rhs_vs_reference(golden, tag, mk, zNo):
+    g = golden("n2_rhs")
+    Y, F = g[f"y_{tag}"], g[f"f_{tag}"]
+    ens = O.Ensemble(mk(), N=len(Y))
+    assert np.allclose(ens.iv_n2(zNo)[0], Y[0], rtol=1e-15)
+    f = ens.rhs_n2(Y)
+    assert f.shape == F.shape
+    assert relerr(f, F, floor=1e-9) < 1e-11
+    if tag == "readme_z5":
+        assert np.allclose(f[0][:, 0], [-1.8481007150019408, -1.0894938433835588, 2.1453598702699304,
+                                        0.7101904075743676, -1.7324286179635533, 1.0558660268863722,
+                                        0.5319153449678685], rtol=1e-10)
