@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — reactor-solves/sec on BASELINE.json configs[1] (N1 steady-state ensemble, 65,536 reactors per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch: K0 prolog -> K2 fused BDF solve -> K5 un-scale of the
+outlet rows, for every reactor of the rank's shard (weak scaling: 65,536 reactors per GPU; N>1 adds the single
+NCCL all-gather of outlet rows).  `value` times the step with inputs resident in HBM; `e2e` times the
+host-buffer C-ABI call (pinned host input table -> H2D -> kernels -> D2H of outlet/status).  `cpu_baseline` /
+`--impl reference` time the CPU path (oracle port of the reference: SciPy LSODA at the reference's default
+tolerances on the NumPy restatement of its RHS, one process per host core) on a bounded sample of the same rows.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 65536
+RTOL, ATOL = 1e-9, 1e-13
+METRIC = "reactor-solves/sec"
+WORKLOAD = "N1 steady-state methanol/DME packed-bed ensemble, 65536 reactors/GPU sweeping inlet T, P, feed composition (BASELINE configs[1])"
+
+
+# ----------------------------------------------------------------------------- CPU path (oracle port)
+def _cpu_worker(args):
+    lo, hi, tol = args
+    from oracle import pbr_oracle as O
+    from pyremot_b200 import cases
+    rows = cases.ensemble_rows(hi - lo, offset=lo)
+    ens = O.Ensemble(cases.readme_case("N1"), {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]})
+    kw = {} if tol is None else {"rtol": tol[0], "atol": tol[1]}
+    _, data, nfev = O.solve_n1(ens, method="LSODA", **kw)
+    return hi - lo, int(nfev.sum())
+
+
+def cpu_path(n_inst, cores=None, tol=None):
+    """Solve rows [0, n_inst) with the oracle port on `cores` processes; returns (solves/s, seconds, total nfev)."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    per = max(1, n_inst // (cores*2))
+    chunks = [(lo, min(lo + per, n_inst), tol) for lo in range(0, n_inst, per)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(0, 1, tol)]*cores)      # warm the workers (imports) outside the timed region
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, chunks, chunksize=1)
+        dt = time.perf_counter() - t0
+    return n_inst/dt, dt, sum(r[1] for r in res)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = max(8*cores, 64)
+    # bounded sample per step: ~0.35 s per solve per core
+    times = []
+    for s in range(a.warmup + a.steps):
+        v, dt, nfev = cpu_path(n, cores)
+        if s >= a.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = n*len(times)/total
+    sample = f"rows 0..{n-1} of the seeded config-2 table per step, SciPy LSODA rtol 1e-3/atol 1e-6 (the reference's defaults), {cores} processes"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3*total/len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_per_step": n},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.stop = [], False
+        self.index = index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append([x.strip() for x in o])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for s in self.samples if len(s) >= 6 for k in range(4) if s[2 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def algorithmic_flops(model, stats):
+    """Algorithmic FP64 operation count of one K2 launch from the per-instance integrator counters.
+
+    Per-unit figures: every +,-,*,/ and every exp/log/log10/pow/sqrt counts 1.
+    rate DAG ops are counted exactly from the compiled expressions; the balance / linear-algebra terms are
+    hand counts of the formulas in csrc/pbr_device.cuh."""
+    nv, n, R = model.nv1, model.n, model.n_rxn
+    ops_r, ops_rj = model.rates.op_counts()
+    rhs = ops_r + (16*n + 14*R + 40)                 # balances: scaling, x_i, M, rho, Ergun, S^T r, Cp, dH, energy
+    jac = ops_rj + (16*n + 14*R + 40) + nv*(4*R*n//2 + 6*n + 30)    # chain rule per column + stores
+    lu = (2*nv**3)//3 + nv*nv
+    solve = 2*nv*nv + 6*nv                           # triangular solves + Newton update / norms
+    step = 30*nv                                     # predictor, psi, error norms, D update (per accepted step)
+    nsteps, nrej, nfev, nlu = [float(x) for x in stats.sum(axis=1)]
+    return nfev*(rhs + solve) + nlu*(jac + lu) + (nsteps + nrej)*step, {"rhs": rhs, "jac": jac, "lu": lu, "solve": solve, "step": step}
+
+
+def run_gpu(a):
+    import torch
+    import torch.distributed as dist
+    from pyremot_b200 import cases
+    from pyremot_b200.api import get_model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N = N_PER_GPU
+    mi = cases.readme_case("N1")
+    model = get_model(mi, device=local)
+    rows = cases.ensemble_rows(N, offset=rank*N)          # every rank regenerates its own shard from the seed
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    tab_h = torch.from_numpy(model.instance_table(mi, sweep)).pin_memory()
+    tab_d = tab_h.cuda()
+    flush = torch.empty(256*1024*1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    gathered = torch.empty((world*N, model.nv1), dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def step_device():
+        par = model.prolog(tab_d)
+        r = model.solve_n1(par, rtol=RTOL, atol=ATOL, n_out=101, profile=False, stats=True)
+        out = model.unscale_n1(par, r["outlet_y"][None])          # [N, nv1, 1]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out.view(N, model.nv1))
+        return r, out
+
+    # host-buffer path: pinned output buffers
+    out_h = {"outlet": torch.empty((N, model.nv1), dtype=torch.float64).pin_memory().numpy(),
+             "status": torch.empty((N,), dtype=torch.int32).pin_memory().numpy(),
+             "stats": torch.empty((4, N), dtype=torch.int32).pin_memory().numpy()}
+
+    def step_host():
+        return model.solve_n1_host(tab_h.numpy(), rtol=RTOL, atol=ATOL, n_out=101, profile=False, out=out_h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        r, out = step_device()
+    torch.cuda.synchronize()
+    assert int((r["status"] != 0).sum().item()) == 0, "some reactors failed to integrate"
+    stats = r["stats"].cpu().numpy()
+
+    # ---- timed: device-resident
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    l0 = model.launch_count
+    barrier()
+    with ClockSampler(local) as clk:
+        for k in range(a.steps):
+            flush.fill_(k)                                   # L2 flush between timed iterations (untimed)
+            ev[k][0].record()
+            par = model.prolog(tab_d)
+            kev[k][0].record()
+            r = model.solve_n1(par, rtol=RTOL, atol=ATOL, n_out=101, profile=False, stats=True)
+            kev[k][1].record()
+            out = model.unscale_n1(par, r["outlet_y"][None])
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, out.view(N, model.nv1))
+            ev[k][1].record()
+        barrier()
+    launches = model.launch_count - l0
+    t_dev = sum(e0.elapsed_time(e1) for e0, e1 in ev)*1e-3
+    t_k2 = sum(e0.elapsed_time(e1) for e0, e1 in kev)*1e-3/a.steps
+    # ---- timed: end-to-end through the host-buffer C-ABI call
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(a.steps):
+        rh = step_host()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    assert (rh["status"] == 0).all()
+    assert np.array_equal(rh["outlet"], out.view(N, model.nv1).cpu().numpy()), "host and device paths disagree"
+
+    tt = torch.tensor([t_dev, t_e2e, t_k2], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e, t_k2 = [float(x) for x in tt.cpu()]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        fp64_peak = model.fp64_peak()
+        flops, per_unit = algorithmic_flops(model, stats)
+        achieved = flops/t_k2/1e12
+        # secondary: standalone N2 RHS kernel (HBM-bound side of the path), zNo=100, inputs larger than L2
+        rhs = bench_rhs_n2(model, mi, peaks)
+        cores = os.cpu_count() or 1
+        n_cpu = max(4*cores, 32)
+        cpu_v, cpu_dt, _ = cpu_path(n_cpu, cores)
+        line = {
+            "metric": METRIC, "value": world*N*a.steps/t_dev, "unit": "solves/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": 1e3*t_dev/a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "instances_per_gpu": N, "rtol": RTOL, "atol": ATOL, "integrator": "BDF(1-5)/Newton, analytic Jacobian",
+                       "outputs": "outlet rows (n+2) per reactor", "l2": "flushed between timed iterations (256 MiB write)"},
+            "e2e": {"value": world*N*a.steps/t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(tab_h.numel()*8),
+                    "d2h_bytes_per_step": int(sum(v.nbytes for v in out_h.values()))},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {"kernel": "pbr_k2_solve_n1", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved/fp64_peak if fp64_peak else None, "traffic": None,
+                         "peak_source": "DFMA probe pbr_k_dfma_peak measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                         "kernel_ms": 1e3*t_k2, "algorithmic_flops_per_launch": flops, "flops_per_unit": per_unit,
+                         "mean_steps": float(stats[0].mean()), "mean_nfev": float(stats[2].mean()), "mean_nlu": float(stats[3].mean()),
+                         "max_over_mean_nfev": float(stats[2].max()/stats[2].mean())},
+            "rhs_n2_roofline": rhs,
+            "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cores, "kind": "port",
+                             "sample": f"rows 0..{n_cpu-1} of the same table, SciPy LSODA at the reference's default rtol 1e-3/atol 1e-6 "
+                                       f"on the NumPy RHS restatement, {cores} processes, {cpu_dt:.1f} s"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_rhs_n2(model, mi, peaks):
+    """K3 standalone: RHS evals/s and achieved GB/s (16*(n+1)*zNo B per instance-eval) at zNo=100."""
+    import torch
+    from pyremot_b200 import cases
+    from pyremot_b200.api import get_model
+    mi2 = cases.readme_case("N2")
+    m2 = get_model(mi2, device=model.device)
+    zNo, N = 100, 65536                       # 2 x 367 MB of state: larger than L2
+    rows = cases.ensemble_rows(N)
+    tab = torch.from_numpy(m2.instance_table(mi2, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]})).cuda()
+    par = m2.prolog(tab)
+    Y = torch.empty((N, m2.nv2, zNo), dtype=torch.float64, device="cuda")
+    Y[:, :m2.n, :] = par[16:16 + m2.n].t()[:, :, None]
+    Y[:, m2.n, :] = torch.linspace(0, 0.2, zNo, device="cuda", dtype=torch.float64)[None, :]
+    dY = torch.empty_like(Y)
+    for _ in range(3):
+        m2.rhs_n2(par, Y, out=dY)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        m2.rhs_n2(par, Y, out=dY)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)/reps
+    bytes_ = 16.0*m2.nv2*zNo*N
+    gbs = bytes_/(ms*1e-3)/1e9
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return {"kernel": "pbr_k3_rhs_n2", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs/peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+            "traffic": None, "zNo": zNo, "instances": N, "ms": ms, "rhs_evals_per_s": N/(ms*1e-3), "node_evals_per_s": N*zNo/(ms*1e-3)}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_gpu(a)

@@ -1,0 +1,114 @@
+/* pbr.h — C ABI of libpbr.so, the B200-native replacement of PyREMOT's N1 / N2 hot path.
+ *
+ * The reference has no FFI layer: its boundary is the Python call rmtExe(modelInput)
+ * (/root/reference/PyREMOT/rmt.py:21-80).  Everything below rmtExe that the path executes
+ * (PyREMOT/docs/pbHomoReactor.py runN1 :2694-3015 / runN2 :3319-3704 and the SciPy solve_ivp
+ * calls at :2931, :3609) is replaced by the entry points declared here; the thin Python host
+ * (pyremot_b200/engine.py, ctypes) is their only caller.  INTEGRATION.md shows the binding a
+ * PyREMOT maintainer would add.
+ *
+ * Conventions: plain C types only; every function returns 0 on success and a negative pbr_status on
+ * failure, with a message available from pbr_last_error().  A pbr_ctx is bound to one CUDA device and
+ * is not thread-safe (one ctx per host thread).  `stream` is a cudaStream_t passed as void* (NULL =
+ * legacy default stream).  "dev" pointers are device memory owned by the caller; "host" pointers are
+ * host memory (pinned or pageable).  All floating point data is IEEE binary64.
+ *
+ * Per-instance tables
+ *   inst_in  [N][k_in]   AoS rows: T0, P0, VoFlRa, ReInDi, ReLe, PaDi, BeVoFr, U, Tm, C0[n_comp], rate_par[n_par]
+ *                        (the fields runN1/runN2 read from modelInput: pbHomoReactor.py:2716-2782, :3341-3411)
+ *   inst_par [k_par][N]  SoA derived constants written by pbr_prolog (K0)
+ * State layouts
+ *   N1  y  [nv1][N]              instance-minor; nv1 = n_comp+2 (iso-thermal: n_comp+1): c_i/Cmax, P/Pf, (T-Tf)/Tf
+ *   N2  Y  [N][nv2][zNo]         the reference's var-major flatten (pbHomoReactor.py:3873); nv2 = n_comp+1 (iso: n_comp)
+ */
+#ifndef PBR_H
+#define PBR_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pbr_ctx pbr_ctx;
+
+typedef enum {
+    PBR_SUCCESS = 0,
+    PBR_E_INVALID = -1,      /* bad argument / call order */
+    PBR_E_CUDA = -2,         /* CUDA runtime or driver error */
+    PBR_E_NVRTC = -3,        /* rate source failed to compile (see log) */
+    PBR_E_NODEVICE = -4,     /* compute entry point called on a compile-only context */
+    PBR_E_NOMEM = -5
+} pbr_status;
+
+/* per-instance integrator status written to `status[]` (0 = solved) */
+#define PBR_INST_OK 0
+#define PBR_INST_STEP_TOO_SMALL 1
+#define PBR_INST_MAX_STEPS 2
+#define PBR_INST_NONFINITE 3
+#define PBR_INST_SINGULAR 4
+
+/* device >= 0: bind to that CUDA device (fails loudly if there is none). device < 0: compile-only context
+ * (NVRTC needs no GPU) — used by the build check and the CPU-side tests. */
+pbr_ctx* pbr_create(int device);
+void pbr_destroy(pbr_ctx* ctx);
+const char* pbr_last_error(pbr_ctx* ctx);
+const char* pbr_version(void);
+
+/* Species / reaction tables of the model (replaces rmtCore.initComponentData / initReaction,
+ * PyREMOT/docs/rmtCore.py:129-183, and the property look-ups of rmtThermo.py:16-49, 129-198):
+ *   MW[n_comp] g/mol; cp_coef[n_comp][4] (a + bT + cT^2 + dT^3, J/mol/K); vis_coef[n_comp][4] (eq1 A,B,C,D);
+ *   S[n_rxn][n_comp] stoichiometric matrix; dH25[n_rxn] J/mol; dcp_coef[n_rxn][4] = sum_k nu_jk cp_coef[k]
+ *   (over ALL species named in reaction j, also those absent from the component list — rmtThermo.py:258-312). */
+int pbr_set_species(pbr_ctx* ctx, int n_comp, int n_rxn, const double* MW, const double* cp_coef,
+                    const double* vis_coef, const double* S, const double* dH25, const double* dcp_coef,
+                    int iso_thermal);
+
+/* Compile the model: `cuda_src` defines PBR_NP, pbr_rates() and pbr_rates_jac() (output of the rate-expression
+ * compiler; replaces reactionRateExe, PyREMOT/docs/rmtReaction.py:11-61).  NVRTC -> sm_100a cubin, cached in
+ * `cache_dir` (may be NULL) under a hash of the full program text.  `*log` (may be NULL) receives the NVRTC log. */
+int pbr_load_rates(pbr_ctx* ctx, const char* cuda_src, int n_par, const char* cache_dir, const char** log);
+
+int pbr_model_dims(pbr_ctx* ctx, int* n_comp, int* n_rxn, int* n_par, int* nv1, int* nv2, int* k_in, int* k_par);
+const char* pbr_model_source(pbr_ctx* ctx);          /* full program text handed to NVRTC */
+int pbr_model_cubin(pbr_ctx* ctx, const void** data, unsigned long* size);
+int pbr_kernel_attr(pbr_ctx* ctx, const char* kernel, int* regs, int* static_smem, int* local_bytes);
+
+/* K0 — prolog of runN1 / runN2 (pbHomoReactor.py:2744-2862, :3370-3497) */
+int pbr_prolog(pbr_ctx* ctx, long N, const double* inst_in_dev, double* inst_par_dev, void* stream);
+
+/* RHS callbacks modelEquationN1 (:3017-3314) / modelEquationN2 (:3706-4134), batched */
+int pbr_rhs_n1(pbr_ctx* ctx, long N, const double* inst_par_dev, const double* y_dev, double* f_dev, void* stream);
+int pbr_jac_n1(pbr_ctx* ctx, long N, const double* inst_par_dev, const double* y_dev, double* f_dev,
+               double* J_dev /* [nv1*nv1][N], row-major (i,k) = d f_i / d y_k */, void* stream);
+int pbr_rhs_n2(pbr_ctx* ctx, long N, int zNo, const double* inst_par_dev, const double* Y_dev, double* dYdt_dev,
+               void* stream);
+
+/* K2 — the solve_ivp call of runN1 (:2931) with t_eval = linspace(0,1,n_out) (:2862): variable-order BDF.
+ *   prof_y_dev   [n_out][nv1][N] scaled state at the output points, or NULL
+ *   outlet_y_dev [nv1][N]        scaled state at z = 1
+ *   status_dev   [N] int         PBR_INST_*
+ *   stats_dev    [4][N] int      steps, rejected+failed, RHS evals, LU factorisations; or NULL */
+int pbr_solve_n1(pbr_ctx* ctx, long N, const double* inst_par_dev, double rtol, double atol, int n_out,
+                 int max_steps, double* prof_y_dev, double* outlet_y_dev, int* status_dev, int* stats_dev,
+                 void* stream);
+
+/* K5 — sortResult4 + mole fractions (solResultAnalysis.py:191-249, pbHomoReactor.py:2973-2983):
+ * scaled y [K][nv1][N] -> dataYs [N][nv1][K] = rows x_1..x_n, P [Pa], T [K] */
+int pbr_unscale_n1(pbr_ctx* ctx, long N, int K, const double* inst_par_dev, const double* y_dev, double* out_dev,
+                   void* stream);
+
+/* Whole N1 path with HOST buffers (what rmtExe does per reactor, batched): H2D of inst_in, K0, K2, K5, D2H.
+ *   prof_host   [N][nv1][n_out] dataYs per instance, or NULL;  outlet_host [N][nv1] = dataYs[:, -1]
+ *   status_host [N];  stats_host [4][N] or NULL */
+int pbr_solve_n1_host(pbr_ctx* ctx, long N, const double* inst_in_host, double rtol, double atol, int n_out,
+                      int max_steps, double* prof_host, double* outlet_host, int* status_host, int* stats_host);
+
+/* FP64-pipe peak probe (DFMA streams) — roofline denominator the driver's MEASURED_PEAKS.json lacks. */
+int pbr_fp64_peak(pbr_ctx* ctx, int iters, double* tflops);
+
+/* number of kernel launches issued through this context since creation */
+long pbr_launch_count(pbr_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBR_H */

@@ -1,0 +1,174 @@
+"""Drop-in boundary: ``rmtExe(modelInput)`` / ``rmtCom()`` with PyREMOT's signatures, plus the ensemble entry.
+
+Mirrors `PyREMOT/rmt.py:21-92` for the models this package accelerates ("N1", "N2"): same ``modelInput``
+schema, same result layout (``dataPack`` / ``resPack``, `pbHomoReactor.py:2991-3007`,
+`:3664-3696`), same error behaviour (prints then re-raises; unknown component ->
+``Exception("Component database is not up to date!")``; missing key -> ``KeyError``; solver failure ->
+``RuntimeError``).  Everything below this call runs on the GPU through libpbr.so; there is no CPU path.
+
+Differences that are deliberate and documented in DESIGN.md:
+* the integrator is the batched BDF of libpbr at tight tolerances (default rtol 1e-9 / atol 1e-13), so results
+  are the *converged* solution of the reference's equations; the reference itself integrates at SciPy's
+  default rtol 1e-3 and differs from its own converged answer by up to 1e-3.  ``solver-config`` accepts the
+  optional keys ``rtol`` / ``atol``; ``ivp`` is accepted and ignored ("AM" is rejected: explicit fixed step).
+* ``display-result`` must be "False" (no plotting in a batch solver).
+* grid sizes come from ``pyremot_b200.solverSetting`` (same keys as `PyREMOT/solvers/solSetting.py:30-39`).
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import components as DB
+from . import engine
+
+# same mutable-module-dict mechanism as `PyREMOT/solvers/solSetting.py:30-39`
+solverSetting = {
+    "N1": {"zNo": 100},
+    "N2": {"zNo": 20, "rNo": 5, "tNo": 5, "timesNo": 5},
+}
+
+DEFAULT_RTOL = 1e-9
+DEFAULT_ATOL = 1e-13
+
+_models = {}
+
+
+def rmtCom():
+    """Components available in the database, `PyREMOT/rmt.py:83-92`."""
+    return ",".join(DB.componentSymbolList)
+
+
+def _component_list(FeCom):
+    """`PyREMOT/docs/rmtUtility.py:313-340`: shell + tube + medium."""
+    out = []
+    for k in ("shell", "tube", "medium"):
+        v = FeCom.get(k)
+        if v:
+            out.extend(v)
+    return out
+
+
+def get_model(modelInput, params=(), device=0):
+    """Compile (or fetch) the model for the static part of ``modelInput``."""
+    probe = engine.ratec.compile_rates(modelInput["reaction-rates"], len(modelInput["feed"]["components"]["shell"]),
+                                       params=params)
+    key = (tuple(modelInput["feed"]["components"]["shell"]), tuple(modelInput["reactions"].items()),
+           modelInput["operating-conditions"]["process-type"], probe.key, tuple(params), device)
+    m = _models.get(key)
+    if m is None:
+        m = engine.Model(modelInput, params=params, device=device)
+        _models[key] = m
+    return m
+
+
+def _tolerances(modelInput):
+    sc = modelInput["solver-config"]
+    ivp = sc["ivp"]
+    if ivp == "AM":
+        raise NotImplementedError("ivp='AM' (explicit fixed-step, PyREMOT/solvers/odeSolver.py) is out of scope")
+    if sc["display-result"] == "True":
+        raise NotImplementedError("display-result must be \"False\": plotting is out of scope for the batched solver")
+    return float(sc.get("rtol", DEFAULT_RTOL)), float(sc.get("atol", DEFAULT_ATOL))
+
+
+def _n1_pack(modelInput, model, dataYs, y_scaled, elapsed):
+    """One reference-layout result dict, `pbHomoReactor.py:2949-3007`.
+    dataYs: [nv1, K] un-scaled; y_scaled: [nv1, K]."""
+    compList = list(modelInput["feed"]["components"]["shell"])
+    n = len(compList)
+    iso = model.iso
+    K = dataYs.shape[1]
+    labelList = compList + ["Pressure"] + ([] if iso else ["Temperature"])
+    Cmax = float(np.max(np.asarray(modelInput["feed"]["concentration"], dtype=np.float64)))
+    cons1 = y_scaled[:n]
+    theta = y_scaled[n + 1] if not iso else np.repeat(0, K).reshape(K)
+    T = dataYs[n + 1:n + 2] if not iso else np.full((1, K), float(modelInput["operating-conditions"]["temperature"]))
+    return {
+        "modelId": modelInput["model"],
+        "processType": modelInput["operating-conditions"]["process-type"],
+        "successStatus": True,
+        "computation-time": elapsed,
+        "dataShape": (K,),
+        "labelList": labelList,
+        "indexList": [n, n, n + 1],
+        "dataTime": [],
+        "dataXs": np.linspace(0, 1, K),
+        "dataYCons1": cons1,
+        "dataYCons2": cons1*Cmax,
+        "dataYTemp1": theta,
+        "dataYTemp2": T,
+        "dataYs": dataYs,
+    }
+
+
+def _run_n1(modelInput, device=0):
+    import torch
+    start = time.perf_counter()
+    rtol, atol = _tolerances(modelInput)
+    model = get_model(modelInput, device=device)
+    K = solverSetting["N1"]["zNo"] + 1                       # `pbHomoReactor.py:2858-2862`
+    tab = torch.from_numpy(model.instance_table(modelInput)).to(model._dev())
+    par = model.prolog(tab)
+    res = model.solve_n1(par, rtol=rtol, atol=atol, n_out=K, profile=True)
+    st = int(res["status"][0].item())
+    if st != 0:
+        print('ODE Error')
+        raise RuntimeError(f"N1 integration failed (status {st})")     # reference: bare raise -> RuntimeError
+    dataYs = model.unscale_n1(par, res["prof_y"])[0].cpu().numpy()
+    y_scaled = res["prof_y"][:, :, 0].t().contiguous().cpu().numpy()
+    elapsed = round(time.perf_counter() - start, 3)
+    return [_n1_pack(modelInput, model, dataYs, y_scaled, elapsed)]
+
+
+def rmtExe(modelInput, device=0):
+    """Check the model input, then run it — same contract as `PyREMOT/rmt.py:21-80`."""
+    try:
+        tic = time.perf_counter()
+        modelType = modelInput['model']
+        compList = _component_list(modelInput['feed']['components'])
+        for c in compList:
+            if c not in DB.componentSymbolList:
+                raise Exception("Component database is not up to date!")
+        if modelType == "N1":
+            resModel = _run_n1(modelInput, device=device)
+        elif modelType == "N2":
+            from .n2 import run_n2
+            resModel = run_n2(modelInput, device=device)
+        else:
+            raise NotImplementedError(f"model {modelType!r}: only the pseudo-homogeneous packed-bed models "
+                                      "N1 and N2 are implemented by pyremot_b200")
+        return {"resModel": resModel, "comTime": (time.perf_counter() - tic)*1000}
+    except Exception as e:
+        print(e)
+        raise
+
+
+def rmtExeBatch(modelInput, sweep, params=(), device=0, rtol=None, atol=None, profile=False, n_out=None,
+                return_device=False):
+    """Ensemble entry (new): solve N reactor instances that share ``modelInput``'s static part.
+
+    ``sweep``: dict of per-instance arrays (see ``engine.Model.instance_table``).  N1 only for now.
+    Returns dict(outlet [N, nv1] = last column of each instance's dataYs, dataYs [N, nv1, K] if profile,
+    status [N], stats [4, N]) as numpy arrays (torch CUDA tensors if ``return_device``).
+    """
+    import torch
+    if modelInput["model"] != "N1":
+        raise NotImplementedError("rmtExeBatch: N1 only")
+    r0, a0 = _tolerances(modelInput)
+    rtol = r0 if rtol is None else rtol
+    atol = a0 if atol is None else atol
+    model = get_model(modelInput, params=params, device=device)
+    K = n_out or (solverSetting["N1"]["zNo"] + 1)
+    tab = model.instance_table(modelInput, sweep)
+    if not return_device:
+        r = model.solve_n1_host(tab, rtol=rtol, atol=atol, n_out=K, profile=profile)
+        return r
+    tab = torch.from_numpy(tab).to(model._dev())
+    par = model.prolog(tab)
+    res = model.solve_n1(par, rtol=rtol, atol=atol, n_out=K, profile=profile)
+    out = {"outlet": model.unscale_n1(par, res["outlet_y"][None])[:, :, 0], "status": res["status"], "stats": res["stats"]}
+    if profile:
+        out["dataYs"] = model.unscale_n1(par, res["prof_y"])
+    return out

@@ -1,0 +1,884 @@
+// pbr_device.cuh — device code of the packed-bed reactor (N1 / N2) ensemble solver, sm_100a, FP64.
+//
+// This text is compiled at run time by NVRTC *after* a generated model header that defines
+//   PBR_NC, PBR_NR, PBR_NP, PBR_ISO                     species / reactions / runtime rate parameters / iso-thermal flag
+//   PBR_MW[NC], PBR_CP[NC][4], PBR_CPREF[NC]            MW [g/mol], Cp polynomial, Cp(298.15)      (data/componentData.py)
+//   PBR_VIS[NC][4]                                      viscosity eq1 parameters                    (data/dataGasViscosity.py)
+//   PBR_DH25[NR], PBR_DCP[NR][4], PBR_DCPREF[NR]        dH(25C) [J/mol], sum_k nu_jk Cp_k polynomial and its value at 298.15
+//   PBR_S_NNZ(F)                                        X-macro over the non-zeros F(j,i,nu) of the stoichiometric matrix
+//   pbr_rates / pbr_rates_jac                           the compiled rate expressions (pyremot_b200/ratec.py)
+// so every table is a compile-time constant and every loop over species / reactions unrolls.
+// With -DPBR_HOST the same text compiles as plain C++ (tests/hostsim: scalar emulation of one thread).
+//
+// What it replaces in the reference (all under /root/reference/PyREMOT):
+//   K0 prolog      docs/pbHomoReactor.py:2744-2862, :3370-3497 (+ gasTransPor.py:137-274, rmtThermo.py:52-101)
+//   N1 RHS         docs/pbHomoReactor.py:3133-3302  (modelEquationN1)
+//   N2 RHS         docs/pbHomoReactor.py:3827-4131  (modelEquationN2)
+//   integrator     scipy solve_ivp call sites :2931, :3609 -> variable-order BDF/NDF (scipy/integrate/_ivp/bdf.py)
+//   K5 epilog      solvers/solResultAnalysis.py:191-301, pbHomoReactor.py:2973-2983, :3655-3661
+#pragma once
+
+#ifndef PBR_NV1
+#define PBR_NV1 (PBR_NC + (PBR_ISO ? 1 : 2))   // N1 state: c_1..c_n, p, [theta]
+#endif
+#define PBR_NV2 (PBR_NC + (PBR_ISO ? 0 : 1))   // N2 per-node state: c_1..c_n, [theta]
+#define PBR_NPA (PBR_NP > 0 ? PBR_NP : 1)
+
+#define PBR_R 8.314472          // core/constants.py:8
+#define PBR_TREF 298.15         // core/constants.py:23
+#define PBR_EPS 1e-30           // core/constants.py:11
+#define PBR_PI 3.141592653589793
+
+// ---- rows of the derived per-instance parameter table inst_par[KPAR][N] (written by K0, SoA: row-major, instance-minor)
+enum {
+    PAR_TF = 0, PAR_PF, PAR_CMAX, PAR_CT0, PAR_VS0, PAR_EPS, PAR_ZF, PAR_E1, PAR_E2, PAR_RHO0,
+    PAR_CPMIX0, PAR_G, PAR_GH, PAR_UA, PAR_TM, PAR_MU, PAR_C0,          // c0[NC] follows
+    PAR_RP = PAR_C0 + PBR_NC,                                           // rate parameters [NP]
+    PBR_KPAR = PAR_RP + PBR_NP
+};
+// ---- columns of the raw per-instance input table inst_in[N][KIN] (AoS, as the host assembles it)
+enum {
+    IN_T = 0, IN_P, IN_VOFLRA, IN_REINDI, IN_RELE, IN_PADI, IN_BEVOFR, IN_U, IN_TM, IN_C0,
+    IN_RP = IN_C0 + PBR_NC,
+    PBR_KIN = IN_RP + PBR_NP
+};
+
+struct InstPar {
+    double Tf, Pf, Cmax, Ct0, vs0, eps, zf, E1, E2, rho0, Cpmix0, G, GH, Ua, Tm;
+    double c0[PBR_NC];
+    double rp[PBR_NPA];
+};
+
+PBR_DEV void pbr_load_par(const double* __restrict__ par, long N, long i, InstPar& p) {
+    p.Tf = par[PAR_TF*N + i];       p.Pf = par[PAR_PF*N + i];     p.Cmax = par[PAR_CMAX*N + i];
+    p.Ct0 = par[PAR_CT0*N + i];     p.vs0 = par[PAR_VS0*N + i];   p.eps = par[PAR_EPS*N + i];
+    p.zf = par[PAR_ZF*N + i];       p.E1 = par[PAR_E1*N + i];     p.E2 = par[PAR_E2*N + i];
+    p.rho0 = par[PAR_RHO0*N + i];   p.Cpmix0 = par[PAR_CPMIX0*N + i];
+    p.G = par[PAR_G*N + i];         p.GH = par[PAR_GH*N + i];     p.Ua = par[PAR_UA*N + i];
+    p.Tm = par[PAR_TM*N + i];
+#pragma unroll
+    for (int k = 0; k < PBR_NC; ++k) p.c0[k] = par[(PAR_C0 + k)*N + i];
+#pragma unroll
+    for (int k = 0; k < PBR_NP; ++k) p.rp[k] = par[(PAR_RP + k)*N + i];
+}
+
+// ---- property polynomials
+PBR_DEV double pbr_poly(const double* c, double T) { return c[0] + T*(c[1] + T*(c[2] + T*c[3])); }
+PBR_DEV double pbr_dpoly(const double* c, double T) { return c[1] + T*(2.0*c[2] + T*3.0*c[3]); }
+
+// =====================================================================================================
+// K0 prolog: raw inputs -> derived constants (one thread per instance)
+// =====================================================================================================
+PBR_DEV void pbr_prolog_one(const double* in, double* out, long N, long i) {
+    const double T = in[IN_T], P = in[IN_P], D = in[IN_REINDI], zf = in[IN_RELE], dp = in[IN_PADI];
+    const double eps = in[IN_BEVOFR], U = in[IN_U];
+    double C0[PBR_NC], x0[PBR_NC], mu[PBR_NC];
+    double Ct0 = 0.0, Cmax = 0.0;
+#pragma unroll
+    for (int k = 0; k < PBR_NC; ++k) { C0[k] = in[IN_C0 + k]; Ct0 += C0[k]; Cmax = fmax(Cmax, C0[k]); }
+    const double A = PBR_PI*(D*D)/4;                                   // pbHomoReactor.py:2751
+    const double vs0 = in[IN_VOFLRA]/A;                                // :2763
+    double M0 = 0.0, Cpmix0 = 0.0;
+#pragma unroll
+    for (int k = 0; k < PBR_NC; ++k) {
+        x0[k] = C0[k]/Ct0;                                             // :2766
+        // gasTransPor.py:137-155 eq1: A*1e-6*T^B/(1+C/T+D/T^2)  (DME's eq2 string is the same form with D=0)
+        mu[k] = PBR_VIS[k][0]*1e-6*pow(T, PBR_VIS[k][1])/(1.0 + PBR_VIS[k][2]/T + PBR_VIS[k][3]/(T*T));
+        M0 += x0[k]*PBR_MW[k];
+        Cpmix0 += x0[k]*0.5*(PBR_CPREF[k] + pbr_poly(PBR_CP[k], T));   // rmtThermo.py:52-101
+    }
+    M0 *= 1e-3;                                                        // :2793 kg/mol
+    // Wilke mixing rule, gasTransPor.py:229-274
+    double mumix = 0.0;
+#pragma unroll
+    for (int a = 0; a < PBR_NC; ++a) {
+        double den = 0.0;
+#pragma unroll
+        for (int b = 0; b < PBR_NC; ++b) {
+            double phi;
+            if (a == b) phi = 1.0;
+            else {
+                const int lo = a < b ? a : b, hi = a < b ? b : a;
+                const double t = 1.0 + sqrt(mu[lo]/mu[hi])*sqrt(sqrt(PBR_MW[hi]/PBR_MW[lo]));
+                const double up = t*t/sqrt(8.0*(1.0 + PBR_MW[lo]/PBR_MW[hi]));   // phi_{lo,hi}
+                phi = (a < b) ? up : (mu[a]/mu[b])*(PBR_MW[b]/PBR_MW[a])*up;
+            }
+            den += x0[b]*phi;
+        }
+        mumix += mu[a]*x0[a]/den;
+    }
+    const double rho0 = M0*Ct0;                                        // :2796
+    const double e3 = eps*eps*eps;
+    out[PAR_TF*N + i] = T;
+    out[PAR_PF*N + i] = P;
+    out[PAR_CMAX*N + i] = Cmax;                                        // :2819-2820 "MAX"
+    out[PAR_CT0*N + i] = Ct0;
+    out[PAR_VS0*N + i] = vs0;
+    out[PAR_EPS*N + i] = eps;
+    out[PAR_ZF*N + i] = zf;
+    out[PAR_E1*N + i] = 150.0*mumix*((1.0 - eps)*(1.0 - eps))/(e3*dp*dp);   // Ergun viscous coefficient :3214-3215
+    out[PAR_E2*N + i] = 1.75*(1.0 - eps)/(e3*dp);                      // Ergun inertial coefficient :3216-3217
+    out[PAR_RHO0*N + i] = rho0;
+    out[PAR_CPMIX0*N + i] = Cpmix0;
+    out[PAR_G*N + i] = (vs0/zf)*Cmax;                                  // :2821
+    out[PAR_GH*N + i] = rho0*vs0*T*(Cpmix0/M0)/zf;                     // :2823
+    out[PAR_UA*N + i] = U*(4.0/D);                                     // :2778 (input EfHeTrAr ignored)
+    out[PAR_TM*N + i] = in[IN_TM];
+    out[PAR_MU*N + i] = mumix;
+#pragma unroll
+    for (int k = 0; k < PBR_NC; ++k) out[(PAR_C0 + k)*N + i] = C0[k]/Cmax;  // :2833
+#pragma unroll
+    for (int k = 0; k < PBR_NP; ++k) out[(PAR_RP + k)*N + i] = in[IN_RP + k];
+}
+
+// =====================================================================================================
+// shared thermo-kinetic core: everything both models evaluate at one (c[], T, P) point
+// =====================================================================================================
+struct PointEval {
+    double x[PBR_NC], C[PBR_NC];
+    double Ct, invCt, T, P, M, rho;
+    double r[PBR_NR], ri[PBR_NC];
+    double cpm[PBR_NC], Cpmix, dH[PBR_NR], Hsum, Q;
+    // partials (JAC only)
+    double drT[PBR_NR], drP[PBR_NR], drx[PBR_NR][PBR_NC], drC[PBR_NR][PBR_NC], sx[PBR_NR];
+    double dCpmixT, dHdT[PBR_NR];
+};
+
+template <bool JAC>
+PBR_DEV void pbr_point(const double* c, double T, double P, const InstPar& p, PointEval& e) {
+    double Ct = 0.0;
+#pragma unroll
+    for (int i = 0; i < PBR_NC; ++i) { e.C[i] = c[i]*p.Cmax; Ct += e.C[i]; }      // :3161-3167
+    e.Ct = Ct; e.invCt = 1.0/Ct; e.T = T; e.P = P;
+    double M = 0.0;
+#pragma unroll
+    for (int i = 0; i < PBR_NC; ++i) { e.x[i] = e.C[i]*e.invCt; M += e.x[i]*PBR_MW[i]; }   // :3176, :3202
+    e.M = M*1e-3;
+    e.rho = P*e.M/(PBR_R*T);                                                      // rmtThermo.py:353-369
+    if (JAC) pbr_rates_jac(T, P, e.x, e.C, p.rp, e.r, e.drT, e.drP, e.drx, e.drC);
+    else     pbr_rates(T, P, e.x, e.C, p.rp, e.r);                                // rmtReaction.py:11-61
+#pragma unroll
+    for (int i = 0; i < PBR_NC; ++i) e.ri[i] = 0.0;
+#define PBR_ACC(j, i, nu) e.ri[i] += (nu)*e.r[j];
+    PBR_S_NNZ(PBR_ACC)                                                            // rmtReaction.py:64-97
+#undef PBR_ACC
+    if (!PBR_ISO) {
+        double Cpmix = 0.0, dCp = 0.0;
+#pragma unroll
+        for (int i = 0; i < PBR_NC; ++i) {
+            e.cpm[i] = 0.5*(PBR_CPREF[i] + pbr_poly(PBR_CP[i], T));               // rmtThermo.py:52-75
+            Cpmix += e.x[i]*e.cpm[i];
+            if (JAC) dCp += e.x[i]*0.5*pbr_dpoly(PBR_CP[i], T);
+        }
+        e.Cpmix = Cpmix; e.dCpmixT = dCp;
+        double Hsum = 0.0;
+#pragma unroll
+        for (int j = 0; j < PBR_NR; ++j) {
+            const double m = 0.5*(PBR_DCPREF[j] + pbr_poly(PBR_DCP[j], T));       // rmtThermo.py:258-312
+            e.dH[j] = PBR_DH25[j] + m*(T - PBR_TREF);
+            if (JAC) e.dHdT[j] = m + 0.5*pbr_dpoly(PBR_DCP[j], T)*(T - PBR_TREF);
+            Hsum += e.r[j]*e.dH[j];
+        }
+        e.Hsum = Hsum;
+        e.Q = (p.Tm == 0.0) ? 0.0 : p.Ua*(p.Tm - T);                              // rmtUtility.py:424-452
+    }
+    if (JAC) {
+#pragma unroll
+        for (int j = 0; j < PBR_NR; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < PBR_NC; ++i) s += e.x[i]*e.drx[j][i];
+            e.sx[j] = s;
+        }
+    }
+}
+
+// d r_j / d c_k  (c = scaled concentration; x_i = C_i/Ct, C_i = c_i Cmax), mask = d max(c,eps)/dc
+PBR_DEV void pbr_dr_dc(const PointEval& e, const InstPar& p, int k, double mask, double* drk) {
+    const double cmct = p.Cmax*e.invCt*mask;
+#pragma unroll
+    for (int j = 0; j < PBR_NR; ++j) drk[j] = cmct*(e.drx[j][k] - e.sx[j]) + (p.Cmax*mask)*e.drC[j][k];
+}
+
+PBR_DEV void pbr_dri(const double* drk, double* dri) {
+#pragma unroll
+    for (int i = 0; i < PBR_NC; ++i) dri[i] = 0.0;
+#define PBR_ACC(j, i, nu) dri[i] += (nu)*drk[j];
+    PBR_S_NNZ(PBR_ACC)
+#undef PBR_ACC
+}
+
+// =====================================================================================================
+// N1: steady-state axial ODE.  y = [c_1..c_n, p, theta]; f = dy/dz.   modelEquationN1 :3133-3302
+// Store: functor st(i, k, dfi_dyk) receiving the Jacobian column by column (JAC only).
+// =====================================================================================================
+struct NoStore { PBR_DEV void operator()(int, int, double) const {} };
+
+template <bool JAC, class Store>
+PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st) {
+    const int n = PBR_NC;
+    const double pr = y[n];
+    const double th = PBR_ISO ? 0.0 : y[n + (PBR_ISO ? 0 : 1)];
+    const double T = th*p.Tf + p.Tf;                                   // :3170
+    const double P = pr*p.Pf;                                          // :3173
+    PointEval e;
+    pbr_point<JAC>(y, T, P, p, e);
+    const double w = (e.Ct/p.Ct0)*(p.Pf/P);                            // :3180 v/v0 (interstitial == superficial ratio)
+    const double vs = p.vs0*w;                                         // :3184
+    const double zP = p.zf/p.Pf;                                       // :3219
+    f[n] = -(p.E1*vs + p.E2*e.rho*vs*vs)*zP;                           // :3214-3220
+    const double invGw = 1.0/(p.G*w);                                  // :3283, :3288
+#pragma unroll
+    for (int i = 0; i < n; ++i) f[i] = e.ri[i]*invGw;
+    double Den = 1.0, fth = 0.0;
+    if (!PBR_ISO) {
+        const double Num = (-e.Hsum + e.Q)/p.GH;                       // :3298
+        Den = (e.rho/p.rho0)*((e.Cpmix/p.Cpmix0)*p.eps)*w;             // :3284
+        fth = Num/Den;
+        f[n + 1] = fth;
+    }
+    if (JAC) {
+        const double cmct = p.Cmax*e.invCt;
+        const double dfp_dw = -zP*(p.E1*p.vs0 + 2.0*p.E2*e.rho*p.vs0*p.vs0*w);
+        const double dfp_drho = -zP*(p.E2*vs*vs);
+        double drk[PBR_NR], dri[PBR_NC];
+        // ---- species columns
+#pragma unroll
+        for (int k = 0; k < n; ++k) {
+            pbr_dr_dc(e, p, k, 1.0, drk);
+            pbr_dri(drk, dri);
+            const double dw = w*cmct;
+            const double drho = (e.rho/e.M)*cmct*(1e-3*PBR_MW[k] - e.M);
+#pragma unroll
+            for (int i = 0; i < n; ++i) st(i, k, dri[i]*invGw - f[i]*cmct);
+            st(n, k, dfp_dw*dw + dfp_drho*drho);
+            if (!PBR_ISO) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j];
+                const double dNum = -s/p.GH;
+                const double dDen = Den*(drho/e.rho + cmct*(e.cpm[k] - e.Cpmix)/e.Cpmix + cmct);
+                st(n + 1, k, (dNum - fth*dDen)/Den);
+            }
+        }
+        // ---- pressure column
+        {
+#pragma unroll
+            for (int j = 0; j < PBR_NR; ++j) drk[j] = p.Pf*e.drP[j];
+            pbr_dri(drk, dri);
+            const double dw = -w/pr, drho = e.rho/pr;
+#pragma unroll
+            for (int i = 0; i < n; ++i) st(i, n, dri[i]*invGw + f[i]/pr);
+            st(n, n, dfp_dw*dw + dfp_drho*drho);
+            if (!PBR_ISO) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j];
+                st(n + 1, n, (-s/p.GH)/Den);                           // d(rho*w)/dp = 0
+            }
+        }
+        // ---- temperature column
+        if (!PBR_ISO) {
+#pragma unroll
+            for (int j = 0; j < PBR_NR; ++j) drk[j] = p.Tf*e.drT[j];
+            pbr_dri(drk, dri);
+            const double drho = -e.rho*p.Tf/T;
+#pragma unroll
+            for (int i = 0; i < n; ++i) st(i, n + 1, dri[i]*invGw);
+            st(n, n + 1, dfp_drho*drho);
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j] + p.Tf*e.r[j]*e.dHdT[j];
+            const double dQ = (p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
+            const double dNum = (-s + dQ)/p.GH;
+            const double dDen = Den*(drho/e.rho + p.Tf*e.dCpmixT/e.Cpmix);
+            st(n + 1, n + 1, (dNum - fth*dDen)/Den);
+        }
+    }
+}
+
+// =====================================================================================================
+// N2: one axial node of the method-of-lines system.  modelEquationN2 :3892-4128
+//   yc[NV2] node state (unclamped), yb[NV2] upstream state (first==true: inlet BC), Pz pressure at the node.
+//   Returns dP/dz slope (Pa/m, dimensional: P_z[z+1] = P_z[z] + slope*dz, :3974-3979).
+//   JAC: diagonal block d f/d yc via st(i,k,v); sub-diagonal block is diagonal: sub[k] = d f_k / d yb_k.
+// =====================================================================================================
+template <bool JAC, class Store>
+PBR_DEV double pbr_n2_node(const double* yc, const double* yb, bool first, double Pz, double inv_dz,
+                           const InstPar& p, double* f, Store& st, double* sub) {
+    const int n = PBR_NC;
+    double c[PBR_NC];
+#pragma unroll
+    for (int i = 0; i < n; ++i) c[i] = fmax(yc[i], PBR_EPS);                    // :3899
+    const double th = PBR_ISO ? 0.0 : yc[PBR_ISO ? 0 : n];
+    const double T = th*p.Tf + p.Tf;                                            // :3914
+    PointEval e;
+    pbr_point<JAC>(c, T, Pz, p, e);
+    const double slope = -(p.E1*p.vs0 + p.E2*e.rho*p.vs0*p.vs0);                // :3970-3974 (v == vs0, :3937)
+    const double F1 = 1.0/(p.eps*(p.zf/p.vs0));                                 // :4075
+    const double invG = 1.0/p.G;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        const double cb = first ? p.c0[i] : fmax(yb[i], PBR_EPS);              // :4088-4093
+        f[i] = F1*(-((yc[i] - cb)*inv_dz) + e.ri[i]*invG);                      // :4095-4098 (unclamped centre)
+        if (JAC) sub[i] = (first || !(yb[i] > PBR_EPS)) ? 0.0 : F1*inv_dz;
+    }
+    double D2 = 1.0, heat = 0.0, rs = 1.0, cps = 1.0;
+    if (!PBR_ISO) {
+        rs = e.rho/p.rho0; cps = e.Cpmix/p.Cpmix0;
+        D2 = rs*cps*p.eps*(p.zf/p.vs0);                                         // 1/const_T2 :4077
+        const double thb = first ? 0.0 : yb[n];                                 // :4106-4111
+        const double conv = -1.0*rs*(cps*p.eps)*((th - thb)*inv_dz);            // :4116
+        heat = (1.0/p.GH)*(-e.Hsum) + (1.0/p.GH)*e.Q;                           // :4118-4120
+        f[n] = (conv + heat)/D2;                                                // :4125
+        if (JAC) sub[n] = first ? 0.0 : (p.vs0/p.zf)*inv_dz;
+    }
+    if (JAC) {
+        double drk[PBR_NR], dri[PBR_NC];
+#pragma unroll
+        for (int k = 0; k < n; ++k) {
+            const double mask = (yc[k] > PBR_EPS) ? 1.0 : 0.0;
+            pbr_dr_dc(e, p, k, mask, drk);
+            pbr_dri(drk, dri);
+#pragma unroll
+            for (int i = 0; i < n; ++i) st(i, k, F1*(dri[i]*invG - (i == k ? inv_dz : 0.0)));
+            if (!PBR_ISO) {
+                const double cmct = p.Cmax*e.invCt*mask;
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j];
+                const double dheat = -s/p.GH;
+                const double dD2 = D2*(cmct*(1e-3*PBR_MW[k] - e.M)/e.M + cmct*(e.cpm[k] - e.Cpmix)/e.Cpmix);
+                // d(conv/D2)/dc = 0: conv/D2 = -(vs0/zf)(th-thb)/dz exactly
+                st(n, k, (dheat - (heat/D2)*dD2)/D2);
+            }
+        }
+        if (!PBR_ISO) {
+#pragma unroll
+            for (int j = 0; j < PBR_NR; ++j) drk[j] = p.Tf*e.drT[j];
+            pbr_dri(drk, dri);
+#pragma unroll
+            for (int i = 0; i < n; ++i) st(i, n, F1*dri[i]*invG);
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j] + p.Tf*e.r[j]*e.dHdT[j];
+            const double dQ = (p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
+            const double dheat = (-s + dQ)/p.GH;
+            const double dD2 = D2*(-p.Tf/T + p.Tf*e.dCpmixT/e.Cpmix);
+            st(n, n, -(p.vs0/p.zf)*inv_dz + (dheat - (heat/D2)*dD2)/D2);
+        }
+    }
+    return slope;
+}
+
+// =====================================================================================================
+// dense LU with partial pivoting on a per-thread matrix held in strided storage (shared memory on device)
+// =====================================================================================================
+struct Strided {            // element idx of this thread's private array lives at base[idx*stride]
+    double* base; int stride;
+    PBR_DEV double& operator[](int idx) const { return base[(long)idx*stride]; }
+};
+
+// In-place LU of the NxN row-major matrix a; unit-lower L below the diagonal, U on/above, diagonal stored INVERTED.
+// piv: 4 bits per column (N <= 16). Returns false if a pivot is exactly zero / non-finite.
+template <int N>
+PBR_DEV bool pbr_lu_factor(const Strided& a, unsigned long long& piv) {
+    piv = 0ull;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        int pk = k;
+        double amax = fabs(a[k*N + k]);
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const double v = fabs(a[i*N + k]);
+            if (v > amax) { amax = v; pk = i; }
+        }
+        piv |= (unsigned long long)pk << (4*k);
+        if (pk != k) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) { const double t = a[k*N + j]; a[k*N + j] = a[pk*N + j]; a[pk*N + j] = t; }
+        }
+        if (!(amax > 0.0) || !(amax < 1e300)) ok = false;
+        const double inv = 1.0/a[k*N + k];
+        a[k*N + k] = inv;
+        double rowk[N];
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) rowk[j] = a[k*N + j];
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const double l = a[i*N + k]*inv;
+            a[i*N + k] = l;
+#pragma unroll
+            for (int j = k + 1; j < N; ++j) a[i*N + j] -= l*rowk[j];
+        }
+    }
+    return ok;
+}
+
+template <int N>
+PBR_DEV void pbr_lu_solve(const Strided& a, unsigned long long piv, double* b) {
+    // rows were swapped whole (multipliers included, LAPACK style): permute b first, then substitute
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const int pk = (int)((piv >> (4*k)) & 15ull);
+        const double bk_old = b[k];
+        double bk = bk_old;
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) if (j == pk) { bk = b[j]; b[j] = bk_old; }
+        b[k] = bk;
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) b[i] -= a[i*N + k]*b[k];
+    }
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+        double s = b[k];
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) s -= a[k*N + j]*b[j];
+        b[k] = s*a[k*N + k];
+    }
+}
+
+struct LuStore {            // receives Jacobian entries, stores the Newton matrix I - c*J
+    Strided a; double c;
+    PBR_DEV void operator()(int i, int k, double v) const { a[i*PBR_NV1 + k] = (i == k ? 1.0 : 0.0) - c*v; }
+};
+
+// =====================================================================================================
+// variable-order BDF / NDF (orders 1..5), quasi-constant step, following scipy/integrate/_ivp/bdf.py
+// =====================================================================================================
+#define PBR_MAXORD 5
+#define PBR_NEWTON_MAXITER 4
+#define PBR_MIN_FACTOR 0.2
+#define PBR_MAX_FACTOR 10.0
+#define PBR_DROWS (PBR_MAXORD + 3)
+
+enum { PBR_OK = 0, PBR_ERR_STEP_TOO_SMALL = 1, PBR_ERR_MAX_STEPS = 2, PBR_ERR_NONFINITE = 3, PBR_ERR_SINGULAR = 4 };
+
+// kappa = [0,-0.1850,-1/9,-0.0823,-0.0415,0]; gamma_k = sum_{j<=k} 1/j; alpha = (1-kappa)*gamma;
+// error_const = kappa*gamma + 1/(k+1)      (bdf.py:244-247)
+PBR_DEV double pbr_bdf_gamma(int k) {
+    switch (k) { case 1: return 1.0; case 2: return 1.5; case 3: return 1.0 + 0.5 + 1.0/3.0;
+                 case 4: return 1.0 + 0.5 + 1.0/3.0 + 0.25; case 5: return 1.0 + 0.5 + 1.0/3.0 + 0.25 + 0.2; default: return 0.0; }
+}
+PBR_DEV double pbr_bdf_kappa(int k) {
+    switch (k) { case 1: return -0.1850; case 2: return -1.0/9.0; case 3: return -0.0823; case 4: return -0.0415; default: return 0.0; }
+}
+PBR_DEV double pbr_bdf_alpha(int k) { return (1.0 - pbr_bdf_kappa(k))*pbr_bdf_gamma(k); }
+PBR_DEV double pbr_bdf_errc(int k) { return pbr_bdf_kappa(k)*pbr_bdf_gamma(k) + 1.0/(k + 1); }
+
+// D[:order+1] <- (R U)^T D[:order+1]  (bdf.py:18-33).  U is the signed Pascal matrix U[l][j] = (-1)^l C(j,l);
+// R[i][l] = prod_{m=1..i} (m-1-factor*l)/m, R[0][l] = 1, R[i>0][0] = 0.   D row r, state v at D[r*NV+v].
+template <int NV>
+PBR_DEV void pbr_change_D(const Strided& D, int order, double factor) {
+#pragma unroll 1
+    for (int v = 0; v < NV; ++v) {
+        double d[PBR_MAXORD + 1], E[PBR_MAXORD + 1];
+#pragma unroll
+        for (int i = 0; i <= PBR_MAXORD; ++i) d[i] = (i <= order) ? D[i*NV + v] : 0.0;
+        E[0] = d[0];
+#pragma unroll
+        for (int l = 1; l <= PBR_MAXORD; ++l) {
+            double r = 1.0, s = d[0];
+#pragma unroll
+            for (int i = 1; i <= PBR_MAXORD; ++i) {
+                r *= ((double)(i - 1) - factor*(double)l)/(double)i;
+                s += r*d[i];                      // d[i] = 0 beyond order
+            }
+            E[l] = s;
+        }
+        // D_new[j] = sum_{l<=j} (-1)^l C(j,l) E[l]
+        const double c2[3] = {1, -2, 1}, c3[4] = {1, -3, 3, -1}, c4[5] = {1, -4, 6, -4, 1}, c5[6] = {1, -5, 10, -10, 5, -1};
+        D[0*NV + v] = E[0];
+        if (order >= 1) D[1*NV + v] = E[0] - E[1];
+        if (order >= 2) D[2*NV + v] = c2[0]*E[0] + c2[1]*E[1] + c2[2]*E[2];
+        if (order >= 3) D[3*NV + v] = c3[0]*E[0] + c3[1]*E[1] + c3[2]*E[2] + c3[3]*E[3];
+        if (order >= 4) D[4*NV + v] = c4[0]*E[0] + c4[1]*E[1] + c4[2]*E[2] + c4[3]*E[3] + c4[4]*E[4];
+        if (order >= 5) D[5*NV + v] = c5[0]*E[0] + c5[1]*E[1] + c5[2]*E[2] + c5[3]*E[3] + c5[4]*E[4] + c5[5]*E[5];
+    }
+}
+
+PBR_DEV double pbr_ulp10(double t) {   // 10*|nextafter(t, inf) - t|  (bdf.py:319)
+    const double a = fabs(t);
+    return 10.0*(a < 2.2250738585072014e-308 ? 4.9406564584124654e-324 : (a*1.0000000000000002 - a));
+}
+
+struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
+
+// Sink for dense output: out(k, y[NV]) is called for every requested point index k (z_k = k/(n_out-1)).
+// Storage: work = Strided array of (PBR_DROWS*NV + NV*NV) doubles: D rows then the LU matrix.
+template <class Sink>
+PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double atol, int n_out, int max_steps,
+                         const Strided& work, Sink& out, N1Stats& stt) {
+    const int NV = PBR_NV1;
+    const Strided D = work;
+    const Strided LU = {work.base + (long)PBR_DROWS*NV*work.stride, work.stride};
+    const double t_bound = 1.0;                        // DoLe = 1, pbHomoReactor.py:2856
+    const double dz_out = 1.0/(double)(n_out - 1);     // np.linspace(0, 1, zNo+1), :2862
+    const double newton_tol = fmax(10.0*2.220446049250313e-16/rtol, fmin(0.03, sqrt(rtol)));   // bdf.py:217
+    NoStore nost;
+    double y[NV], f[NV], d[NV], scale[NV];
+    stt.nsteps = stt.nrej = stt.nfev = stt.nlu = stt.nfail = 0;
+
+    // ---- initial step, scipy common.py:68-140 (order 1)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) y[v] = y0[v];
+    pbr_n1_eval<false>(y, p, f, nost); stt.nfev++;
+    double h;
+    {
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            scale[v] = atol + fabs(y[v])*rtol;
+            d0 += (y[v]/scale[v])*(y[v]/scale[v]); d1 += (f[v]/scale[v])*(f[v]/scale[v]);
+        }
+        d0 = sqrt(d0/NV); d1 = sqrt(d1/NV);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
+        h0 = fmin(h0, t_bound);
+        double y1[NV], f1[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) y1[v] = y[v] + h0*f[v];
+        pbr_n1_eval<false>(y1, p, f1, nost); stt.nfev++;
+        double d2 = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) d2 += ((f1[v] - f[v])/scale[v])*((f1[v] - f[v])/scale[v]);
+        d2 = sqrt(d2/NV)/h0;
+        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0*1e-3) : sqrt(0.01/fmax(d1, d2));
+        h = fmin(fmin(100.0*h0, h1), t_bound);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        D[0*NV + v] = y[v]; D[1*NV + v] = f[v]*h;                   // bdf.py:249-252
+#pragma unroll
+        for (int r = 2; r < PBR_DROWS; ++r) D[r*NV + v] = 0.0;
+    }
+    out(0, y);
+    int next_out = 1;
+    int order = 1, n_equal = 0;
+    bool lu_ok = false;
+    unsigned long long piv = 0ull;
+    double t = 0.0;
+    int status = PBR_OK;
+
+    while (t < t_bound) {
+        if (stt.nsteps + stt.nrej + stt.nfail >= max_steps) { status = PBR_ERR_MAX_STEPS; break; }
+        const double min_step = pbr_ulp10(t);
+        if (h < min_step) { pbr_change_D<NV>(D, order, min_step/h); h = min_step; n_equal = 0; lu_ok = false; }
+        // ---------------- one step (with retries) ----------------
+        bool accepted = false;
+        double t_new = t, safety = 1.0, err_norm = 0.0;
+        int fail = 0;
+        while (!accepted) {
+            if (h < min_step) { fail = PBR_ERR_STEP_TOO_SMALL; break; }
+            t_new = t + h;
+            if (t_new > t_bound) {                                   // bdf.py:351-355
+                t_new = t_bound;
+                pbr_change_D<NV>(D, order, (t_new - t)/h);
+                n_equal = 0; lu_ok = false;
+            }
+            h = t_new - t;
+            const double alpha = pbr_bdf_alpha(order);
+            const double c = h/alpha;
+            double psi[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {                           // predictor + psi, bdf.py:360-363
+                double yp = D[v], ps = 0.0;
+                for (int r = 1; r <= order; ++r) { const double Dr = D[r*NV + v]; yp += Dr; ps += Dr*pbr_bdf_gamma(r); }
+                y[v] = yp; psi[v] = ps/alpha; d[v] = 0.0;
+                scale[v] = atol + rtol*fabs(yp);
+            }
+            bool fresh = false, converged = false;
+            int n_iter = 0;
+            for (int attempt = 0; attempt < 2 && !converged; ++attempt) {
+                if (attempt == 1) {                                   // stale LU failed: back to the predictor (bdf.py:375-379)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        double yp = D[v];
+                        for (int r = 1; r <= order; ++r) yp += D[r*NV + v];
+                        y[v] = yp; d[v] = 0.0;
+                    }
+                }
+                if (!lu_ok) {                                         // fresh analytic Jacobian with every factorisation
+                    LuStore st = {LU, c};
+                    double ftmp[NV];
+                    pbr_n1_eval<true>(y, p, ftmp, st);
+                    const bool okf = pbr_lu_factor<NV>(LU, piv);
+                    stt.nlu++;
+                    lu_ok = true; fresh = true;
+                    if (!okf) break;                                  // singular iteration matrix: treat as Newton failure
+                }
+                // ---- solve_bdf_system, bdf.py:36-68
+                double dy_norm_old = -1.0;
+                for (int k = 0; k < PBR_NEWTON_MAXITER; ++k) {
+                    n_iter = k + 1;
+                    pbr_n1_eval<false>(y, p, f, nost); stt.nfev++;
+                    double b[NV], nrm = 0.0;
+                    bool fin = true;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) { b[v] = c*f[v] - psi[v] - d[v]; fin = fin && (fabs(b[v]) < 1e300); }
+                    if (!fin) break;
+                    pbr_lu_solve<NV>(LU, piv, b);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) nrm += (b[v]/scale[v])*(b[v]/scale[v]);
+                    const double dy_norm = sqrt(nrm/NV);
+                    double rate = -1.0;
+                    if (dy_norm_old >= 0.0) rate = dy_norm/dy_norm_old;
+                    if (rate >= 0.0 && (rate >= 1.0 || pow(rate, (double)(PBR_NEWTON_MAXITER - k))/(1.0 - rate)*dy_norm > newton_tol)) break;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) { y[v] += b[v]; d[v] += b[v]; }
+                    if (dy_norm == 0.0 || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; break; }
+                    dy_norm_old = dy_norm;
+                }
+                if (!converged) {
+                    if (fresh) break;                                 // Jacobian was current: shrink the step
+                    lu_ok = false;                                    // stale factorisation: refresh J at the predictor, retry
+                }
+            }
+            if (fail) break;
+            if (!converged) {                                         // bdf.py:381-387
+                h *= 0.5; pbr_change_D<NV>(D, order, 0.5); n_equal = 0; lu_ok = false; stt.nfail++;
+                if (stt.nsteps + stt.nrej + stt.nfail >= max_steps) { fail = PBR_ERR_MAX_STEPS; break; }
+                continue;
+            }
+            safety = 0.9*(2*PBR_NEWTON_MAXITER + 1)/(double)(2*PBR_NEWTON_MAXITER + n_iter);
+            const double errc = pbr_bdf_errc(order);
+            double en = 0.0;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                scale[v] = atol + rtol*fabs(y[v]);
+                const double ev = errc*d[v]/scale[v]; en += ev*ev;
+            }
+            err_norm = sqrt(en/NV);
+            if (!(err_norm <= 1.0)) {                                 // also rejects NaN
+                if (!(err_norm == err_norm)) { fail = PBR_ERR_NONFINITE; break; }
+                const double factor = fmax(PBR_MIN_FACTOR, safety*pow(err_norm, -1.0/(order + 1)));
+                h *= factor; pbr_change_D<NV>(D, order, factor); n_equal = 0; lu_ok = false; stt.nrej++;
+                if (stt.nsteps + stt.nrej + stt.nfail >= max_steps) { fail = PBR_ERR_MAX_STEPS; break; }
+            } else accepted = true;
+        }
+        if (fail) { status = fail; break; }
+        // ---------------- accepted ----------------
+        n_equal++; stt.nsteps++;
+        t = t_new;
+        double em = 0.0, ep = 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {                                // bdf.py:416-421
+            const double Dk1 = D[(order + 1)*NV + v];
+            D[(order + 2)*NV + v] = d[v] - Dk1;
+            D[(order + 1)*NV + v] = d[v];
+            double acc = d[v];
+            for (int r = order; r >= 0; --r) { acc += D[r*NV + v]; D[r*NV + v] = acc; }
+            if (order > 1) { const double e1 = pbr_bdf_errc(order - 1)*D[order*NV + v]/scale[v]; em += e1*e1; }
+            if (order < PBR_MAXORD) { const double e2 = pbr_bdf_errc(order + 1)*(d[v] - Dk1)/scale[v]; ep += e2*e2; }
+        }
+        // ---------------- dense output on (t_old, t], BdfDenseOutput bdf.py:462-484 ----------------
+        while (next_out < n_out) {
+            const double te = (next_out == n_out - 1) ? 1.0 : next_out*dz_out;
+            if (te > t) break;
+            double yo[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) yo[v] = D[v];
+            double pr = 1.0;
+            for (int r = 1; r <= order; ++r) {
+                pr *= (te - (t - h*(r - 1)))/(h*r);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) yo[v] += D[r*NV + v]*pr;
+            }
+            out(next_out, yo);
+            next_out++;
+        }
+        if (n_equal < order + 1) continue;
+        // ---------------- order / step selection, bdf.py:426-455 ----------------
+        const double fm = (order > 1) ? pow(sqrt(em/NV), -1.0/order) : 0.0;
+        const double f0 = pow(err_norm, -1.0/(order + 1));          // err_norm == 0 -> inf, as in scipy
+        const double fp = (order < PBR_MAXORD) ? pow(sqrt(ep/NV), -1.0/(order + 2)) : 0.0;
+        double fmaxv = f0; int dord = 0;
+        if (fm > fmaxv) { fmaxv = fm; dord = -1; }
+        if (fp > fmaxv) { fmaxv = fp; dord = +1; }
+        order += dord;
+        const double factor = fmin(PBR_MAX_FACTOR, safety*fmaxv);
+        h *= factor; pbr_change_D<NV>(D, order, factor); n_equal = 0; lu_ok = false;
+    }
+    return status;
+}
+
+// =====================================================================================================
+// kernels
+// =====================================================================================================
+#ifndef PBR_HOST
+
+extern "C" __global__ void __launch_bounds__(128) pbr_k0_prolog(long N, const double* __restrict__ inst_in, double* __restrict__ inst_par) {
+    const long i = (long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < N) pbr_prolog_one(inst_in + i*PBR_KIN, inst_par, N, i);
+}
+
+// ---- standalone N1 RHS / Jacobian (tests, RHS-evals/s metric). y, f: [NV1][N] instance-minor; J: [NV1*NV1][N].
+extern "C" __global__ void __launch_bounds__(128) pbr_k_rhs_n1(long N, const double* __restrict__ par,
+                                                               const double* __restrict__ y, double* __restrict__ f) {
+    const long i = (long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    InstPar p; pbr_load_par(par, N, i, p);
+    double yy[PBR_NV1], ff[PBR_NV1];
+#pragma unroll
+    for (int v = 0; v < PBR_NV1; ++v) yy[v] = y[v*N + i];
+    NoStore ns;
+    pbr_n1_eval<false>(yy, p, ff, ns);
+#pragma unroll
+    for (int v = 0; v < PBR_NV1; ++v) f[v*N + i] = ff[v];
+}
+
+struct GlobalJacStore { double* J; long N, i; __device__ __forceinline__ void operator()(int r, int c, double v) const { J[(long)(r*PBR_NV1 + c)*N + i] = v; } };
+
+extern "C" __global__ void __launch_bounds__(128) pbr_k_jac_n1(long N, const double* __restrict__ par,
+                                                               const double* __restrict__ y, double* __restrict__ f, double* __restrict__ J) {
+    const long i = (long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    InstPar p; pbr_load_par(par, N, i, p);
+    double yy[PBR_NV1], ff[PBR_NV1];
+#pragma unroll
+    for (int v = 0; v < PBR_NV1; ++v) yy[v] = y[v*N + i];
+    GlobalJacStore st = {J, N, i};
+    pbr_n1_eval<true>(yy, p, ff, st);
+#pragma unroll
+    for (int v = 0; v < PBR_NV1; ++v) f[v*N + i] = ff[v];
+}
+
+// ---- K2: fused N1 solver, one thread per reactor instance; BDF history + LU in shared memory (strided per thread)
+#ifndef PBR_N1_BLOCK
+#define PBR_N1_BLOCK 32
+#endif
+#define PBR_N1_WORK (PBR_DROWS*PBR_NV1 + PBR_NV1*PBR_NV1)
+
+struct N1Sink {      // scaled state -> prof_y[k][v][N] (coalesced across the warp's instances)
+    double* prof; double* outlet; long N, i; int n_out;
+    __device__ __forceinline__ void operator()(int k, const double* y) const {
+        if (prof) {
+#pragma unroll
+            for (int v = 0; v < PBR_NV1; ++v) prof[((long)k*PBR_NV1 + v)*N + i] = y[v];
+        }
+        if (k == n_out - 1) {
+#pragma unroll
+            for (int v = 0; v < PBR_NV1; ++v) outlet[(long)v*N + i] = y[v];
+        }
+    }
+};
+
+extern "C" __global__ void __launch_bounds__(PBR_N1_BLOCK)
+pbr_k2_solve_n1(long N, const double* __restrict__ par, double rtol, double atol, int n_out, int max_steps,
+                double* __restrict__ prof_y, double* __restrict__ outlet_y, int* __restrict__ status, int* __restrict__ stats) {
+    extern __shared__ double pbr_smem[];
+    const long i = (long)blockIdx.x*PBR_N1_BLOCK + threadIdx.x;
+    if (i >= N) return;
+    InstPar p; pbr_load_par(par, N, i, p);
+    double y0[PBR_NV1];
+#pragma unroll
+    for (int k = 0; k < PBR_NC; ++k) y0[k] = p.c0[k];                 // IV, pbHomoReactor.py:2831-2842
+    y0[PBR_NC] = 1.0;
+    if (!PBR_ISO) y0[PBR_NC + (PBR_ISO ? 0 : 1)] = 0.0;
+    const Strided work = {pbr_smem + threadIdx.x, PBR_N1_BLOCK};
+    N1Sink sink = {prof_y, outlet_y, N, i, n_out};
+    N1Stats st;
+    const int rc = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, work, sink, st);
+    status[i] = rc;
+    if (stats) { stats[0*N + i] = st.nsteps; stats[1*N + i] = st.nrej + st.nfail; stats[2*N + i] = st.nfev; stats[3*N + i] = st.nlu; }
+}
+
+// ---- K5 epilog (N1): scaled y[K][NV1][N] -> reference layout dataYs[N][NV1][K] = [x_i ; P ; T]
+//      solvers/solResultAnalysis.py:191-249, pbHomoReactor.py:2973-2983.  One thread per (instance, point).
+extern "C" __global__ void __launch_bounds__(256) pbr_k5_unscale_n1(long N, int K, const double* __restrict__ par,
+                                                                    const double* __restrict__ y, double* __restrict__ out) {
+    const long g = (long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (g >= N*K) return;
+    const long i = g % N; const int k = (int)(g / N);
+    const double Cmax = par[PAR_CMAX*N + i], Pf = par[PAR_PF*N + i], Tf = par[PAR_TF*N + i];
+    double C[PBR_NC], Ct = 0.0;
+#pragma unroll
+    for (int v = 0; v < PBR_NC; ++v) { C[v] = y[((long)k*PBR_NV1 + v)*N + i]*Cmax; Ct += C[v]; }
+    double* o = out + (long)i*PBR_NV1*K + k;
+#pragma unroll
+    for (int v = 0; v < PBR_NC; ++v) o[(long)v*K] = C[v]/Ct;
+    o[(long)PBR_NC*K] = y[((long)k*PBR_NV1 + PBR_NC)*N + i]*Pf;
+    if (!PBR_ISO) { const double th = y[((long)k*PBR_NV1 + PBR_NC + (PBR_ISO ? 0 : 1))*N + i]; o[(long)(PBR_NC + 1)*K] = th*Tf + Tf; }
+}
+
+// ---- K3: fused N2 RHS. One warp per reactor instance, lanes over axial nodes.
+//      Y, dYdt: [N][NV2][zNo] (the reference's var-major flatten, :3873); consecutive lanes read consecutive nodes.
+//      The Ergun pressure recurrence P[z+1] = P[z] + slope(P[z], T_z, M_z)*dz is affine in P[z]:
+//      P[z+1] = a_z P[z] + b_z, a_z = 1 - dz*E2*vs0^2*M_z/(R T_z), b_z = -dz*E1*vs0  -> warp scan of affine maps.
+extern "C" __global__ void __launch_bounds__(128) pbr_k3_rhs_n2(long N, int zNo, const double* __restrict__ par,
+                                                                const double* __restrict__ Y, double* __restrict__ dY) {
+    const int lane = threadIdx.x & 31;
+    const long inst = ((long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    if (inst >= N) return;
+    InstPar p; pbr_load_par(par, N, inst, p);
+    const double dz = 1.0/(double)(zNo - 1);                          // :3439
+    const double inv_dz = (double)(zNo - 1);
+    const double* Yi = Y + inst*(long)PBR_NV2*zNo;
+    double* dYi = dY + inst*(long)PBR_NV2*zNo;
+    double Pcarry = p.Pf;                                             // P_z[0] = P0, :3848
+    double prev_last[PBR_NV2];                                        // state of the last node of the previous chunk
+#pragma unroll
+    for (int v = 0; v < PBR_NV2; ++v) prev_last[v] = 0.0;
+    NoStore ns;
+    for (int z0 = 0; z0 < zNo; z0 += 32) {
+        const int z = z0 + lane;
+        const bool act = z < zNo;
+        double yc[PBR_NV2], yb[PBR_NV2];
+#pragma unroll
+        for (int v = 0; v < PBR_NV2; ++v) yc[v] = act ? Yi[(long)v*zNo + z] : 1.0;
+        // affine map of this node
+        double a = 1.0, b = 0.0;
+        if (act) {
+            double Ct = 0.0, M = 0.0;
+#pragma unroll
+            for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yc[i], PBR_EPS)*p.Cmax; Ct += C; M += C*PBR_MW[i]; }
+            M = (M/Ct)*1e-3;
+            const double th = PBR_ISO ? 0.0 : yc[PBR_ISO ? 0 : PBR_NC];
+            const double T = th*p.Tf + p.Tf;
+            a = 1.0 - dz*p.E2*p.vs0*p.vs0*M/(PBR_R*T);
+            b = -dz*p.E1*p.vs0;
+        }
+        // inclusive scan of (a,b) under composition (a2,b2)o(a1,b1) = (a2 a1, a2 b1 + b2)
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double a1 = __shfl_up_sync(0xffffffffu, a, off);
+            const double b1 = __shfl_up_sync(0xffffffffu, b, off);
+            if (lane >= off) { b = a*b1 + b; a = a*a1; }
+        }
+        // exclusive: pressure AT node z = map of nodes z0..z-1 applied to Pcarry
+        double ae = __shfl_up_sync(0xffffffffu, a, 1), be = __shfl_up_sync(0xffffffffu, b, 1);
+        if (lane == 0) { ae = 1.0; be = 0.0; }
+        const double Pz = ae*Pcarry + be;
+        const double Pnext = __shfl_sync(0xffffffffu, a*Pcarry + b, 31);     // pressure entering the next chunk
+        // upstream neighbour
+#pragma unroll
+        for (int v = 0; v < PBR_NV2; ++v) {
+            const double up = __shfl_up_sync(0xffffffffu, yc[v], 1);
+            yb[v] = (lane == 0) ? prev_last[v] : up;
+            prev_last[v] = __shfl_sync(0xffffffffu, yc[v], 31);
+        }
+        if (act) {
+            double f[PBR_NV2];
+            pbr_n2_node<false>(yc, yb, z == 0, Pz, inv_dz, p, f, ns, (double*)0);
+#pragma unroll
+            for (int v = 0; v < PBR_NV2; ++v) dYi[(long)v*zNo + z] = f[v];
+        }
+        Pcarry = Pnext;
+    }
+}
+
+// ---- FP64 pipe peak probe: dependent-free DFMA streams (roofline denominator; no FP64 number in MEASURED_PEAKS.json)
+extern "C" __global__ void __launch_bounds__(256) pbr_k_dfma_peak(int iters, double* out) {
+    double a0 = threadIdx.x*1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000000001, c = 1e-12;
+    for (int k = 0; k < iters; ++k) {
+        a0 = a0*m + c; a1 = a1*m + c; a2 = a2*m + c; a3 = a3*m + c;
+        a4 = a4*m + c; a5 = a5*m + c; a6 = a6*m + c; a7 = a7*m + c;
+    }
+    out[(long)blockIdx.x*blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+#endif  // !PBR_HOST

@@ -1,0 +1,294 @@
+"""ctypes host layer over libpbr.so (include/pbr.h) — the only caller of the C ABI.
+
+``Model`` turns the static part of a PyREMOT ``modelInput`` (components, reactions, rate expressions,
+process type — what `PyREMOT/docs/rmtCore.py:63-183` prepares per call) into a compiled sm_100a module;
+its methods launch the kernels on torch-owned device memory.  There is NO CPU fallback: without the
+built library or without a CUDA device every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from . import components as DB
+from . import ratec
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpbr.so")
+CACHE_DIR = os.environ.get("PBR_CACHE_DIR", os.path.join(_HERE, "_cache"))
+
+ISO_THERMAL = "iso-thermal"   # `PyREMOT/docs/modelSetting.py:21-23`
+
+
+class PbrError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libpbr.so (built in-tree by ``python -m pyremot_b200.build`` / ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PbrError(f"{LIB_PATH} is missing: build it with `python -m pyremot_b200.build` "
+                       "(there is no CPU fallback for this path)")
+    L = C.CDLL(LIB_PATH)
+    vp, dp, ip, i, l, d = C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_double
+    sigs = {
+        "pbr_create": (vp, [i]),
+        "pbr_destroy": (None, [vp]),
+        "pbr_last_error": (C.c_char_p, [vp]),
+        "pbr_version": (C.c_char_p, []),
+        "pbr_set_species": (i, [vp, i, i, dp, dp, dp, dp, dp, dp, i]),
+        "pbr_load_rates": (i, [vp, C.c_char_p, i, C.c_char_p, C.POINTER(C.c_char_p)]),
+        "pbr_model_dims": (i, [vp] + [C.POINTER(i)]*7),
+        "pbr_model_source": (C.c_char_p, [vp]),
+        "pbr_model_cubin": (i, [vp, C.POINTER(vp), C.POINTER(C.c_ulong)]),
+        "pbr_kernel_attr": (i, [vp, C.c_char_p, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+        "pbr_prolog": (i, [vp, l, dp, dp, vp]),
+        "pbr_rhs_n1": (i, [vp, l, dp, dp, dp, vp]),
+        "pbr_jac_n1": (i, [vp, l, dp, dp, dp, dp, vp]),
+        "pbr_rhs_n2": (i, [vp, l, i, dp, dp, dp, vp]),
+        "pbr_solve_n1": (i, [vp, l, dp, d, d, i, i, dp, dp, ip, ip, vp]),
+        "pbr_unscale_n1": (i, [vp, l, i, dp, dp, dp, vp]),
+        "pbr_solve_n1_host": (i, [vp, l, dp, d, d, i, i, dp, dp, ip, ip]),
+        "pbr_fp64_peak": (i, [vp, i, C.POINTER(d)]),
+        "pbr_launch_count": (l, [vp]),
+    }
+    for name, (res, args) in sigs.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _lib = L
+    return L
+
+
+EXPORTS = ("pbr_create pbr_destroy pbr_last_error pbr_version pbr_set_species pbr_load_rates pbr_model_dims "
+           "pbr_model_source pbr_model_cubin pbr_kernel_attr pbr_prolog pbr_rhs_n1 pbr_jac_n1 pbr_rhs_n2 pbr_solve_n1 "
+           "pbr_unscale_n1 pbr_solve_n1_host pbr_fp64_peak pbr_launch_count").split()
+
+
+# ----------------------------------------------------------------------------- reaction parsing
+_TERM = re.compile(r"([0-9.]*)([a-zA-Z0-9.]+)")
+
+
+def parse_reactions(reactions, comps):
+    """Reaction strings -> (S [R][n], dH25 [R] J/mol, dcp [R][4]).
+
+    Same grammar as `PyREMOT/docs/rmtUtility.py:172-249` (regex per side, reactant coefficients
+    negative); species absent from ``comps`` drop out of S (`rmtReaction.py:64-97`) but still count in
+    dH25 (`rmtThermo.py:129-198`) and in the Cp sum of the dH(T) correction (`rmtThermo.py:258-312`).
+    """
+    S, dH25, dcp = [], [], []
+    for expr in reactions.values():
+        lhs, rhs = expr.replace("<", "").replace(">", "").replace(" ", "").split("=")
+        terms = [(s, -(float(c) if c else 1.0)) for c, s in _TERM.findall(lhs)]
+        terms += [(s, (float(c) if c else 1.0)) for c, s in _TERM.findall(rhs)]
+        row = [0.0]*len(comps)
+        h, poly = 0.0, [0.0]*4
+        for s, nu in terms:
+            if s in comps:
+                row[comps.index(s)] += nu
+            if s not in DB.COMPONENTS:
+                raise Exception("Component database is not up to date!")
+            h += nu*DB.dHf25(s)
+            for k in range(4):
+                poly[k] += nu*DB.cp_coef(s)[k]
+        S.append(row)
+        dH25.append(h*1000.0)
+        dcp.append(poly)
+    return np.array(S, dtype=np.float64), np.array(dH25, dtype=np.float64), np.array(dcp, dtype=np.float64)
+
+
+def _arr(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+class Model:
+    """Compiled model = (components, reactions, rate expressions, process type) bound to one CUDA device.
+
+    ``device=None`` -> compile-only (no GPU needed; used by the build check and CPU-side tests).
+    ``params``: names of scalar VARS entries that become per-instance runtime parameters.
+    """
+
+    def __init__(self, modelInput, params=(), device=0, cache_dir=CACHE_DIR):
+        L = lib()
+        comps = list(modelInput["feed"]["components"]["shell"])
+        for s in comps:
+            if s not in DB.componentSymbolList:          # `PyREMOT/rmt.py:55-57`
+                raise Exception("Component database is not up to date!")
+        self.comps = comps
+        self.n = len(comps)
+        self.iso = modelInput["operating-conditions"]["process-type"] == ISO_THERMAL
+        self.S, self.dH25, self.dcp = parse_reactions(modelInput["reactions"], comps)
+        self.rates = ratec.compile_rates(modelInput["reaction-rates"], self.n, params=params)
+        if self.rates.n_rxn != self.S.shape[0]:
+            raise PbrError(f"{self.S.shape[0]} reactions but {self.rates.n_rxn} rate expressions")
+        self.params = list(params)
+        self.device = device
+        self._ctx = L.pbr_create(-1 if device is None else int(device))
+        if not self._ctx:
+            raise PbrError(f"pbr_create({device}) failed: no usable CUDA device (this path has no CPU fallback)")
+        mw, p_mw = _arr([DB.MW(s) for s in comps])
+        cp, p_cp = _arr([DB.cp_coef(s) for s in comps])
+        vis, p_vis = _arr([DB.vis_coef(s) for s in comps])
+        s_, p_s = _arr(self.S)
+        dh, p_dh = _arr(self.dH25)
+        dc, p_dc = _arr(self.dcp)
+        self._check(L.pbr_set_species(self._ctx, self.n, self.S.shape[0], p_mw, p_cp, p_vis, p_s, p_dh, p_dc, int(self.iso)))
+        if cache_dir:
+            os.makedirs(cache_dir, exist_ok=True)
+        log = C.c_char_p()
+        self._check(L.pbr_load_rates(self._ctx, self.rates.cuda_source.encode(), len(self.params),
+                                     (cache_dir or "").encode(), C.byref(log)))
+        self.nvrtc_log = (log.value or b"").decode()
+        d = [C.c_int() for _ in range(7)]
+        self._check(L.pbr_model_dims(self._ctx, *[C.byref(x) for x in d]))
+        _, self.n_rxn, self.n_par, self.nv1, self.nv2, self.k_in, self.k_par = [x.value for x in d]
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise PbrError(f"libpbr error {rc}: {lib().pbr_last_error(self._ctx).decode()}")
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            lib().pbr_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def source(self):
+        return lib().pbr_model_source(self._ctx).decode()
+
+    @property
+    def launch_count(self):
+        return lib().pbr_launch_count(self._ctx)
+
+    def kernel_attr(self, name):
+        r, s, l = C.c_int(), C.c_int(), C.c_int()
+        self._check(lib().pbr_kernel_attr(self._ctx, name.encode(), C.byref(r), C.byref(s), C.byref(l)))
+        return {"regs": r.value, "static_smem": s.value, "local_bytes": l.value}
+
+    @staticmethod
+    def _stream():
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _dev(self):
+        import torch
+        return torch.device("cuda", self.device)
+
+    # -- per-instance input table (host)
+    def instance_table(self, modelInput, sweep=None, N=None):
+        """inst_in [N][k_in] (numpy, host): the numbers runN1/runN2 read from modelInput
+        (`pbHomoReactor.py:2716-2782`), per instance.  ``sweep``: {"T","P","VoFlRa","conc"[N,n],"ReInDi",
+        "ReLe","PaDi","BeVoFr","U","Tm","VARS:<name>"} -> per-instance arrays overriding the base value."""
+        sweep = dict(sweep or {})
+        if N is None:
+            N = len(next(iter(sweep.values()))) if sweep else 1
+        oc, fe, re_, eh = (modelInput["operating-conditions"], modelInput["feed"], modelInput["reactor"],
+                           modelInput["external-heat"])
+        t = np.empty((N, self.k_in), dtype=np.float64)
+        base = {"T": oc["temperature"], "P": oc["pressure"], "VoFlRa": fe["volumetric-flowrate"],
+                "ReInDi": re_["ReInDi"], "ReLe": re_["ReLe"], "PaDi": re_["PaDi"], "BeVoFr": re_["BeVoFr"],
+                "U": eh["OvHeTrCo"], "Tm": eh["MeTe"]}
+        for col, key in enumerate(("T", "P", "VoFlRa", "ReInDi", "ReLe", "PaDi", "BeVoFr", "U", "Tm")):
+            t[:, col] = sweep.pop(key, base[key])
+        t[:, 9:9 + self.n] = np.asarray(sweep.pop("conc", fe["concentration"]), dtype=np.float64)
+        for k, name in enumerate(self.params):
+            t[:, 9 + self.n + k] = sweep.pop("VARS:" + name, self.rates.param_defaults[k])
+        if sweep:
+            raise KeyError(f"unknown sweep keys {sorted(sweep)} (rate parameters must be listed in params=)")
+        return t
+
+    # -- kernels on torch tensors (float64, CUDA, contiguous)
+    def prolog(self, inst_in):
+        import torch
+        N = inst_in.shape[0]
+        assert inst_in.is_cuda and inst_in.dtype == torch.float64 and inst_in.is_contiguous() and inst_in.shape[1] == self.k_in
+        par = torch.empty((self.k_par, N), dtype=torch.float64, device=inst_in.device)
+        self._check(lib().pbr_prolog(self._ctx, N, inst_in.data_ptr(), par.data_ptr(), self._stream()))
+        return par
+
+    def rhs_n1(self, par, y):
+        import torch
+        N = par.shape[1]
+        assert y.shape == (self.nv1, N) and y.is_contiguous() and y.dtype == torch.float64
+        f = torch.empty_like(y)
+        self._check(lib().pbr_rhs_n1(self._ctx, N, par.data_ptr(), y.data_ptr(), f.data_ptr(), self._stream()))
+        return f
+
+    def jac_n1(self, par, y):
+        import torch
+        N = par.shape[1]
+        f = torch.empty_like(y)
+        J = torch.empty((self.nv1, self.nv1, N), dtype=torch.float64, device=y.device)
+        self._check(lib().pbr_jac_n1(self._ctx, N, par.data_ptr(), y.data_ptr(), f.data_ptr(), J.data_ptr(), self._stream()))
+        return f, J
+
+    def rhs_n2(self, par, Y, out=None):
+        import torch
+        N, nv, zNo = Y.shape
+        assert nv == self.nv2 and N == par.shape[1] and Y.is_contiguous() and Y.dtype == torch.float64
+        dY = torch.empty_like(Y) if out is None else out
+        self._check(lib().pbr_rhs_n2(self._ctx, N, zNo, par.data_ptr(), Y.data_ptr(), dY.data_ptr(), self._stream()))
+        return dY
+
+    def solve_n1(self, par, rtol=1e-8, atol=1e-12, n_out=101, profile=True, max_steps=0, stats=True):
+        """K2 on device tensors. Returns dict(prof_y [n_out,nv1,N] or None, outlet_y [nv1,N], status [N], stats [4,N])."""
+        import torch
+        N = par.shape[1]
+        dev = par.device
+        prof = torch.empty((n_out, self.nv1, N), dtype=torch.float64, device=dev) if profile else None
+        outlet = torch.empty((self.nv1, N), dtype=torch.float64, device=dev)
+        status = torch.empty((N,), dtype=torch.int32, device=dev)
+        st = torch.empty((4, N), dtype=torch.int32, device=dev) if stats else None
+        self._check(lib().pbr_solve_n1(self._ctx, N, par.data_ptr(), rtol, atol, n_out, max_steps,
+                                       prof.data_ptr() if profile else None, outlet.data_ptr(), status.data_ptr(),
+                                       st.data_ptr() if stats else None, self._stream()))
+        return {"prof_y": prof, "outlet_y": outlet, "status": status, "stats": st}
+
+    def unscale_n1(self, par, y):
+        """K5: scaled y [K,nv1,N] -> dataYs [N,nv1,K]."""
+        import torch
+        K, nv, N = y.shape
+        out = torch.empty((N, nv, K), dtype=torch.float64, device=y.device)
+        self._check(lib().pbr_unscale_n1(self._ctx, N, K, par.data_ptr(), y.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def solve_n1_host(self, inst_in, rtol=1e-8, atol=1e-12, n_out=101, profile=True, max_steps=0, out=None):
+        """Whole N1 path through the host-buffer C-ABI call (H2D, K0, K2, K5, D2H inside).
+
+        inst_in: numpy [N,k_in].  Returns dict(dataYs [N,nv1,n_out] or None, outlet [N,nv1], status [N], stats [4,N]).
+        ``out`` may carry preallocated (e.g. pinned) numpy buffers under the same keys."""
+        inst_in = np.ascontiguousarray(inst_in, dtype=np.float64)
+        N = inst_in.shape[0]
+        out = out or {}
+        prof = out.get("dataYs") if profile else None
+        if profile and prof is None:
+            prof = np.empty((N, self.nv1, n_out), dtype=np.float64)
+        outlet = out.get("outlet") if out.get("outlet") is not None else np.empty((N, self.nv1), dtype=np.float64)
+        status = out.get("status") if out.get("status") is not None else np.empty((N,), dtype=np.int32)
+        stats = out.get("stats") if out.get("stats") is not None else np.empty((4, N), dtype=np.int32)
+        self._check(lib().pbr_solve_n1_host(
+            self._ctx, N, inst_in.ctypes.data_as(C.c_void_p), rtol, atol, n_out, max_steps,
+            prof.ctypes.data_as(C.c_void_p) if profile else None, outlet.ctypes.data_as(C.c_void_p),
+            status.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p)))
+        return {"dataYs": prof, "outlet": outlet, "status": status, "stats": stats}
+
+    def fp64_peak(self, iters=8192):
+        t = C.c_double()
+        self._check(lib().pbr_fp64_peak(self._ctx, iters, C.byref(t)))
+        return t.value

@@ -1,0 +1,81 @@
+"""Scalar host emulation of the device code — TEST HARNESS ONLY (see hostsim_driver.cpp).
+
+Builds, with g++ -DPBR_HOST, the same program text libpbr gives NVRTC, so kernel numerics can be checked
+against the oracle without a GPU.  Never imported by the product package.
+"""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(tempfile.gettempdir(), "pbr_hostsim")
+
+
+class HostSim:
+    def __init__(self, model):
+        src = model.source
+        key = hashlib.sha256((src + open(os.path.join(_HERE, "hostsim_driver.cpp")).read()).encode()).hexdigest()[:16]
+        os.makedirs(_BUILD, exist_ok=True)
+        so = os.path.join(_BUILD, f"hs_{key}.so")
+        if not os.path.exists(so):
+            cu = os.path.join(_BUILD, f"hs_{key}.h")
+            with open(cu, "w") as f:
+                f.write(src)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off",
+                            f'-DPBR_MODEL_FILE="{cu}"', "-DPBR_N1_WORK_HOST=(PBR_DROWS*PBR_NV1+PBR_NV1*PBR_NV1)",
+                            os.path.join(_HERE, "hostsim_driver.cpp"), "-o", so + ".tmp"], check=True)
+            os.replace(so + ".tmp", so)
+        self.L = C.CDLL(so)
+        d = [C.c_int() for _ in range(4)]
+        self.L.hs_dims(*[C.byref(x) for x in d])
+        self.nv1, self.nv2, self.kin, self.kpar = [x.value for x in d]
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def prolog(self, inst_in):
+        inst_in = np.ascontiguousarray(inst_in, dtype=np.float64)
+        N = inst_in.shape[0]
+        par = np.zeros((self.kpar, N))
+        self.L.hs_prolog(C.c_long(N), self._p(inst_in), self._p(par))
+        return par
+
+    def rhs_n1(self, par, y):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        f = np.zeros_like(y)
+        self.L.hs_rhs_n1(C.c_long(par.shape[1]), self._p(par), self._p(y), self._p(f))
+        return f
+
+    def jac_n1(self, par, y):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        N = par.shape[1]
+        f = np.zeros_like(y)
+        J = np.zeros((self.nv1, self.nv1, N))
+        self.L.hs_jac_n1(C.c_long(N), self._p(par), self._p(y), self._p(f), self._p(J))
+        return f, J
+
+    def rhs_n2(self, par, Y, jac=False):
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        N, nv, zNo = Y.shape
+        dY = np.zeros_like(Y)
+        if jac:
+            Jd = np.zeros((N, zNo, nv, nv))
+            Js = np.zeros((N, zNo, nv))
+            self.L.hs_rhs_n2(C.c_long(N), C.c_int(zNo), self._p(par), self._p(Y), self._p(dY), self._p(Jd), self._p(Js))
+            return dY, Jd, Js
+        self.L.hs_rhs_n2(C.c_long(N), C.c_int(zNo), self._p(par), self._p(Y), self._p(dY), None, None)
+        return dY
+
+    def solve_n1(self, par, rtol=1e-8, atol=1e-12, n_out=101, max_steps=1000000):
+        N = par.shape[1]
+        prof = np.zeros((n_out, self.nv1, N))
+        status = np.zeros(N, dtype=np.int32)
+        stats = np.zeros((5, N), dtype=np.int32)
+        self.L.hs_solve_n1(C.c_long(N), self._p(par), C.c_double(rtol), C.c_double(atol), C.c_int(n_out),
+                           C.c_int(max_steps), self._p(prof), self._p(status), self._p(stats))
+        return prof, status, stats

@@ -1,0 +1,95 @@
+// hostsim_driver.cpp — TEST HARNESS ONLY (not part of the product, never loaded by pyremot_b200).
+// Compiles the exact device-code text that libpbr hands to NVRTC (pbr_model_source()) as plain C++
+// (-DPBR_HOST) and drives the per-thread functions in scalar loops, so the physics / Jacobians / BDF logic
+// can be checked against the oracle on the CPU-only build container before spending GPU time.
+// The model program is #included from the file named by -DPBR_MODEL_FILE.
+#define PBR_HOST 1
+#include PBR_MODEL_FILE
+#include <vector>
+
+extern "C" {
+
+void hs_dims(int* nv1, int* nv2, int* kin, int* kpar) { *nv1 = PBR_NV1; *nv2 = PBR_NV2; *kin = PBR_KIN; *kpar = PBR_KPAR; }
+
+void hs_prolog(long N, const double* in, double* par) { for (long i = 0; i < N; ++i) pbr_prolog_one(in + i*PBR_KIN, par, N, i); }
+
+void hs_rhs_n1(long N, const double* par, const double* y, double* f) {
+    NoStore ns;
+    for (long i = 0; i < N; ++i) {
+        InstPar p; pbr_load_par(par, N, i, p);
+        double yy[PBR_NV1], ff[PBR_NV1];
+        for (int v = 0; v < PBR_NV1; ++v) yy[v] = y[v*N + i];
+        pbr_n1_eval<false>(yy, p, ff, ns);
+        for (int v = 0; v < PBR_NV1; ++v) f[v*N + i] = ff[v];
+    }
+}
+
+struct JS { double* J; long N, i; void operator()(int r, int c, double v) const { J[(long)(r*PBR_NV1 + c)*N + i] = v; } };
+
+void hs_jac_n1(long N, const double* par, const double* y, double* f, double* J) {
+    for (long i = 0; i < N; ++i) {
+        InstPar p; pbr_load_par(par, N, i, p);
+        double yy[PBR_NV1], ff[PBR_NV1];
+        for (int v = 0; v < PBR_NV1; ++v) yy[v] = y[v*N + i];
+        JS st = {J, N, i};
+        pbr_n1_eval<true>(yy, p, ff, st);
+        for (int v = 0; v < PBR_NV1; ++v) f[v*N + i] = ff[v];
+    }
+}
+
+// Y, dY: [N][NV2][zNo]; sequential pressure march exactly as the reference loop (:3892-3979)
+struct JS2 { double* J; void operator()(int r, int c, double v) const { J[r*PBR_NV2 + c] = v; } };
+
+void hs_rhs_n2(long N, int zNo, const double* par, const double* Y, double* dY, double* Jd, double* Js) {
+    const double dz = 1.0/(zNo - 1), inv_dz = (double)(zNo - 1);
+    for (long i = 0; i < N; ++i) {
+        InstPar p; pbr_load_par(par, N, i, p);
+        double Pz = p.Pf;
+        for (int z = 0; z < zNo; ++z) {
+            double yc[PBR_NV2], yb[PBR_NV2], f[PBR_NV2], sub[PBR_NV2];
+            for (int v = 0; v < PBR_NV2; ++v) { yc[v] = Y[(i*PBR_NV2 + v)*zNo + z]; yb[v] = z ? Y[(i*PBR_NV2 + v)*zNo + z - 1] : 0.0; }
+            double slope;
+            if (Jd) {
+                JS2 st = {Jd + ((i*zNo + z)*PBR_NV2*PBR_NV2)};
+                slope = pbr_n2_node<true>(yc, yb, z == 0, Pz, inv_dz, p, f, st, sub);
+                for (int v = 0; v < PBR_NV2; ++v) Js[(i*zNo + z)*PBR_NV2 + v] = sub[v];
+            } else {
+                NoStore ns;
+                slope = pbr_n2_node<false>(yc, yb, z == 0, Pz, inv_dz, p, f, ns, (double*)0);
+            }
+            for (int v = 0; v < PBR_NV2; ++v) dY[(i*PBR_NV2 + v)*zNo + z] = f[v];
+            Pz = slope*dz + Pz;
+        }
+    }
+}
+
+struct Sink { double* prof; long N, i; int n_out; void operator()(int k, const double* y) const {
+    for (int v = 0; v < PBR_NV1; ++v) prof[((long)k*PBR_NV1 + v)*N + i] = y[v]; } };
+
+// prof: [n_out][NV1][N] scaled; stats [5][N]
+void hs_solve_n1(long N, const double* par, double rtol, double atol, int n_out, int max_steps, double* prof, int* status, int* stats) {
+    std::vector<double> work(PBR_N1_WORK_HOST);
+    for (long i = 0; i < N; ++i) {
+        InstPar p; pbr_load_par(par, N, i, p);
+        double y0[PBR_NV1];
+        for (int k = 0; k < PBR_NC; ++k) y0[k] = p.c0[k];
+        y0[PBR_NC] = 1.0;
+        if (!PBR_ISO) y0[PBR_NV1 - 1] = 0.0;
+        Strided w = {work.data(), 1};
+        Sink sk = {prof, N, i, n_out};
+        N1Stats st;
+        status[i] = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, w, sk, st);
+        stats[0*N + i] = st.nsteps; stats[1*N + i] = st.nrej; stats[2*N + i] = st.nfev; stats[3*N + i] = st.nlu; stats[4*N + i] = st.nfail;
+    }
+}
+
+void hs_lu_test(int n_unused, double* A /*NV1 x NV1 row-major, overwritten*/, double* b) {
+    Strided a = {A, 1};
+    unsigned long long piv;
+    pbr_lu_factor<PBR_NV1>(a, piv);
+    pbr_lu_solve<PBR_NV1>(a, piv, b);
+}
+
+void hs_change_D(double* D, int order, double factor) { Strided d = {D, 1}; pbr_change_D<PBR_NV1>(d, order, factor); }
+
+}

@@ -1,0 +1,202 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Everything goes through the C-ABI (libpbr.so).
+
+Tolerances: RHS / prolog values 1e-11 relative against reference-generated golden vectors (pow / T**3
+last-bit differences); solves 1e-6 relative (the bar BASELINE.json's north_star states) on mole fractions,
+P, T over the whole axial profile against the reference integrated at converged tolerances.
+"""
+import numpy as np
+import pytest
+
+from oracle import pbr_oracle as O
+from pyremot_b200 import cases
+
+pytestmark = pytest.mark.gpu
+
+RTOL_SOLVE = 1e-6      # north_star tolerance
+RTOL_RHS = 1e-11
+
+
+def relerr(a, b, floor=0.0):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b)/(np.abs(b) + floor)))
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    return torch
+
+
+def _model(mi, params=()):
+    from pyremot_b200.api import get_model
+    return get_model(mi, params=params, device=0)
+
+
+def _sweep24():
+    rows = cases.ensemble_rows(24)
+    return {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+
+
+def test_prolog_matches_oracle(torch_cuda):
+    torch = torch_cuda
+    mi = cases.readme_case("N1")
+    m = _model(mi)
+    sweep = _sweep24()
+    par = m.prolog(torch.from_numpy(m.instance_table(mi, sweep)).cuda()).cpu().numpy()
+    ens = O.Ensemble(mi, sweep)
+    eps, dp = ens.BeVoFr, ens.PaDi
+    ref = {0: ens.T0, 1: ens.P0, 2: ens.Cmax, 3: ens.Ct0, 4: ens.vs0, 5: eps, 6: ens.ReLe,
+           7: 150*ens.mu*((1-eps)**2)/(eps**3)/(dp**2), 8: 1.75*(1-eps)/(eps**3)/dp, 9: ens.rho0,
+           10: ens.Cpmix0, 11: ens.G, 12: ens.GH, 13: ens.U*ens.a, 14: ens.Tm, 15: ens.mu}
+    for row, v in ref.items():
+        assert relerr(par[row], v) < 1e-13, row
+    assert relerr(par[16:22].T, ens.c0) < 1e-15
+
+
+@pytest.mark.parametrize("tag,pt", [("noniso", "non-iso-thermal"), ("iso", "iso-thermal")])
+def test_rhs_n1_vs_reference_golden(torch_cuda, golden, tag, pt):
+    torch = torch_cuda
+    g = golden("n1_rhs")
+    Y, F = g[f"y_{tag}"], g[f"f_{tag}"]
+    mi = cases.readme_case("N1", pt)
+    m = _model(mi)
+    par = m.prolog(torch.from_numpy(m.instance_table(mi, N=len(Y))).cuda())
+    f = m.rhs_n1(par, torch.from_numpy(np.ascontiguousarray(Y.T)).cuda()).cpu().numpy().T
+    assert relerr(f, F, floor=1e-300) < RTOL_RHS
+    f2, J = m.jac_n1(par, torch.from_numpy(np.ascontiguousarray(Y.T)).cuda())
+    assert np.array_equal(f2.cpu().numpy().T, f)
+
+
+def test_rhs_n1_sweep_and_jacobian(torch_cuda, golden):
+    torch = torch_cuda
+    g = golden("n1_rhs")
+    mi = cases.readme_case("N1")
+    m = _model(mi)
+    sweep = _sweep24()
+    par = m.prolog(torch.from_numpy(m.instance_table(mi, sweep)).cuda())
+    ens = O.Ensemble(mi, sweep)
+    for k in range(2):
+        y = np.ascontiguousarray(g["y_sweep"][:, k].T)
+        f, J = m.jac_n1(par, torch.from_numpy(y).cuda())
+        assert relerr(f.cpu().numpy().T, g["f_sweep"][:, k], floor=1e-300) < RTOL_RHS
+        J = J.cpu().numpy()
+        if k == 1:   # analytic Jacobian against central differences of the oracle RHS
+            for i in (0, 7, 23):
+                e = ens.sub(i)
+                Jfd = O.fd_jacobian(lambda yy: e.rhs_n1(yy[None])[0], y[:, i], rel=1e-6)
+                colmax = np.max(np.abs(Jfd), axis=0, keepdims=True)
+                assert np.max(np.abs(J[:, :, i] - Jfd)/colmax) < 1e-5
+
+
+def test_rate_parameters_as_runtime_inputs(torch_cuda):
+    """Scalar VARS promoted to per-instance parameters (config 5 mechanism) give the same RHS as constants."""
+    torch = torch_cuda
+    mi = cases.readme_case("N1")
+    mi_p = cases.readme_case("N1", theta_as_vars=True)
+    m, mp = _model(mi), _model(mi_p, params=tuple(cases.MEOH_DME_THETA))
+    sweep = _sweep24()
+    y = torch.from_numpy(np.ascontiguousarray(O.Ensemble(mi, sweep).iv_n1().T)).cuda()
+    f0 = m.rhs_n1(m.prolog(torch.from_numpy(m.instance_table(mi, sweep)).cuda()), y).cpu().numpy()
+    fp = mp.rhs_n1(mp.prolog(torch.from_numpy(mp.instance_table(mi_p, sweep)).cuda()), y).cpu().numpy()
+    assert relerr(fp, f0, floor=1e-300) < 1e-13
+    sw2 = dict(sweep)
+    sw2["VARS:A_K1"] = np.full(24, 35.45*1.5)
+    f2 = mp.rhs_n1(mp.prolog(torch.from_numpy(mp.instance_table(mi_p, sw2)).cuda()), y).cpu().numpy()
+    e2 = O.Ensemble(mi_p, sw2)
+    assert relerr(f2.T, e2.rhs_n1(y.cpu().numpy().T), floor=1e-300) < RTOL_RHS
+    assert relerr(f2, f0, floor=1e-300) > 1e-3
+
+
+@pytest.mark.parametrize("tag,pt", [("noniso", "non-iso-thermal"), ("iso", "iso-thermal")])
+def test_rmtExe_n1_matches_converged_reference(torch_cuda, golden, tag, pt):
+    from pyremot_b200 import rmtExe
+    g = golden("n1_solve")
+    res = rmtExe(cases.readme_case("N1", pt))
+    d = res["resModel"][0]
+    assert set(d) == {"modelId", "processType", "successStatus", "computation-time", "dataShape", "labelList",
+                      "indexList", "dataTime", "dataXs", "dataYCons1", "dataYCons2", "dataYTemp1", "dataYTemp2", "dataYs"}
+    assert list(d["labelList"]) == list(g[f"{tag}_labelList"]) and list(d["indexList"]) == list(g[f"{tag}_indexList"])
+    assert tuple(d["dataShape"]) == tuple(g[f"{tag}_dataShape"]) and d["dataTime"] == [] and d["successStatus"] is True
+    for k in ("dataXs", "dataYCons1", "dataYCons2", "dataYTemp1", "dataYTemp2", "dataYs"):
+        ref = g[f"{tag}_conv_{k}"]
+        assert np.shape(d[k]) == ref.shape, k
+        assert relerr(d[k], ref, floor=1e-9 if k in ("dataXs", "dataYTemp1") else 0.0) < RTOL_SOLVE, k
+    # distance to what the reference returns at its own default tolerances (it runs solve_ivp at rtol 1e-3)
+    for ivp in ("default", "BDF", "Radau"):
+        assert relerr(d["dataYs"][:, -1], g[f"{tag}_{ivp}_dataYs"][:, -1]) < 2e-3
+    if tag == "noniso":   # SURVEY.md §8c converged outlet
+        assert np.allclose(d["dataYs"][:, -1], [0.4529955649935, 0.2615213300567, 0.02404559612944, 0.2384624972004,
+                                                0.006905891959625, 0.01606911966034, 4992662.119233, 620.8459970187],
+                           rtol=1e-7)
+
+
+def test_batch_sweep_matches_converged_reference(torch_cuda, golden):
+    """16 corners + 16 random rows of the config-2 box, full 101-point profiles, device and host-buffer paths."""
+    from pyremot_b200 import rmtExeBatch
+    gs = golden("n1_sweep")
+    mi = cases.readme_case("N1")
+    sweep = {"T": gs["T"], "P": gs["P"], "conc": gs["conc"], "Tm": gs["T"]}
+    out = rmtExeBatch(mi, sweep, profile=True)
+    assert (out["status"] == 0).all()
+    assert relerr(out["dataYs"], gs["dataYs"]) < RTOL_SOLVE
+    assert relerr(out["outlet"], gs["outlet"]) < RTOL_SOLVE
+    assert np.array_equal(out["outlet"], out["dataYs"][:, :, -1])
+    dev = rmtExeBatch(mi, sweep, profile=True, return_device=True)
+    assert np.array_equal(dev["dataYs"].cpu().numpy(), out["dataYs"])
+    assert np.array_equal(dev["outlet"].cpu().numpy(), out["outlet"])
+
+
+def test_error_behaviour(torch_cuda):
+    from pyremot_b200 import rmtExe
+    mi = cases.readme_case("N1")
+    mi["feed"]["components"]["shell"] = ["H2", "CO2", "H2O", "CO", "CH3OH", "XYZ"]
+    with pytest.raises(Exception, match="Component database is not up to date!"):
+        rmtExe(mi)
+    mi = cases.readme_case("N1")
+    del mi["feed"]["volumetric-flowrate"]
+    with pytest.raises(KeyError):
+        rmtExe(mi)
+    mi = cases.readme_case("N1")
+    mi["reaction-rates"]["VARS"] = {"K1": lambda x: x["nope"]*2.0, **mi["reaction-rates"]["VARS"]}
+    with pytest.raises(KeyError):       # forward reference, as in rmtReaction.py:44-51
+        rmtExe(mi)
+
+
+def test_full_size_ensemble_properties(torch_cuda):
+    """BASELINE config 2 at full size (65,536 reactors): size-independent invariants.
+
+    * every instance integrates (status 0);
+    * mole fractions sum to 1;
+    * element totals sum_i a_ik c_i are linear invariants of dc/dz = (..) S^T r (each reaction conserves C, H, O),
+      and BDF preserves linear invariants: C:H:O ratios of the outlet mixture equal the feed's;
+    * determinism: a second run is bit-identical; a sub-batch reproduces the same rows (no cross-instance coupling).
+    """
+    from pyremot_b200 import rmtExeBatch
+    N = 65536
+    rows = cases.ensemble_rows(N)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    mi = cases.readme_case("N1")
+    out = rmtExeBatch(mi, sweep)
+    assert (out["status"] == 0).all()
+    x = out["outlet"][:, :6]
+    assert np.max(np.abs(x.sum(axis=1) - 1)) < 1e-12
+    #           H2 CO2 H2O CO CH3OH DME
+    A = np.array([[0, 1, 0, 1, 1, 2],      # C
+                  [2, 0, 2, 0, 4, 6],      # H
+                  [0, 2, 1, 1, 1, 1]])     # O
+    x0 = rows["conc"]/rows["conc"].sum(axis=1, keepdims=True)
+    e0, e1 = x0 @ A.T, x @ A.T
+    assert relerr(e1[:, 1]/e1[:, 0], e0[:, 1]/e0[:, 0]) < 1e-9
+    assert relerr(e1[:, 2]/e1[:, 0], e0[:, 2]/e0[:, 0]) < 1e-9
+    T, P = out["outlet"][:, 7], out["outlet"][:, 6]
+    assert T.min() > 493 and T.max() < 700 and (P < rows["P"]).all() and (P > 0.99*rows["P"]).all()
+    out2 = rmtExeBatch(mi, sweep)
+    assert np.array_equal(out2["outlet"], out["outlet"])
+    sub = rmtExeBatch(mi, {k: v[1000:1100] for k, v in sweep.items()})
+    assert np.array_equal(sub["outlet"], out["outlet"][1000:1100])
+    # spot-check 3 instances against the oracle integrated by SciPy at converged tolerance
+    idx = [0, 31337, 65535]
+    ens = O.Ensemble(mi, {k: v[idx] for k, v in sweep.items()})
+    _, ref, _ = O.solve_n1(ens, method="BDF", rtol=1e-11, atol=1e-14)
+    assert relerr(out["outlet"][idx], ref[:, :, -1]) < RTOL_SOLVE
