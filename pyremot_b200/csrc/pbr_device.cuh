@@ -62,6 +62,15 @@ PBR_DEV void pbr_load_par(const double* __restrict__ par, long N, long i, InstPa
     for (int k = 0; k < PBR_NP; ++k) p.rp[k] = par[(PAR_RP + k)*N + i];
 }
 
+#ifdef PBR_HOST
+#define PBR_NOINLINE inline
+#else
+#define PBR_NOINLINE __device__ __noinline__
+#endif
+// pow() inlines to ~300 instructions per site; the integrator needs it at five rarely executed places
+// (step-size factors), so one out-of-line copy keeps the solver kernel inside the instruction cache.
+PBR_NOINLINE double pbr_pow(double x, double e) { return pow(x, e); }
+
 // ---- property polynomials
 PBR_DEV double pbr_poly(const double* c, double T) { return c[0] + T*(c[1] + T*(c[2] + T*c[3])); }
 PBR_DEV double pbr_dpoly(const double* c, double T) { return c[1] + T*(2.0*c[2] + T*3.0*c[3]); }
@@ -238,9 +247,12 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
         f[n + 1] = fth;
     }
     if (JAC) {
+        // reciprocals once: an FP64 divide costs ~12 instructions and the columns below would need ~40 of them
         const double cmct = p.Cmax*e.invCt;
+        const double iGH = 1.0/p.GH, iDen = 1.0/Den, irho = 1.0/e.rho, iCp = PBR_ISO ? 1.0 : 1.0/e.Cpmix, ipr = 1.0/pr;
         const double dfp_dw = -zP*(p.E1*p.vs0 + 2.0*p.E2*e.rho*p.vs0*p.vs0*w);
         const double dfp_drho = -zP*(p.E2*vs*vs);
+        const double rhoM = e.rho/e.M;
         double drk[PBR_NR], dri[PBR_NC];
         // ---- species columns
 #pragma unroll
@@ -248,7 +260,7 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
             pbr_dr_dc(e, p, k, 1.0, drk);
             pbr_dri(drk, dri);
             const double dw = w*cmct;
-            const double drho = (e.rho/e.M)*cmct*(1e-3*PBR_MW[k] - e.M);
+            const double drho = rhoM*cmct*(1e-3*PBR_MW[k] - e.M);
 #pragma unroll
             for (int i = 0; i < n; ++i) st(i, k, dri[i]*invGw - f[i]*cmct);
             st(n, k, dfp_dw*dw + dfp_drho*drho);
@@ -256,9 +268,9 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
                 double s = 0.0;
 #pragma unroll
                 for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j];
-                const double dNum = -s/p.GH;
-                const double dDen = Den*(drho/e.rho + cmct*(e.cpm[k] - e.Cpmix)/e.Cpmix + cmct);
-                st(n + 1, k, (dNum - fth*dDen)/Den);
+                const double dNum = -s*iGH;
+                const double dDen = Den*(drho*irho + cmct*(e.cpm[k] - e.Cpmix)*iCp + cmct);
+                st(n + 1, k, (dNum - fth*dDen)*iDen);
             }
         }
         // ---- pressure column
@@ -266,15 +278,15 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
 #pragma unroll
             for (int j = 0; j < PBR_NR; ++j) drk[j] = p.Pf*e.drP[j];
             pbr_dri(drk, dri);
-            const double dw = -w/pr, drho = e.rho/pr;
+            const double dw = -w*ipr, drho = e.rho*ipr;
 #pragma unroll
-            for (int i = 0; i < n; ++i) st(i, n, dri[i]*invGw + f[i]/pr);
+            for (int i = 0; i < n; ++i) st(i, n, dri[i]*invGw + f[i]*ipr);
             st(n, n, dfp_dw*dw + dfp_drho*drho);
             if (!PBR_ISO) {
                 double s = 0.0;
 #pragma unroll
                 for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j];
-                st(n + 1, n, (-s/p.GH)/Den);                           // d(rho*w)/dp = 0
+                st(n + 1, n, (-s*iGH)*iDen);                           // d(rho*w)/dp = 0
             }
         }
         // ---- temperature column
@@ -290,9 +302,9 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
 #pragma unroll
             for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j] + p.Tf*e.r[j]*e.dHdT[j];
             const double dQ = (p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
-            const double dNum = (-s + dQ)/p.GH;
-            const double dDen = Den*(drho/e.rho + p.Tf*e.dCpmixT/e.Cpmix);
-            st(n + 1, n + 1, (dNum - fth*dDen)/Den);
+            const double dNum = (-s + dQ)*iGH;
+            const double dDen = Den*(drho*irho + p.Tf*e.dCpmixT*iCp);
+            st(n + 1, n + 1, (dNum - fth*dDen)*iDen);
         }
     }
 }
@@ -335,6 +347,8 @@ PBR_DEV double pbr_n2_node(const double* yc, const double* yb, bool first, doubl
     }
     if (JAC) {
         double drk[PBR_NR], dri[PBR_NC];
+        const double iGH = 1.0/p.GH, iD2 = 1.0/D2, iM = 1.0/e.M, iCp = PBR_ISO ? 1.0 : 1.0/e.Cpmix;
+        const double hD2 = heat*iD2;
 #pragma unroll
         for (int k = 0; k < n; ++k) {
             const double mask = (yc[k] > PBR_EPS) ? 1.0 : 0.0;
@@ -347,10 +361,10 @@ PBR_DEV double pbr_n2_node(const double* yc, const double* yb, bool first, doubl
                 double s = 0.0;
 #pragma unroll
                 for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j];
-                const double dheat = -s/p.GH;
-                const double dD2 = D2*(cmct*(1e-3*PBR_MW[k] - e.M)/e.M + cmct*(e.cpm[k] - e.Cpmix)/e.Cpmix);
+                const double dheat = -s*iGH;
+                const double dD2 = D2*(cmct*(1e-3*PBR_MW[k] - e.M)*iM + cmct*(e.cpm[k] - e.Cpmix)*iCp);
                 // d(conv/D2)/dc = 0: conv/D2 = -(vs0/zf)(th-thb)/dz exactly
-                st(n, k, (dheat - (heat/D2)*dD2)/D2);
+                st(n, k, (dheat - hD2*dD2)*iD2);
             }
         }
         if (!PBR_ISO) {
@@ -363,9 +377,9 @@ PBR_DEV double pbr_n2_node(const double* yc, const double* yb, bool first, doubl
 #pragma unroll
             for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j] + p.Tf*e.r[j]*e.dHdT[j];
             const double dQ = (p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
-            const double dheat = (-s + dQ)/p.GH;
-            const double dD2 = D2*(-p.Tf/T + p.Tf*e.dCpmixT/e.Cpmix);
-            st(n, n, -(p.vs0/p.zf)*inv_dz + (dheat - (heat/D2)*dD2)/D2);
+            const double dheat = (-s + dQ)*iGH;
+            const double dD2 = D2*(-p.Tf/T + p.Tf*e.dCpmixT*iCp);
+            st(n, n, -(p.vs0/p.zf)*inv_dz + (dheat - hD2*dD2)*iD2);
         }
     }
     return slope;
@@ -381,15 +395,17 @@ struct Strided {            // element idx of this thread's private array lives 
 
 // In-place LU of the NxN row-major matrix a; unit-lower L below the diagonal, U on/above, diagonal stored INVERTED.
 // piv: 4 bits per column (N <= 16). Returns false if a pivot is exactly zero / non-finite.
+// Loops are kept rolled on purpose: the matrix lives in (dynamically indexable) shared memory and the solver
+// kernel is instruction-cache bound, so ~170 FMAs are not worth 1500 unrolled instructions.
 template <int N>
 PBR_DEV bool pbr_lu_factor(const Strided& a, unsigned long long& piv) {
     piv = 0ull;
     bool ok = true;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < N; ++k) {
         int pk = k;
         double amax = fabs(a[k*N + k]);
-#pragma unroll
+#pragma unroll 1
         for (int i = k + 1; i < N; ++i) {
             const double v = fabs(a[i*N + k]);
             if (v > amax) { amax = v; pk = i; }
@@ -402,15 +418,12 @@ PBR_DEV bool pbr_lu_factor(const Strided& a, unsigned long long& piv) {
         if (!(amax > 0.0) || !(amax < 1e300)) ok = false;
         const double inv = 1.0/a[k*N + k];
         a[k*N + k] = inv;
-        double rowk[N];
-#pragma unroll
-        for (int j = k + 1; j < N; ++j) rowk[j] = a[k*N + j];
-#pragma unroll
+#pragma unroll 1
         for (int i = k + 1; i < N; ++i) {
             const double l = a[i*N + k]*inv;
             a[i*N + k] = l;
-#pragma unroll
-            for (int j = k + 1; j < N; ++j) a[i*N + j] -= l*rowk[j];
+#pragma unroll 1
+            for (int j = k + 1; j < N; ++j) a[i*N + j] -= l*a[k*N + j];
         }
     }
     return ok;
@@ -459,21 +472,35 @@ struct LuStore {            // receives Jacobian entries, stores the Newton matr
 enum { PBR_OK = 0, PBR_ERR_STEP_TOO_SMALL = 1, PBR_ERR_MAX_STEPS = 2, PBR_ERR_NONFINITE = 3, PBR_ERR_SINGULAR = 4 };
 
 // kappa = [0,-0.1850,-1/9,-0.0823,-0.0415,0]; gamma_k = sum_{j<=k} 1/j; alpha = (1-kappa)*gamma;
-// error_const = kappa*gamma + 1/(k+1)      (bdf.py:244-247)
-PBR_DEV double pbr_bdf_gamma(int k) {
-    switch (k) { case 1: return 1.0; case 2: return 1.5; case 3: return 1.0 + 0.5 + 1.0/3.0;
-                 case 4: return 1.0 + 0.5 + 1.0/3.0 + 0.25; case 5: return 1.0 + 0.5 + 1.0/3.0 + 0.25 + 0.2; default: return 0.0; }
-}
-PBR_DEV double pbr_bdf_kappa(int k) {
-    switch (k) { case 1: return -0.1850; case 2: return -1.0/9.0; case 3: return -0.0823; case 4: return -0.0415; default: return 0.0; }
-}
-PBR_DEV double pbr_bdf_alpha(int k) { return (1.0 - pbr_bdf_kappa(k))*pbr_bdf_gamma(k); }
-PBR_DEV double pbr_bdf_errc(int k) { return pbr_bdf_kappa(k)*pbr_bdf_gamma(k) + 1.0/(k + 1); }
+// error_const = kappa*gamma + 1/(k+1)      (bdf.py:244-247).  Tables (constant bank), index = order 0..6.
+#define PBR_G1 1.0
+#define PBR_G2 1.5
+#define PBR_G3 (1.5 + 1.0/3.0)
+#define PBR_G4 (1.5 + 1.0/3.0 + 0.25)
+#define PBR_G5 (1.5 + 1.0/3.0 + 0.25 + 0.2)
+PBR_TABLE double PBR_GAMMA[7] = {0.0, PBR_G1, PBR_G2, PBR_G3, PBR_G4, PBR_G5, 0.0};
+PBR_TABLE double PBR_ALPHA[7] = {0.0, (1.0 + 0.1850)*PBR_G1, (1.0 + 1.0/9.0)*PBR_G2, (1.0 + 0.0823)*PBR_G3,
+                                 (1.0 + 0.0415)*PBR_G4, PBR_G5, 0.0};
+PBR_TABLE double PBR_ERRC[7] = {1.0, -0.1850*PBR_G1 + 1.0/2.0, (-1.0/9.0)*PBR_G2 + 1.0/3.0, -0.0823*PBR_G3 + 1.0/4.0,
+                                -0.0415*PBR_G4 + 1.0/5.0, 1.0/6.0, 1.0/7.0};
+PBR_DEV double pbr_bdf_gamma(int k) { return PBR_GAMMA[k]; }
+PBR_DEV double pbr_bdf_alpha(int k) { return PBR_ALPHA[k]; }
+PBR_DEV double pbr_bdf_errc(int k) { return PBR_ERRC[k]; }
 
 // D[:order+1] <- (R U)^T D[:order+1]  (bdf.py:18-33).  U is the signed Pascal matrix U[l][j] = (-1)^l C(j,l);
 // R[i][l] = prod_{m=1..i} (m-1-factor*l)/m, R[0][l] = 1, R[i>0][0] = 0.   D row r, state v at D[r*NV+v].
 template <int NV>
 PBR_DEV void pbr_change_D(const Strided& D, int order, double factor) {
+    double R[PBR_MAXORD + 1][PBR_MAXORD + 1];       // R[i][l], i,l = 1..5 used
+#pragma unroll
+    for (int l = 1; l <= PBR_MAXORD; ++l) {
+        double r = 1.0;
+#pragma unroll
+        for (int i = 1; i <= PBR_MAXORD; ++i) {
+            r *= ((double)(i - 1) - factor*(double)l)*(1.0/(double)i);
+            R[i][l] = (i <= order) ? r : 0.0;
+        }
+    }
 #pragma unroll 1
     for (int v = 0; v < NV; ++v) {
         double d[PBR_MAXORD + 1], E[PBR_MAXORD + 1];
@@ -482,23 +509,23 @@ PBR_DEV void pbr_change_D(const Strided& D, int order, double factor) {
         E[0] = d[0];
 #pragma unroll
         for (int l = 1; l <= PBR_MAXORD; ++l) {
-            double r = 1.0, s = d[0];
+            double s = d[0];
 #pragma unroll
-            for (int i = 1; i <= PBR_MAXORD; ++i) {
-                r *= ((double)(i - 1) - factor*(double)l)/(double)i;
-                s += r*d[i];                      // d[i] = 0 beyond order
-            }
+            for (int i = 1; i <= PBR_MAXORD; ++i) s += R[i][l]*d[i];
             E[l] = s;
         }
         // D_new[j] = sum_{l<=j} (-1)^l C(j,l) E[l]
-        const double c2[3] = {1, -2, 1}, c3[4] = {1, -3, 3, -1}, c4[5] = {1, -4, 6, -4, 1}, c5[6] = {1, -5, 10, -10, 5, -1};
-        D[0*NV + v] = E[0];
         if (order >= 1) D[1*NV + v] = E[0] - E[1];
-        if (order >= 2) D[2*NV + v] = c2[0]*E[0] + c2[1]*E[1] + c2[2]*E[2];
-        if (order >= 3) D[3*NV + v] = c3[0]*E[0] + c3[1]*E[1] + c3[2]*E[2] + c3[3]*E[3];
-        if (order >= 4) D[4*NV + v] = c4[0]*E[0] + c4[1]*E[1] + c4[2]*E[2] + c4[3]*E[3] + c4[4]*E[4];
-        if (order >= 5) D[5*NV + v] = c5[0]*E[0] + c5[1]*E[1] + c5[2]*E[2] + c5[3]*E[3] + c5[4]*E[4] + c5[5]*E[5];
+        if (order >= 2) D[2*NV + v] = E[0] - 2.0*E[1] + E[2];
+        if (order >= 3) D[3*NV + v] = E[0] - 3.0*E[1] + 3.0*E[2] - E[3];
+        if (order >= 4) D[4*NV + v] = E[0] - 4.0*E[1] + 6.0*E[2] - 4.0*E[3] + E[4];
+        if (order >= 5) D[5*NV + v] = E[0] - 5.0*E[1] + 10.0*E[2] - 10.0*E[3] + 5.0*E[4] - E[5];
     }
+}
+
+PBR_DEV double pbr_ipow(double x, int e) {     // x^e, e = 1..4
+    const double x2 = x*x;
+    return e == 1 ? x : (e == 2 ? x2 : (e == 3 ? x2*x : x2*x2));
 }
 
 PBR_DEV double pbr_ulp10(double t) {   // 10*|nextafter(t, inf) - t|  (bdf.py:319)
@@ -510,6 +537,21 @@ struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
 
 // Sink for dense output: out(k, y[NV]) is called for every requested point index k (z_k = k/(n_out-1)).
 // Storage: work = Strided array of (PBR_DROWS*NV + NV*NV) doubles: D rows then the LU matrix.
+//
+// Control flow is FLAT: one trip of the main loop = one step attempt, and every trip runs the same sequence
+//   [even trips: rescale history, Jacobian + LU at the predictor] -> predictor -> <=4 Newton iterations ->
+//   error test -> [accept: history update, dense output; odd trips: order/step selection]
+// with per-lane predicates only (no break/continue), so the 32 reactors of a warp stay converged although each
+// has its own step size, order and acceptance history.  The trip counter is the same for every lane, which is
+// what makes the schedule warp-uniform.  Differences from scipy's BDF driver, all forced by that layout:
+// (i) the Jacobian is analytic and is refreshed together with the LU factorisation on every EVEN trip for all
+// lanes (scipy keeps J/LU until Newton fails or h changes: bdf.py:365-379); (ii) step-size / order changes are
+// decided at the end of odd trips and applied lazily at the top of the next (even) trip, fused with the clip to
+// the end point (change_D composes: rescaling by f1 then f2 == rescaling by f1*f2); a lane whose attempt failed
+// on an even trip sits out the following odd trip.
+#ifndef PBR_JAC_PERIOD
+#define PBR_JAC_PERIOD 1
+#endif
 template <class Sink>
 PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double atol, int n_out, int max_steps,
                          const Strided& work, Sink& out, N1Stats& stt) {
@@ -520,130 +562,123 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
     const double dz_out = 1.0/(double)(n_out - 1);     // np.linspace(0, 1, zNo+1), :2862
     const double newton_tol = fmax(10.0*2.220446049250313e-16/rtol, fmin(0.03, sqrt(rtol)));   // bdf.py:217
     NoStore nost;
-    double y[NV], f[NV], d[NV], scale[NV];
+    double y[NV], f[NV], d[NV], scale[NV], psi[NV];
     stt.nsteps = stt.nrej = stt.nfev = stt.nlu = stt.nfail = 0;
 
-    // ---- initial step, scipy common.py:68-140 (order 1)
-#pragma unroll
-    for (int v = 0; v < NV; ++v) y[v] = y0[v];
-    pbr_n1_eval<false>(y, p, f, nost); stt.nfev++;
-    double h;
+    // ---- initial step, scipy common.py:68-140 (order 1): f0 = f(y0), f1 = f(y0 + h0 f0); one evaluation site
+    double h = 0.0;
     {
-        double d0 = 0.0, d1 = 0.0;
+        double h0 = 0.0, d1 = 0.0;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            scale[v] = atol + fabs(y[v])*rtol;
-            d0 += (y[v]/scale[v])*(y[v]/scale[v]); d1 += (f[v]/scale[v])*(f[v]/scale[v]);
+        for (int v = 0; v < NV; ++v) { y[v] = y0[v]; scale[v] = atol + fabs(y0[v])*rtol; }
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            pbr_n1_eval<false>(y, p, f, nost); stt.nfev++;
+            if (s == 0) {
+                double d0 = 0.0;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) { d0 += (y[v]/scale[v])*(y[v]/scale[v]); d1 += (f[v]/scale[v])*(f[v]/scale[v]); }
+                d0 = sqrt(d0/NV); d1 = sqrt(d1/NV);
+                h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
+                h0 = fmin(h0, t_bound);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) { D[0*NV + v] = y[v]; D[1*NV + v] = f[v]; y[v] = y[v] + h0*f[v]; }
+            } else {
+                double d2 = 0.0;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) { const double df = f[v] - D[1*NV + v]; d2 += (df/scale[v])*(df/scale[v]); }
+                d2 = sqrt(d2/NV)/h0;
+                const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0*1e-3) : sqrt(0.01/fmax(d1, d2));
+                h = fmin(fmin(100.0*h0, h1), t_bound);
+            }
         }
-        d0 = sqrt(d0/NV); d1 = sqrt(d1/NV);
-        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
-        h0 = fmin(h0, t_bound);
-        double y1[NV], f1[NV];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) y1[v] = y[v] + h0*f[v];
-        pbr_n1_eval<false>(y1, p, f1, nost); stt.nfev++;
-        double d2 = 0.0;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) d2 += ((f1[v] - f[v])/scale[v])*((f1[v] - f[v])/scale[v]);
-        d2 = sqrt(d2/NV)/h0;
-        const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0*1e-3) : sqrt(0.01/fmax(d1, d2));
-        h = fmin(fmin(100.0*h0, h1), t_bound);
     }
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-        D[0*NV + v] = y[v]; D[1*NV + v] = f[v]*h;                   // bdf.py:249-252
+        D[1*NV + v] = D[1*NV + v]*h;                                 // bdf.py:249-252  D[0] = y0, D[1] = h f0
 #pragma unroll
         for (int r = 2; r < PBR_DROWS; ++r) D[r*NV + v] = 0.0;
+        y[v] = D[v];
     }
     out(0, y);
     int next_out = 1;
-    int order = 1, n_equal = 0;
-    bool lu_ok = false;
+    int order = 1, n_equal = 0, trip = 0;
     unsigned long long piv = 0ull;
-    double t = 0.0;
+    double t = 0.0, pend = 1.0;                         // pend: step-size factor decided by earlier attempts
     int status = PBR_OK;
+    bool active = true;
 
-    while (t < t_bound) {
-        if (stt.nsteps + stt.nrej + stt.nfail >= max_steps) { status = PBR_ERR_MAX_STEPS; break; }
-        const double min_step = pbr_ulp10(t);
-        if (h < min_step) { pbr_change_D<NV>(D, order, min_step/h); h = min_step; n_equal = 0; lu_ok = false; }
-        // ---------------- one step (with retries) ----------------
-        bool accepted = false;
-        double t_new = t, safety = 1.0, err_norm = 0.0;
-        int fail = 0;
-        while (!accepted) {
-            if (h < min_step) { fail = PBR_ERR_STEP_TOO_SMALL; break; }
-            t_new = t + h;
-            if (t_new > t_bound) {                                   // bdf.py:351-355
-                t_new = t_bound;
-                pbr_change_D<NV>(D, order, (t_new - t)/h);
-                n_equal = 0; lu_ok = false;
+    while (active) {
+        const bool refresh = (trip % PBR_JAC_PERIOD) == 0;            // warp-uniform: every lane has the same trip count
+        // ---------------- 1. step size for this attempt; lazy history rescale (refresh trips only) ----------------
+        bool sit_out = false;
+        double t_new;
+        {
+            double hn = h*pend;
+            const bool clip = (t + hn > t_bound);                     // bdf.py:351-355
+            if (clip) hn = t_bound - t;
+            const double fac = hn/h;
+            if (fac != 1.0) {
+                if (refresh) { pbr_change_D<NV>(D, order, fac); n_equal = 0; h = hn; pend = 1.0; }
+                else sit_out = true;                                  // wait for the next refresh trip
             }
-            h = t_new - t;
-            const double alpha = pbr_bdf_alpha(order);
-            const double c = h/alpha;
-            double psi[NV];
+            t_new = clip ? t_bound : t + h;
+        }
+        trip++;
+        if (h < pbr_ulp10(t)) { status = PBR_ERR_STEP_TOO_SMALL; active = false; }
+        if (trip > max_steps) { status = PBR_ERR_MAX_STEPS; active = false; }
+        // ---------------- 2. predictor + psi, bdf.py:360-363 ----------------
+        const double alpha = pbr_bdf_alpha(order);
+        const double c = h/alpha;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {                           // predictor + psi, bdf.py:360-363
-                double yp = D[v], ps = 0.0;
-                for (int r = 1; r <= order; ++r) { const double Dr = D[r*NV + v]; yp += Dr; ps += Dr*pbr_bdf_gamma(r); }
-                y[v] = yp; psi[v] = ps/alpha; d[v] = 0.0;
-                scale[v] = atol + rtol*fabs(yp);
-            }
-            bool fresh = false, converged = false;
-            int n_iter = 0;
-            for (int attempt = 0; attempt < 2 && !converged; ++attempt) {
-                if (attempt == 1) {                                   // stale LU failed: back to the predictor (bdf.py:375-379)
+        for (int v = 0; v < NV; ++v) {
+            double yp = D[v], ps = 0.0;
+            for (int r = 1; r <= PBR_MAXORD; ++r) if (r <= order) { const double Dr = D[r*NV + v]; yp += Dr; ps += Dr*pbr_bdf_gamma(r); }
+            y[v] = yp; psi[v] = ps/alpha; d[v] = 0.0;
+            scale[v] = atol + rtol*fabs(yp);
+        }
+        // ---------------- 3. refresh trips: Jacobian + LU of I - cJ at the predictor (also yields f(y_pred)) ----------------
+        bool lu_good = true;
+        if (refresh) {
+            LuStore st = {LU, c};
+            pbr_n1_eval<true>(y, p, f, st);
+            lu_good = pbr_lu_factor<NV>(LU, piv);
+            stt.nlu++; stt.nfev++;
+        }
+        // ---------------- 4. Newton, solve_bdf_system bdf.py:36-68 ----------------
+        bool converged = false, running = active && lu_good && !sit_out;
+        const bool tried = running;
+        double dy_norm_old = -1.0;
+        int n_iter = 0;
+#pragma unroll 1
+        for (int k = 0; k < PBR_NEWTON_MAXITER; ++k) {
+            if (running) {
+                n_iter = k + 1;
+                if (k > 0 || !refresh) { pbr_n1_eval<false>(y, p, f, nost); stt.nfev++; }
+                double b[NV], nrm = 0.0;
+                bool fin = true;
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        double yp = D[v];
-                        for (int r = 1; r <= order; ++r) yp += D[r*NV + v];
-                        y[v] = yp; d[v] = 0.0;
-                    }
-                }
-                if (!lu_ok) {                                         // fresh analytic Jacobian with every factorisation
-                    LuStore st = {LU, c};
-                    double ftmp[NV];
-                    pbr_n1_eval<true>(y, p, ftmp, st);
-                    const bool okf = pbr_lu_factor<NV>(LU, piv);
-                    stt.nlu++;
-                    lu_ok = true; fresh = true;
-                    if (!okf) break;                                  // singular iteration matrix: treat as Newton failure
-                }
-                // ---- solve_bdf_system, bdf.py:36-68
-                double dy_norm_old = -1.0;
-                for (int k = 0; k < PBR_NEWTON_MAXITER; ++k) {
-                    n_iter = k + 1;
-                    pbr_n1_eval<false>(y, p, f, nost); stt.nfev++;
-                    double b[NV], nrm = 0.0;
-                    bool fin = true;
+                for (int v = 0; v < NV; ++v) { b[v] = c*f[v] - psi[v] - d[v]; fin = fin && (fabs(b[v]) < 1e300); }
+                pbr_lu_solve<NV>(LU, piv, b);
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) { b[v] = c*f[v] - psi[v] - d[v]; fin = fin && (fabs(b[v]) < 1e300); }
-                    if (!fin) break;
-                    pbr_lu_solve<NV>(LU, piv, b);
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) nrm += (b[v]/scale[v])*(b[v]/scale[v]);
-                    const double dy_norm = sqrt(nrm/NV);
-                    double rate = -1.0;
-                    if (dy_norm_old >= 0.0) rate = dy_norm/dy_norm_old;
-                    if (rate >= 0.0 && (rate >= 1.0 || pow(rate, (double)(PBR_NEWTON_MAXITER - k))/(1.0 - rate)*dy_norm > newton_tol)) break;
+                for (int v = 0; v < NV; ++v) nrm += (b[v]/scale[v])*(b[v]/scale[v]);
+                const double dy_norm = sqrt(nrm/NV);
+                const double rate = (dy_norm_old >= 0.0) ? dy_norm/dy_norm_old : -1.0;
+                const bool diverge = !fin || !(dy_norm == dy_norm) ||
+                    (rate >= 0.0 && (rate >= 1.0 || pbr_ipow(rate, PBR_NEWTON_MAXITER - k)/(1.0 - rate)*dy_norm > newton_tol));
+                if (diverge) running = false;
+                else {
 #pragma unroll
                     for (int v = 0; v < NV; ++v) { y[v] += b[v]; d[v] += b[v]; }
-                    if (dy_norm == 0.0 || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; break; }
+                    if (dy_norm == 0.0 || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; running = false; }
                     dy_norm_old = dy_norm;
                 }
-                if (!converged) {
-                    if (fresh) break;                                 // Jacobian was current: shrink the step
-                    lu_ok = false;                                    // stale factorisation: refresh J at the predictor, retry
-                }
             }
-            if (fail) break;
-            if (!converged) {                                         // bdf.py:381-387
-                h *= 0.5; pbr_change_D<NV>(D, order, 0.5); n_equal = 0; lu_ok = false; stt.nfail++;
-                if (stt.nsteps + stt.nrej + stt.nfail >= max_steps) { fail = PBR_ERR_MAX_STEPS; break; }
-                continue;
-            }
-            safety = 0.9*(2*PBR_NEWTON_MAXITER + 1)/(double)(2*PBR_NEWTON_MAXITER + n_iter);
+        }
+        // ---------------- 5. error test, bdf.py:381-404 ----------------
+        const double safety = 0.9*(2*PBR_NEWTON_MAXITER + 1)/(double)(2*PBR_NEWTON_MAXITER + n_iter);
+        double err_norm = 0.0;
+        {
             const double errc = pbr_bdf_errc(order);
             double en = 0.0;
 #pragma unroll
@@ -652,55 +687,57 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
                 const double ev = errc*d[v]/scale[v]; en += ev*ev;
             }
             err_norm = sqrt(en/NV);
-            if (!(err_norm <= 1.0)) {                                 // also rejects NaN
-                if (!(err_norm == err_norm)) { fail = PBR_ERR_NONFINITE; break; }
-                const double factor = fmax(PBR_MIN_FACTOR, safety*pow(err_norm, -1.0/(order + 1)));
-                h *= factor; pbr_change_D<NV>(D, order, factor); n_equal = 0; lu_ok = false; stt.nrej++;
-                if (stt.nsteps + stt.nrej + stt.nfail >= max_steps) { fail = PBR_ERR_MAX_STEPS; break; }
-            } else accepted = true;
         }
-        if (fail) { status = fail; break; }
-        // ---------------- accepted ----------------
-        n_equal++; stt.nsteps++;
-        t = t_new;
-        double em = 0.0, ep = 0.0;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {                                // bdf.py:416-421
-            const double Dk1 = D[(order + 1)*NV + v];
-            D[(order + 2)*NV + v] = d[v] - Dk1;
-            D[(order + 1)*NV + v] = d[v];
-            double acc = d[v];
-            for (int r = order; r >= 0; --r) { acc += D[r*NV + v]; D[r*NV + v] = acc; }
-            if (order > 1) { const double e1 = pbr_bdf_errc(order - 1)*D[order*NV + v]/scale[v]; em += e1*e1; }
-            if (order < PBR_MAXORD) { const double e2 = pbr_bdf_errc(order + 1)*(d[v] - Dk1)/scale[v]; ep += e2*e2; }
+        const bool accepted = tried && converged && (err_norm <= 1.0);
+        if ((tried && !converged) || (active && !lu_good)) { pend = 0.5; stt.nfail++; }   // Newton failed (or singular matrix)
+        if (tried && converged && !accepted) {                                    // also catches NaN
+            pend = (err_norm == err_norm) ? fmax(PBR_MIN_FACTOR, safety*pbr_pow(err_norm, -1.0/(order + 1))) : 0.5;
+            stt.nrej++;
         }
-        // ---------------- dense output on (t_old, t], BdfDenseOutput bdf.py:462-484 ----------------
-        while (next_out < n_out) {
-            const double te = (next_out == n_out - 1) ? 1.0 : next_out*dz_out;
-            if (te > t) break;
-            double yo[NV];
+        // ---------------- 6. accepted: history update, dense output, order / step selection ----------------
+        if (accepted) {
+            n_equal++; stt.nsteps++;
+            t = t_new;
+            double em = 0.0, ep = 0.0;
 #pragma unroll
-            for (int v = 0; v < NV; ++v) yo[v] = D[v];
-            double pr = 1.0;
-            for (int r = 1; r <= order; ++r) {
-                pr *= (te - (t - h*(r - 1)))/(h*r);
-#pragma unroll
-                for (int v = 0; v < NV; ++v) yo[v] += D[r*NV + v]*pr;
+            for (int v = 0; v < NV; ++v) {                                // bdf.py:416-421
+                const double Dk1 = D[(order + 1)*NV + v];
+                D[(order + 2)*NV + v] = d[v] - Dk1;
+                D[(order + 1)*NV + v] = d[v];
+                double acc = d[v];
+                for (int r = PBR_MAXORD; r >= 0; --r) if (r <= order) { acc += D[r*NV + v]; D[r*NV + v] = acc; }
+                if (order > 1) { const double e1 = pbr_bdf_errc(order - 1)*D[order*NV + v]/scale[v]; em += e1*e1; }
+                if (order < PBR_MAXORD) { const double e2 = pbr_bdf_errc(order + 1)*(d[v] - Dk1)/scale[v]; ep += e2*e2; }
             }
-            out(next_out, yo);
-            next_out++;
+            // dense output on (t_old, t], BdfDenseOutput bdf.py:462-484
+            while (next_out < n_out && ((next_out == n_out - 1) ? 1.0 : next_out*dz_out) <= t) {
+                const double te = (next_out == n_out - 1) ? 1.0 : next_out*dz_out;
+                double yo[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) yo[v] = D[v];
+                double pr = 1.0;
+                for (int r = 1; r <= PBR_MAXORD; ++r) if (r <= order) {
+                    pr *= (te - (t - h*(r - 1)))/(h*r);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) yo[v] += D[r*NV + v]*pr;
+                }
+                out(next_out, yo);
+                next_out++;
+            }
+            // order / step selection (bdf.py:426-455) only where the change can be applied on the very next trip
+            if (n_equal >= order + 1 && (trip % PBR_JAC_PERIOD) == 0) {
+                const double fm = (order > 1) ? pbr_pow(sqrt(em/NV), -1.0/order) : 0.0;
+                const double f0 = pbr_pow(err_norm, -1.0/(order + 1));      // err_norm == 0 -> inf, as in scipy
+                const double fp = (order < PBR_MAXORD) ? pbr_pow(sqrt(ep/NV), -1.0/(order + 2)) : 0.0;
+                double fmaxv = f0; int dord = 0;
+                if (fm > fmaxv) { fmaxv = fm; dord = -1; }
+                if (fp > fmaxv) { fmaxv = fp; dord = +1; }
+                order += dord;
+                pend = fmin(PBR_MAX_FACTOR, safety*fmaxv);
+                n_equal = 0;
+            }
+            if (!(t < t_bound)) active = false;
         }
-        if (n_equal < order + 1) continue;
-        // ---------------- order / step selection, bdf.py:426-455 ----------------
-        const double fm = (order > 1) ? pow(sqrt(em/NV), -1.0/order) : 0.0;
-        const double f0 = pow(err_norm, -1.0/(order + 1));          // err_norm == 0 -> inf, as in scipy
-        const double fp = (order < PBR_MAXORD) ? pow(sqrt(ep/NV), -1.0/(order + 2)) : 0.0;
-        double fmaxv = f0; int dord = 0;
-        if (fm > fmaxv) { fmaxv = fm; dord = -1; }
-        if (fp > fmaxv) { fmaxv = fp; dord = +1; }
-        order += dord;
-        const double factor = fmin(PBR_MAX_FACTOR, safety*fmaxv);
-        h *= factor; pbr_change_D<NV>(D, order, factor); n_equal = 0; lu_ok = false;
     }
     return status;
 }

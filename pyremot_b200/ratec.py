@@ -100,13 +100,17 @@ class Graph:
         return self._mk(("mul", a, b))
 
     def div(self, a, b):
+        """a/b is emitted as a * rcp(b): one FP64 division per distinct denominator instead of one per use
+        (an FP64 divide is ~12 instructions on the device); the result differs from a true divide by <= 1 ulp."""
         if self.is_const(a) and self.is_const(b):
             return self.const(self.cval(a)/self.cval(b))
         if self.is_const(a, 0.0):
             return self.const(0.0)
         if self.is_const(b, 1.0):
             return a
-        return self._mk(("div", a, b))
+        if self.is_const(b):
+            return self.mul(a, self.const(1.0/self.cval(b)))
+        return self.mul(a, self._mk(("rcp", b)))
 
     def neg(self, a):
         if self.is_const(a):
@@ -362,10 +366,10 @@ def _eval_nodes(g, inputs):
             vals[i] = vals[n[1]] - vals[n[2]]
         elif op == "mul":
             vals[i] = vals[n[1]]*vals[n[2]]
-        elif op == "div":
-            vals[i] = vals[n[1]]/vals[n[2]]
         elif op == "neg":
             vals[i] = -vals[n[1]]
+        elif op == "rcp":
+            vals[i] = 1.0/vals[n[1]]
         elif op == "powi":
             vals[i] = math.pow(vals[n[1]], n[2])
         elif op == "pow":
@@ -405,23 +409,26 @@ def _derivatives(g, outs, n_comp):
                 if k in db:
                     t = g.add(t, g.mul(n[1], db[k]))
                 d[k] = t
-        elif op == "div":
-            da, db = dmap[n[1]], dmap[n[2]]
-            for k in set(da) | set(db):
-                num = da.get(k, g.const(0.0))
-                if k in db:
-                    num = g.sub(num, g.mul(i, db[k]))       # u' - (u/v) v'
-                d[k] = g.div(num, n[2])
+        elif op == "rcp":      # (1/u)' = -(1/u)^2 u'
+            if dmap[n[1]]:
+                m = g.neg(g.mul(i, i))
+                d = {k: g.mul(m, v) for k, v in dmap[n[1]].items()}
         elif op == "neg":
             d = {k: g.neg(v) for k, v in dmap[n[1]].items()}
         elif op == "exp":
             d = {k: g.mul(i, v) for k, v in dmap[n[1]].items()}
         elif op == "log":
-            d = {k: g.div(v, n[1]) for k, v in dmap[n[1]].items()}
+            if dmap[n[1]]:
+                r = g.div(g.const(1.0), n[1])
+                d = {k: g.mul(v, r) for k, v in dmap[n[1]].items()}
         elif op == "log10":
-            d = {k: g.div(v, g.mul(n[1], g.const(LN10))) for k, v in dmap[n[1]].items()}
+            if dmap[n[1]]:
+                r = g.div(g.const(1.0/LN10), n[1])
+                d = {k: g.mul(v, r) for k, v in dmap[n[1]].items()}
         elif op == "sqrt":
-            d = {k: g.div(v, g.mul(g.const(2.0), i)) for k, v in dmap[n[1]].items()}
+            if dmap[n[1]]:
+                r = g.div(g.const(0.5), i)
+                d = {k: g.mul(v, r) for k, v in dmap[n[1]].items()}
         elif op == "powi":
             e = n[2]
             if dmap[n[1]]:
@@ -452,7 +459,7 @@ def _children(n):
     op = n[0]
     if op in ("const", "in"):
         return ()
-    if op in ("add", "sub", "mul", "div", "pow"):
+    if op in ("add", "sub", "mul", "pow"):
         return (n[1], n[2])
     return (n[1],)   # neg, powi (n[2] is the integer exponent), exp, log, log10, sqrt
 
@@ -479,11 +486,13 @@ def _emit_body(g, needed, lines, names):
             names[i] = {"T": "T", "P": "P"}.get(n[1]) or {"X": "x", "C": "C", "PAR": "par"}[n[1]] + f"[{n[2]}]"
             continue
         a = names[n[1]]
-        if op in ("add", "sub", "mul", "div"):
+        if op in ("add", "sub", "mul"):
             b = names[n[2]]
-            rhs = f"{a} {dict(add='+', sub='-', mul='*', div='/')[op]} {b}"
+            rhs = f"{a} {dict(add='+', sub='-', mul='*')[op]} {b}"
         elif op == "neg":
             rhs = f"-{a}"
+        elif op == "rcp":
+            rhs = f"1.0 / {a}"
         elif op == "powi":
             e = n[2]
             rhs = _powi(a, abs(e))
