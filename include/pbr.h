@@ -102,6 +102,25 @@ int pbr_unscale_n1(pbr_ctx* ctx, long N, int K, const double* inst_par_dev, cons
 int pbr_solve_n1_host(pbr_ctx* ctx, long N, const double* inst_in_host, double rtol, double atol, int n_out,
                       int max_steps, double* prof_host, double* outlet_host, int* status_host, int* stats_host);
 
+/* K4 — the interval loop of runN2 (:3589-3685): for each of tNo intervals of length period/tNo the solve_ivp call
+ * (:3609) restarted from the previous end state; variable-order BDF, one warp per reactor, block lower-bidiagonal
+ * Newton matrix (per-node LU + forward substitution along the bed).  IV = feed-filled bed (:3483-3497).
+ *   snaps_y_dev [N][tNo][nv2][zNo] scaled state at the interval ends;  status_dev [N];  stats_dev [4][N] or NULL.
+ * Scratch ((13*nv2 + nv2^2 + 1)*zNo doubles per resident warp) is owned by the context. */
+int pbr_solve_n2(pbr_ctx* ctx, long N, int zNo, int tNo, double period, const double* inst_par_dev, double rtol,
+                 double atol, int max_steps, double* snaps_y_dev, int* status_dev, int* stats_dev, void* stream);
+
+/* K5b — sortResult5 + mole fractions (solResultAnalysis.py:252-301, pbHomoReactor.py:3655-3661):
+ * scaled snapshots [N][tNo][nv2][zNo] -> dataYs [N][tNo][n_comp+1][zNo] = rows x_1..x_n, T [K] */
+int pbr_unscale_n2(pbr_ctx* ctx, long N, int tNo, int zNo, const double* inst_par_dev, const double* snaps_y_dev,
+                   double* out_dev, void* stream);
+
+/* Whole N2 path with HOST buffers: H2D of inst_in, K0, K4, K5b, D2H.
+ *   snaps_y_host [N][tNo][nv2][zNo] or NULL;  data_host [N][tNo][n_comp+1][zNo];  status_host [N];  stats_host [4][N] or NULL */
+int pbr_solve_n2_host(pbr_ctx* ctx, long N, int zNo, int tNo, double period, const double* inst_in_host, double rtol,
+                      double atol, int max_steps, double* snaps_y_host, double* data_host, int* status_host,
+                      int* stats_host);
+
 /* FP64-pipe peak probe (DFMA streams) — roofline denominator the driver's MEASURED_PEAKS.json lacks. */
 int pbr_fp64_peak(pbr_ctx* ctx, int iters, double* tflops);
 

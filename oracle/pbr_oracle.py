@@ -342,51 +342,58 @@ class Ensemble:
         return out
 
     def rhs_n2(self, Y):
-        """modelEquationN2, pbHomoReactor.py:3827-4131. Y: [N, nv, zNo] -> same (var-major per instance)."""
+        """modelEquationN2, pbHomoReactor.py:3827-4131. Y: [N, nv, zNo] -> same (var-major per instance).
+
+        Vectorised over nodes; only the pressure march P_z[z+1] = P_z[z] + (dP/dz)_z*dz (:3979) is a loop."""
         n = self.n
         Y = np.asarray(Y, dtype=np.float64)
         N, nv, zNo = Y.shape
         dz = 1/(zNo-1)                                                 # :3439 (DoLe = 1)
-        out = np.zeros_like(Y)
-        eps, dp = self.BeVoFr, self.PaDi
-        vs = self.vi0*eps                                              # :3833, v_z constant :3937, :4066
-        vs_s = vs/self.vs0                                             # v/vf :3923 (== 1 up to rounding)
-        vi_s = (vs/eps)/self.vi0                                       # :3941-3943
-        const_F1 = 1/(eps*(self.ReLe/self.vs0))                        # :4075
+        eps, dp = self.BeVoFr[:, None], self.PaDi[:, None]
+        vs = (self.vi0*self.BeVoFr)[:, None]                           # :3833, v_z constant :3937, :4066
+        vs_s = vs/self.vs0[:, None]                                    # v/vf :3923 (== 1 up to rounding)
+        vi_s = (vs/eps)/self.vi0[:, None]                              # :3941-3943
+        const_F1 = 1/(eps*(self.ReLe/self.vs0)[:, None])               # :4075
+        c = np.maximum(Y[:, :n, :], EPS_CONST)                         # :3899       [N, n, zNo]
+        C = np.moveaxis(c*self.Cmax[:, None, None], 1, 2)              # :3903       [N, zNo, n]
+        Ct = np.sum(C, axis=2)
+        th = np.zeros((N, zNo)) if self.iso else Y[:, n, :]            # :3883-3884
+        T = th*self.T0[:, None] + self.T0[:, None]                     # :3914
+        x = C/Ct[:, :, None]                                           # :3927
+        M = np.sum(x*self.MW, axis=2)*1e-3                             # :3960
+        ergA = 150*self.mu[:, None]*vs/(dp**2)                         # :3970
+        ergB = ((1-eps)**2)/(eps**3)
+        ergD = (1-eps)/(eps**3)
+        P = np.zeros((N, zNo))
         Pz = self.P0.copy()                                            # :3848
         for z in range(zNo):
-            c = np.maximum(Y[:, :n, z], EPS_CONST)                     # :3899
-            C = c*self.Cmax[:, None]                                   # :3903
-            Ct = np.sum(C, axis=1)
-            th = 0.0*Pz if self.iso else Y[:, n, z]                    # :3883-3884
-            T = th*self.T0 + self.T0                                   # :3914
-            x = C/Ct[:, None]                                          # :3927
-            M = np.sum(x*self.MW, axis=1)*1e-3                         # :3960
-            rho = Pz/((R_CONST/M)*T)                                   # :3964
-            rho_s = rho/self.rho0
-            ergA = 150*self.mu*vs/(dp**2)                              # :3970
-            ergB = ((1-eps)**2)/(eps**3)
-            ergC = 1.75*rho*(vs**2)/dp
-            ergD = (1-eps)/(eps**3)
-            dPdz = -1*(ergA*ergB + ergC*ergD)                          # :3974 (dimensional slope)
-            r = rates(self.rate_expr, T, Pz, x, C, self.var_overrides)  # :3989
-            ri = r @ self.S
-            if z == 0:
-                cb = self.c0                                           # :4090
-            else:
-                cb = np.maximum(Y[:, :n, z-1], EPS_CONST)              # :4093
-            dCdz = (Y[:, :n, z] - cb)/dz                               # :4095 (unclamped centre value)
-            out[:, :n, z] = const_F1[:, None]*(-vs_s[:, None]*dCdz + ri/self.G[:, None])  # :4098
-            if not self.iso:
-                Cpmix, OvHeReT = self._thermo_terms(x, T, r)
-                Cp_s = Cpmix/self.Cpmix0
-                Qm = np.where(self.Tm == 0, 0.0, self.U*self.a*(self.Tm - T))
-                const_T2 = 1/(rho_s*Cp_s*eps*(self.ReLe/self.vs0))     # :4077
-                thb = (self.T0 - self.T0)/self.T0 if z == 0 else Y[:, n, z-1]  # :4108, :4111
-                dTdz = (Y[:, n, z] - thb)/dz
-                conv = -1*vi_s*rho_s*(Cp_s*eps)*dTdz                   # :4116
-                out[:, n, z] = const_T2*(conv + (1/self.GH)*(-OvHeReT) + (1/self.GH)*Qm)  # :4125
+            P[:, z] = Pz
+            rho_z = Pz/((R_CONST/M[:, z])*T[:, z])                     # :3964
+            ergC = 1.75*rho_z*(vs[:, 0]**2)/dp[:, 0]
+            dPdz = -1*(ergA[:, 0]*ergB[:, 0] + ergC*ergD[:, 0])        # :3974 (dimensional slope)
             Pz = dPdz*dz + Pz                                          # :3979 (dimensionless dz on a Pa/m slope)
+        rho = P/((R_CONST/M)*T)
+        rho_s = rho/self.rho0[:, None]
+        ov = {k: v[:, None] for k, v in self.var_overrides.items()}
+        r = rates(self.rate_expr, T, P, x, C, ov)                      # :3989       [N, zNo, R]
+        ri = r @ self.S                                                #             [N, zNo, n]
+        cb = np.concatenate([self.c0[:, :, None], c[:, :, :-1]], axis=2)   # :4088-4093
+        dCdz = (Y[:, :n, :] - cb)/dz                                   # :4095 (unclamped centre value)
+        out = np.zeros_like(Y)
+        out[:, :n, :] = const_F1[:, None, :]*(-vs_s[:, None, :]*dCdz + np.moveaxis(ri, 2, 1)/self.G[:, None, None])  # :4098
+        if not self.iso:
+            Cpm = cp_mean(self.comps, T)
+            Cpmix = np.sum(x*Cpm, axis=-1)
+            OvHeReT = np.sum(r*(dH_correction(self.sides, T) + self.dH25), axis=-1)
+            Cp_s = Cpmix/self.Cpmix0[:, None]
+            Tm, U, a = self.Tm[:, None], self.U[:, None], self.a[:, None]
+            Qm = np.where(Tm == 0, 0.0, U*a*(Tm - T))
+            GH = self.GH[:, None]
+            const_T2 = 1/(rho_s*Cp_s*eps*(self.ReLe/self.vs0)[:, None])     # :4077
+            thb = np.concatenate([np.zeros((N, 1)), Y[:, n, :-1]], axis=1)   # :4108, :4111
+            dTdz = (Y[:, n, :] - thb)/dz
+            conv = -1*vi_s*rho_s*(Cp_s*eps)*dTdz                       # :4116
+            out[:, n, :] = const_T2*(conv + (1/GH)*(-OvHeReT) + (1/GH)*Qm)  # :4125
         return out
 
     # ---- un-scaling (solvers/solResultAnalysis.py:191-301; pbHomoReactor.py:2973-2983, :3655-3661)
@@ -439,7 +446,21 @@ def solve_n1(ens, method="LSODA", rtol=1e-3, atol=1e-6, zNo=100, instances=None)
     return y, sel.unscale_n1(y), np.array(nfev)
 
 
-def solve_n2(ens, zNo=20, tNo=5, timesNo=5, method="LSODA", rtol=1e-3, atol=1e-6, instances=None):
+def n2_jac_sparsity(nv, zNo):
+    """Block lower-bidiagonal pattern of dF/dY in the var-major flatten (the ~1e-3 pressure coupling to all upstream
+    nodes is left out: with SciPy's BDF a slightly inexact Jacobian only costs Newton iterations, not accuracy)."""
+    from scipy.sparse import lil_matrix
+    Sp = lil_matrix((nv*zNo, nv*zNo), dtype=np.int8)
+    for z in range(zNo):
+        for i in range(nv):
+            for k in range(nv):
+                Sp[i*zNo + z, k*zNo + z] = 1
+            if z > 0:
+                Sp[i*zNo + z, i*zNo + z - 1] = 1
+    return Sp.tocsc()
+
+
+def solve_n2(ens, zNo=20, tNo=5, timesNo=5, method="LSODA", rtol=1e-3, atol=1e-6, instances=None, sparse=False):
     """Interval loop with solver restart, pbHomoReactor.py:3557-3558, :3589-3685.
 
     Returns (Y [M, tNo, nv, zNo] scaled snapshots at interval ends, dataYs [M, tNo, n+1, zNo], nfev [M]).
@@ -455,8 +476,9 @@ def solve_n2(ens, zNo=20, tNo=5, timesNo=5, method="LSODA", rtol=1e-3, atol=1e-6
         snaps, nf = [], 0
         for k in range(tNo):
             t = [span[k], span[k+1]]
+            kw = {"jac_sparsity": n2_jac_sparsity(nv, zNo)} if sparse else {}
             sol = solve_ivp(lambda t, y: e.rhs_n2(y.reshape(1, nv, zNo))[0].reshape(-1), t, IV, method=method,
-                            t_eval=np.linspace(t[0], t[1], timesNo), rtol=rtol, atol=atol)
+                            t_eval=np.linspace(t[0], t[1], timesNo), rtol=rtol, atol=atol, **kw)
             if not sol.success:
                 raise RuntimeError(f"oracle N2 solve failed for instance {i}: {sol.message}")
             IV = sol.y[:, -1]

@@ -70,6 +70,9 @@ PBR_DEV void pbr_load_par(const double* __restrict__ par, long N, long i, InstPa
 // pow() inlines to ~300 instructions per site; the integrator needs it at five rarely executed places
 // (step-size factors), so one out-of-line copy keeps the solver kernel inside the instruction cache.
 PBR_NOINLINE double pbr_pow(double x, double e) { return pow(x, e); }
+// Step-size factors need 3 digits, not 16: x^e through single-precision exp2/log2 (MUFU on the device).
+// x = 0 -> +inf for e < 0, as scipy's error_norm ** (-1/(k+1)); the callers clip to [MIN_FACTOR, MAX_FACTOR].
+PBR_DEV double pbr_fpow(double x, double e) { return (double)exp2f((float)e*log2f((float)x)); }
 
 // ---- property polynomials
 PBR_DEV double pbr_poly(const double* c, double T) { return c[0] + T*(c[1] + T*(c[2] + T*c[3])); }
@@ -467,7 +470,7 @@ struct LuStore {            // receives Jacobian entries, stores the Newton matr
 #define PBR_NEWTON_MAXITER 4
 #define PBR_MIN_FACTOR 0.2
 #define PBR_MAX_FACTOR 10.0
-#define PBR_DROWS (PBR_MAXORD + 3)
+#define PBR_DROWS (PBR_MAXORD + 2)   // rows 0..order+2, but row MAXORD+2 would only feed an order increase past MAXORD
 
 enum { PBR_OK = 0, PBR_ERR_STEP_TOO_SMALL = 1, PBR_ERR_MAX_STEPS = 2, PBR_ERR_NONFINITE = 3, PBR_ERR_SINGULAR = 4 };
 
@@ -536,7 +539,7 @@ PBR_DEV double pbr_ulp10(double t) {   // 10*|nextafter(t, inf) - t|  (bdf.py:31
 struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
 
 // Sink for dense output: out(k, y[NV]) is called for every requested point index k (z_k = k/(n_out-1)).
-// Storage: work = Strided array of (PBR_DROWS*NV + NV*NV) doubles: D rows then the LU matrix.
+// Storage: D = Strided array of PBR_DROWS*NV doubles (difference history), LU = Strided NV*NV (Newton matrix).
 //
 // Control flow is FLAT: one trip of the main loop = one step attempt, and every trip runs the same sequence
 //   [even trips: rescale history, Jacobian + LU at the predictor] -> predictor -> <=4 Newton iterations ->
@@ -554,10 +557,8 @@ struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
 #endif
 template <class Sink>
 PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double atol, int n_out, int max_steps,
-                         const Strided& work, Sink& out, N1Stats& stt) {
+                         const Strided& D, const Strided& LU, Sink& out, N1Stats& stt) {
     const int NV = PBR_NV1;
-    const Strided D = work;
-    const Strided LU = {work.base + (long)PBR_DROWS*NV*work.stride, work.stride};
     const double t_bound = 1.0;                        // DoLe = 1, pbHomoReactor.py:2856
     const double dz_out = 1.0/(double)(n_out - 1);     // np.linspace(0, 1, zNo+1), :2862
     const double newton_tol = fmax(10.0*2.220446049250313e-16/rtol, fmin(0.03, sqrt(rtol)));   // bdf.py:217
@@ -691,7 +692,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
         const bool accepted = tried && converged && (err_norm <= 1.0);
         if ((tried && !converged) || (active && !lu_good)) { pend = 0.5; stt.nfail++; }   // Newton failed (or singular matrix)
         if (tried && converged && !accepted) {                                    // also catches NaN
-            pend = (err_norm == err_norm) ? fmax(PBR_MIN_FACTOR, safety*pbr_pow(err_norm, -1.0/(order + 1))) : 0.5;
+            pend = (err_norm == err_norm) ? fmax(PBR_MIN_FACTOR, safety*pbr_fpow(err_norm, -1.0/(order + 1))) : 0.5;
             stt.nrej++;
         }
         // ---------------- 6. accepted: history update, dense output, order / step selection ----------------
@@ -702,7 +703,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
 #pragma unroll
             for (int v = 0; v < NV; ++v) {                                // bdf.py:416-421
                 const double Dk1 = D[(order + 1)*NV + v];
-                D[(order + 2)*NV + v] = d[v] - Dk1;
+                if (order < PBR_MAXORD) D[(order + 2)*NV + v] = d[v] - Dk1;
                 D[(order + 1)*NV + v] = d[v];
                 double acc = d[v];
                 for (int r = PBR_MAXORD; r >= 0; --r) if (r <= order) { acc += D[r*NV + v]; D[r*NV + v] = acc; }
@@ -726,9 +727,9 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             }
             // order / step selection (bdf.py:426-455) only where the change can be applied on the very next trip
             if (n_equal >= order + 1 && (trip % PBR_JAC_PERIOD) == 0) {
-                const double fm = (order > 1) ? pbr_pow(sqrt(em/NV), -1.0/order) : 0.0;
-                const double f0 = pbr_pow(err_norm, -1.0/(order + 1));      // err_norm == 0 -> inf, as in scipy
-                const double fp = (order < PBR_MAXORD) ? pbr_pow(sqrt(ep/NV), -1.0/(order + 2)) : 0.0;
+                const double fm = (order > 1) ? pbr_fpow(sqrt(em/NV), -1.0/order) : 0.0;
+                const double f0 = pbr_fpow(err_norm, -1.0/(order + 1));      // err_norm == 0 -> inf, as in scipy
+                const double fp = (order < PBR_MAXORD) ? pbr_fpow(sqrt(ep/NV), -1.0/(order + 2)) : 0.0;
                 double fmaxv = f0; int dord = 0;
                 if (fm > fmaxv) { fmaxv = fm; dord = -1; }
                 if (fp > fmaxv) { fmaxv = fp; dord = +1; }
@@ -738,6 +739,382 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             }
             if (!(t < t_bound)) active = false;
         }
+    }
+    return status;
+}
+
+// =====================================================================================================
+// N2: method-of-lines integrator.  One WARP per reactor instance, lanes over axial nodes (node z is owned by
+// lane z % 32 in slot z / 32, so every global access is coalesced over z).  Same BDF/NDF logic and the same
+// flat, lock-step control flow as pbr_n1_solve; the scalars (t, h, order, ...) are replicated in all lanes.
+//
+// Newton matrix: J = d f / d Y is block LOWER-BIDIAGONAL in node-major order (upwind differences, :4088-4111):
+//   diagonal blocks   A_z = I - c J_zz               (NV2 x NV2, analytic, LU per node by the owning lane)
+//   sub-diagonal      B_z = -c diag(sub_z)           (d f_z / d Y_{z-1} is diagonal)
+// plus the pressure coupling of node z to ALL upstream nodes through P_z (Ergun march, :3970-3979), which is
+// ~1e-3 of the diagonal entries and is left out of the iteration matrix (inexact Newton; the
+// residual uses the exact RHS).  The linear solve is a block forward substitution
+//   x_z = A_z^{-1} (b_z + c sub_z * x_{z-1})
+// marched along the bed, the owner lane of node z solving and broadcasting x_z to the warp.
+//
+// Scratch (global memory, private to the warp, element (k, z) at ws[k*zNo + z]):
+//   D[PBR_DROWS][NV2] | y[NV2] | d[NV2] | psi[NV2] | scl[NV2] | b[NV2] | sub[NV2] | LU[NV2*NV2] | piv[1]
+// =====================================================================================================
+#define PBR_N2_WS_ROWS ((PBR_DROWS + 6)*PBR_NV2 + PBR_NV2*PBR_NV2 + 1)
+
+struct WarpCtx {
+#ifdef PBR_HOST
+    int lane; enum { NL = 1 };
+    double sum(double x) const { return x; }
+    double bcast(double x, int) const { return x; }
+    void sync() const {}
+    // pressure AT this lane's node given the affine maps (a,b) of the lanes before it; carry advances past the chunk
+    double scan_affine(double a, double b, double& carry) const { const double P = carry; carry = a*P + b; return P; }
+#else
+    int lane; enum { NL = 32 };
+    __device__ __forceinline__ double sum(double x) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        return x;
+    }
+    __device__ __forceinline__ double bcast(double x, int src) const { return __shfl_sync(0xffffffffu, x, src); }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ double scan_affine(double a, double b, double& carry) const {
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double a1 = __shfl_up_sync(0xffffffffu, a, off);
+            const double b1 = __shfl_up_sync(0xffffffffu, b, off);
+            if (lane >= off) { b = a*b1 + b; a = a*a1; }
+        }
+        double ae = __shfl_up_sync(0xffffffffu, a, 1), be = __shfl_up_sync(0xffffffffu, b, 1);
+        if (lane == 0) { ae = 1.0; be = 0.0; }
+        const double P = ae*carry + be;
+        carry = __shfl_sync(0xffffffffu, a*carry + b, 31);
+        return P;
+    }
+#endif
+};
+
+struct N2Ws {            // views into the warp's scratch
+    double* base; int zNo;
+    PBR_DEV double* D(int r, int v) const { return base + (long)(r*PBR_NV2 + v)*zNo; }
+    PBR_DEV double* vec(int which, int v) const { return base + (long)((PBR_DROWS + which)*PBR_NV2 + v)*zNo; }   // 0 y,1 d,2 psi,3 scl,4 b,5 sub
+    PBR_DEV double* lu() const { return base + (long)(PBR_DROWS + 6)*PBR_NV2*zNo; }
+    PBR_DEV double* piv() const { return lu() + (long)PBR_NV2*PBR_NV2*zNo; }
+};
+
+struct Lu2Store {        // Jacobian entries of one node -> I - c*J in the node's strided LU block
+    Strided a; double c;
+    PBR_DEV void operator()(int i, int k, double v) const { a[i*PBR_NV2 + k] = (i == k ? 1.0 : 0.0) - c*v; }
+};
+
+// Evaluate f(Y) for the whole reactor from the iterate in ws.vec(0): result into ws.vec(4) (b) as  c*f - psi - d
+// when `newton`, else plain f into ws.vec(4).  With JAC also factorises the diagonal blocks and fills sub.
+// Returns false (warp-uniform) if something non-finite / singular turned up.
+template <bool JAC>
+PBR_DEV bool pbr_n2_sweep_eval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, double c, bool newton) {
+    const int zNo = ws.zNo;
+    const double dz = 1.0/(double)(zNo - 1), inv_dz = (double)(zNo - 1);        // :3439
+    double Pcarry = p.Pf;                                                        // :3848
+    double bad = 0.0;
+    w.sync();
+    for (int z0 = 0; z0 < zNo; z0 += WarpCtx::NL) {
+        const int z = z0 + w.lane;
+        const bool act = z < zNo;
+        double yc[PBR_NV2], yb[PBR_NV2];
+#pragma unroll
+        for (int v = 0; v < PBR_NV2; ++v) {
+            yc[v] = act ? ws.vec(0, v)[z] : 1.0;
+            yb[v] = (act && z > 0) ? ws.vec(0, v)[z - 1] : 0.0;
+        }
+        double a = 1.0, b = 0.0;
+        if (act) {
+            double Ct = 0.0, M = 0.0;
+#pragma unroll
+            for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yc[i], PBR_EPS)*p.Cmax; Ct += C; M += C*PBR_MW[i]; }
+            M = (M/Ct)*1e-3;
+            const double th = PBR_ISO ? 0.0 : yc[PBR_ISO ? 0 : PBR_NC];
+            a = 1.0 - dz*p.E2*p.vs0*p.vs0*M/(PBR_R*(th*p.Tf + p.Tf));
+            b = -dz*p.E1*p.vs0;
+        }
+        const double Pz = w.scan_affine(a, b, Pcarry);
+        if (act) {
+            double f[PBR_NV2], sub[PBR_NV2];
+            if (JAC) {
+                const Strided blk = {ws.lu() + z, zNo};
+                Lu2Store st = {blk, c};
+                pbr_n2_node<true>(yc, yb, z == 0, Pz, inv_dz, p, f, st, sub);
+                unsigned long long piv;
+                if (!pbr_lu_factor<PBR_NV2>(blk, piv)) bad = 1.0;
+                ws.piv()[z] = (double)piv;
+#pragma unroll
+                for (int v = 0; v < PBR_NV2; ++v) ws.vec(5, v)[z] = sub[v];
+            } else {
+                NoStore ns;
+                pbr_n2_node<false>(yc, yb, z == 0, Pz, inv_dz, p, f, ns, (double*)0);
+            }
+#pragma unroll
+            for (int v = 0; v < PBR_NV2; ++v) {
+                const double r = newton ? (c*f[v] - ws.vec(2, v)[z] - ws.vec(1, v)[z]) : f[v];
+                if (!(fabs(r) < 1e300)) bad = 1.0;
+                ws.vec(4, v)[z] = r;
+            }
+        }
+    }
+    w.sync();
+    return w.sum(bad) == 0.0;
+}
+
+// Block forward substitution: dy_z = A_z^{-1}(b_z + c sub_z*dy_{z-1}); applies the Newton update y += dy, d += dy
+// and returns sum_z sum_v (dy/scale)^2.
+PBR_DEV double pbr_n2_newton_solve(const WarpCtx& w, const N2Ws& ws, double c) {
+    const int zNo = ws.zNo;
+    double xprev[PBR_NV2];
+#pragma unroll
+    for (int v = 0; v < PBR_NV2; ++v) xprev[v] = 0.0;
+    double nrm = 0.0;
+    for (int z = 0; z < zNo; ++z) {
+        const int owner = z % WarpCtx::NL;
+        double x[PBR_NV2];
+#pragma unroll
+        for (int v = 0; v < PBR_NV2; ++v) x[v] = 0.0;
+        if (w.lane == owner) {
+#pragma unroll
+            for (int v = 0; v < PBR_NV2; ++v) x[v] = ws.vec(4, v)[z] + c*ws.vec(5, v)[z]*xprev[v];
+            const Strided blk = {ws.lu() + z, zNo};
+            pbr_lu_solve<PBR_NV2>(blk, (unsigned long long)ws.piv()[z], x);
+#pragma unroll
+            for (int v = 0; v < PBR_NV2; ++v) {
+                ws.vec(0, v)[z] += x[v];
+                ws.vec(1, v)[z] += x[v];
+                const double e = x[v]/ws.vec(3, v)[z];
+                nrm += e*e;
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < PBR_NV2; ++v) xprev[v] = w.bcast(x[v], owner);
+    }
+    return w.sum(nrm);
+}
+
+// D[:order+1] <- (R U)^T D[:order+1] for every (v, z) owned by the lane (same algebra as pbr_change_D).
+PBR_DEV void pbr_n2_change_D(const WarpCtx& w, const N2Ws& ws, int order, double factor) {
+    double R[PBR_MAXORD + 1][PBR_MAXORD + 1];
+#pragma unroll
+    for (int l = 1; l <= PBR_MAXORD; ++l) {
+        double r = 1.0;
+#pragma unroll
+        for (int i = 1; i <= PBR_MAXORD; ++i) {
+            r *= ((double)(i - 1) - factor*(double)l)*(1.0/(double)i);
+            R[i][l] = (i <= order) ? r : 0.0;
+        }
+    }
+    for (int z = w.lane; z < ws.zNo; z += WarpCtx::NL) {
+#pragma unroll 1
+        for (int v = 0; v < PBR_NV2; ++v) {
+            double d[PBR_MAXORD + 1], E[PBR_MAXORD + 1];
+#pragma unroll
+            for (int i = 0; i <= PBR_MAXORD; ++i) d[i] = (i <= order) ? ws.D(i, v)[z] : 0.0;
+            E[0] = d[0];
+#pragma unroll
+            for (int l = 1; l <= PBR_MAXORD; ++l) {
+                double s = d[0];
+#pragma unroll
+                for (int i = 1; i <= PBR_MAXORD; ++i) s += R[i][l]*d[i];
+                E[l] = s;
+            }
+            if (order >= 1) ws.D(1, v)[z] = E[0] - E[1];
+            if (order >= 2) ws.D(2, v)[z] = E[0] - 2.0*E[1] + E[2];
+            if (order >= 3) ws.D(3, v)[z] = E[0] - 3.0*E[1] + 3.0*E[2] - E[3];
+            if (order >= 4) ws.D(4, v)[z] = E[0] - 4.0*E[1] + 6.0*E[2] - 4.0*E[3] + E[4];
+            if (order >= 5) ws.D(5, v)[z] = E[0] - 5.0*E[1] + 10.0*E[2] - 10.0*E[3] + 5.0*E[4] - E[5];
+        }
+    }
+}
+
+struct N2Stats { int nsteps, nrej, nfev, nlu, nfail; };
+
+// Integrate one interval [t0, t1] from the state in ws.D(0,.) (restart: order 1, fresh initial step — the reference
+// restarts solve_ivp at every interval, pbHomoReactor.py:3589-3685).  On success ws.D(0,.) holds Y(t1).
+PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, double t0, double t1,
+                            double rtol, double atol, int max_steps, N2Stats& stt) {
+    const int zNo = ws.zNo;
+    const double nTot = (double)(PBR_NV2*zNo);
+    const double newton_tol = fmax(10.0*2.220446049250313e-16/rtol, fmin(0.03, sqrt(rtol)));
+    const double span = t1 - t0;
+    // ---- initial step (scipy common.py:68-140): f0 = f(Y0), f1 = f(Y0 + h0 f0)
+    double h = 0.0;
+    {
+        double h0 = 0.0, d1 = 0.0;
+        for (int z = w.lane; z < zNo; z += WarpCtx::NL)
+#pragma unroll
+            for (int v = 0; v < PBR_NV2; ++v) { const double y = ws.D(0, v)[z]; ws.vec(0, v)[z] = y; ws.vec(3, v)[z] = atol + fabs(y)*rtol; }
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+            if (!pbr_n2_sweep_eval<false>(w, p, ws, 0.0, false)) return PBR_ERR_NONFINITE;
+            stt.nfev++;
+            double a0 = 0.0, a1 = 0.0;
+            if (s == 0) {
+                for (int z = w.lane; z < zNo; z += WarpCtx::NL)
+#pragma unroll
+                    for (int v = 0; v < PBR_NV2; ++v) {
+                        const double sc = ws.vec(3, v)[z], y = ws.vec(0, v)[z], f = ws.vec(4, v)[z];
+                        a0 += (y/sc)*(y/sc); a1 += (f/sc)*(f/sc);
+                        ws.D(1, v)[z] = f;
+                    }
+                const double d0 = sqrt(w.sum(a0)/nTot);
+                d1 = sqrt(w.sum(a1)/nTot);
+                h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
+                h0 = fmin(h0, span);
+                for (int z = w.lane; z < zNo; z += WarpCtx::NL)
+#pragma unroll
+                    for (int v = 0; v < PBR_NV2; ++v) ws.vec(0, v)[z] = ws.D(0, v)[z] + h0*ws.D(1, v)[z];
+            } else {
+                for (int z = w.lane; z < zNo; z += WarpCtx::NL)
+#pragma unroll
+                    for (int v = 0; v < PBR_NV2; ++v) { const double df = (ws.vec(4, v)[z] - ws.D(1, v)[z])/ws.vec(3, v)[z]; a0 += df*df; }
+                const double d2 = sqrt(w.sum(a0)/nTot)/h0;
+                const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0*1e-3) : sqrt(0.01/fmax(d1, d2));
+                h = fmin(fmin(100.0*h0, h1), span);
+            }
+        }
+    }
+    for (int z = w.lane; z < zNo; z += WarpCtx::NL)
+#pragma unroll
+        for (int v = 0; v < PBR_NV2; ++v) {
+            ws.D(1, v)[z] *= h;
+            for (int r = 2; r < PBR_DROWS; ++r) ws.D(r, v)[z] = 0.0;
+        }
+    int order = 1, n_equal = 0, trip = 0;
+    double t = t0, pend = 1.0;
+    int status = PBR_OK;
+    bool active = true;
+
+    while (active) {
+        // ---- 1. step size, lazy history rescale
+        double hn = h*pend;
+        const bool clip = (t + hn > t1) || (t1 - (t + hn) < 1e-13*span);
+        if (clip) hn = t1 - t;
+        const double t_new = clip ? t1 : t + hn;
+        const double fac = hn/h;
+        if (fac != 1.0) { pbr_n2_change_D(w, ws, order, fac); n_equal = 0; }
+        h = hn; pend = 1.0;
+        trip++;
+        if (h < pbr_ulp10(t)) { status = PBR_ERR_STEP_TOO_SMALL; break; }
+        if (trip > max_steps) { status = PBR_ERR_MAX_STEPS; break; }
+        // ---- 2. predictor, psi, scale, d = 0
+        const double alpha = pbr_bdf_alpha(order);
+        const double c = h/alpha;
+        for (int z = w.lane; z < zNo; z += WarpCtx::NL)
+#pragma unroll
+            for (int v = 0; v < PBR_NV2; ++v) {
+                double yp = ws.D(0, v)[z], ps = 0.0;
+                for (int r = 1; r <= order; ++r) { const double Dr = ws.D(r, v)[z]; yp += Dr; ps += Dr*pbr_bdf_gamma(r); }
+                ws.vec(0, v)[z] = yp; ws.vec(1, v)[z] = 0.0; ws.vec(2, v)[z] = ps/alpha;
+                ws.vec(3, v)[z] = atol + rtol*fabs(yp);
+            }
+        // ---- 3./4. Jacobian blocks + LU at the predictor, then Newton (bdf.py:36-68)
+        bool converged = false;
+        bool running = pbr_n2_sweep_eval<true>(w, p, ws, c, true);
+        stt.nlu++; stt.nfev++;
+        double dy_norm_old = -1.0;
+        int n_iter = 0;
+#pragma unroll 1
+        for (int k = 0; k < PBR_NEWTON_MAXITER; ++k) {
+            if (running) {
+                n_iter = k + 1;
+                bool fin = true;
+                if (k > 0) { fin = pbr_n2_sweep_eval<false>(w, p, ws, c, true); stt.nfev++; }
+                if (!fin) running = false;
+                else {
+                    const double dy_norm = sqrt(pbr_n2_newton_solve(w, ws, c)/nTot);
+                    const double rate = (dy_norm_old >= 0.0) ? dy_norm/dy_norm_old : -1.0;
+                    const bool diverge = !(dy_norm == dy_norm) ||
+                        (rate >= 0.0 && (rate >= 1.0 || pbr_ipow(rate, PBR_NEWTON_MAXITER - k)/(1.0 - rate)*dy_norm > newton_tol));
+                    if (diverge) running = false;
+                    else {
+                        if (dy_norm == 0.0 || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; running = false; }
+                        dy_norm_old = dy_norm;
+                    }
+                }
+            }
+        }
+        // ---- 5. error test
+        const double safety = 0.9*(2*PBR_NEWTON_MAXITER + 1)/(double)(2*PBR_NEWTON_MAXITER + n_iter);
+        double err_norm = 0.0;
+        if (converged) {
+            const double errc = pbr_bdf_errc(order);
+            double en = 0.0;
+            for (int z = w.lane; z < zNo; z += WarpCtx::NL)
+#pragma unroll
+                for (int v = 0; v < PBR_NV2; ++v) {
+                    const double sc = atol + rtol*fabs(ws.vec(0, v)[z]);
+                    ws.vec(3, v)[z] = sc;
+                    const double ev = errc*ws.vec(1, v)[z]/sc; en += ev*ev;
+                }
+            err_norm = sqrt(w.sum(en)/nTot);
+        }
+        const bool accepted = converged && (err_norm <= 1.0);
+        if (!converged) { pend = 0.5; stt.nfail++; }
+        else if (!accepted) {
+            pend = (err_norm == err_norm) ? fmax(PBR_MIN_FACTOR, safety*pbr_fpow(err_norm, -1.0/(order + 1))) : 0.5;
+            stt.nrej++;
+        }
+        // ---- 6. accepted: history update, order / step selection
+        if (accepted) {
+            n_equal++; stt.nsteps++;
+            t = t_new;
+            double em = 0.0, ep = 0.0;
+            for (int z = w.lane; z < zNo; z += WarpCtx::NL)
+#pragma unroll
+                for (int v = 0; v < PBR_NV2; ++v) {
+                    const double dv = ws.vec(1, v)[z], sc = ws.vec(3, v)[z];
+                    const double Dk1 = ws.D(order + 1, v)[z];
+                    if (order < PBR_MAXORD) ws.D(order + 2, v)[z] = dv - Dk1;
+                    ws.D(order + 1, v)[z] = dv;
+                    double acc = dv;
+                    for (int r = order; r >= 0; --r) { acc += ws.D(r, v)[z]; ws.D(r, v)[z] = acc; }
+                    if (order > 1) { const double e1 = pbr_bdf_errc(order - 1)*ws.D(order, v)[z]/sc; em += e1*e1; }
+                    if (order < PBR_MAXORD) { const double e2 = pbr_bdf_errc(order + 1)*(dv - Dk1)/sc; ep += e2*e2; }
+                }
+            if (n_equal >= order + 1) {
+                em = w.sum(em); ep = w.sum(ep);
+                const double fm = (order > 1) ? pbr_fpow(sqrt(em/nTot), -1.0/order) : 0.0;
+                const double f0 = pbr_fpow(err_norm, -1.0/(order + 1));
+                const double fp = (order < PBR_MAXORD) ? pbr_fpow(sqrt(ep/nTot), -1.0/(order + 2)) : 0.0;
+                double fmaxv = f0; int dord = 0;
+                if (fm > fmaxv) { fmaxv = fm; dord = -1; }
+                if (fp > fmaxv) { fmaxv = fp; dord = +1; }
+                order += dord;
+                pend = fmin(PBR_MAX_FACTOR, safety*fmaxv);
+                n_equal = 0;
+            }
+            if (!(t < t1)) active = false;
+        }
+    }
+    return status;
+}
+
+// Whole N2 run of one instance: IV (c0 everywhere, theta = 0, :3483-3497), tNo intervals of length period/tNo
+// (:3557-3558), snapshot of the scaled state at every interval end -> snaps[tNo][NV2][zNo].
+PBR_DEV int pbr_n2_solve(const WarpCtx& w, const InstPar& p, const N2Ws& ws, int tNo, double period, double rtol, double atol,
+                         int max_steps, double* snaps, N2Stats& stt) {
+    const int zNo = ws.zNo;
+    stt.nsteps = stt.nrej = stt.nfev = stt.nlu = stt.nfail = 0;
+    for (int z = w.lane; z < zNo; z += WarpCtx::NL) {
+#pragma unroll
+        for (int v = 0; v < PBR_NC; ++v) ws.D(0, v)[z] = p.c0[v];
+        if (!PBR_ISO) ws.D(0, PBR_ISO ? 0 : PBR_NC)[z] = 0.0;
+    }
+    int status = PBR_OK;
+    for (int k = 0; k < tNo && status == PBR_OK; ++k) {
+        const double t0 = (k == 0) ? 0.0 : period*((double)k/(double)tNo);          // np.linspace(0, opT, tNo+1)
+        const double t1 = (k == tNo - 1) ? period : period*((double)(k + 1)/(double)tNo);
+        status = pbr_n2_interval(w, p, ws, t0, t1, rtol, atol, max_steps, stt);
+        w.sync();
+        for (int z = w.lane; z < zNo; z += WarpCtx::NL)
+#pragma unroll
+            for (int v = 0; v < PBR_NV2; ++v) snaps[((long)k*PBR_NV2 + v)*zNo + z] = ws.D(0, v)[z];
     }
     return status;
 }
@@ -787,7 +1164,10 @@ extern "C" __global__ void __launch_bounds__(128) pbr_k_jac_n1(long N, const dou
 #ifndef PBR_N1_BLOCK
 #define PBR_N1_BLOCK 32
 #endif
-#define PBR_N1_WORK (PBR_DROWS*PBR_NV1 + PBR_NV1*PBR_NV1)
+#ifndef PBR_N1_D_LOCAL
+#define PBR_N1_D_LOCAL 0      // 1: BDF history in per-thread local memory instead of shared memory (measured slower)
+#endif
+#define PBR_N1_SMEM_DOUBLES (PBR_NV1*PBR_NV1 + (PBR_N1_D_LOCAL ? 0 : PBR_DROWS*PBR_NV1))
 
 struct N1Sink {      // scaled state -> prof_y[k][v][N] (coalesced across the warp's instances)
     double* prof; double* outlet; long N, i; int n_out;
@@ -815,10 +1195,16 @@ pbr_k2_solve_n1(long N, const double* __restrict__ par, double rtol, double atol
     for (int k = 0; k < PBR_NC; ++k) y0[k] = p.c0[k];                 // IV, pbHomoReactor.py:2831-2842
     y0[PBR_NC] = 1.0;
     if (!PBR_ISO) y0[PBR_NC + (PBR_ISO ? 0 : 1)] = 0.0;
-    const Strided work = {pbr_smem + threadIdx.x, PBR_N1_BLOCK};
+    const Strided LU = {pbr_smem + threadIdx.x, PBR_N1_BLOCK};
+#if PBR_N1_D_LOCAL
+    double Dloc[PBR_DROWS*PBR_NV1];
+    const Strided D = {Dloc, 1};
+#else
+    const Strided D = {pbr_smem + (long)PBR_NV1*PBR_NV1*PBR_N1_BLOCK + threadIdx.x, PBR_N1_BLOCK};
+#endif
     N1Sink sink = {prof_y, outlet_y, N, i, n_out};
     N1Stats st;
-    const int rc = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, work, sink, st);
+    const int rc = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, D, LU, sink, st);
     status[i] = rc;
     if (stats) { stats[0*N + i] = st.nsteps; stats[1*N + i] = st.nrej + st.nfail; stats[2*N + i] = st.nfev; stats[3*N + i] = st.nlu; }
 }
@@ -905,6 +1291,45 @@ extern "C" __global__ void __launch_bounds__(128) pbr_k3_rhs_n2(long N, int zNo,
         }
         Pcarry = Pnext;
     }
+}
+
+// ---- K4: fused N2 solver. Persistent warps: warp g handles instances g, g+G, ... with its own scratch slab.
+extern "C" __global__ void __launch_bounds__(128) pbr_k4_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+                                                                  double rtol, double atol, int max_steps, double* __restrict__ work,
+                                                                  double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
+    const long gw = ((long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const long G = ((long)gridDim.x*blockDim.x) >> 5;
+    WarpCtx w; w.lane = threadIdx.x & 31;
+    const N2Ws ws = {work + gw*(long)PBR_N2_WS_ROWS*zNo, zNo};
+    for (long inst = gw; inst < N; inst += G) {
+        InstPar p; pbr_load_par(par, N, inst, p);
+        N2Stats st;
+        const int rc = pbr_n2_solve(w, p, ws, tNo, period, rtol, atol, max_steps, snaps + inst*(long)tNo*PBR_NV2*zNo, st);
+        if (w.lane == 0) {
+            status[inst] = rc;
+            if (stats) { stats[0*N + inst] = st.nsteps; stats[1*N + inst] = st.nrej + st.nfail; stats[2*N + inst] = st.nfev; stats[3*N + inst] = st.nlu; }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- K5b epilog (N2): scaled snapshots [N][tNo][NV2][zNo] -> dataYs [N][tNo][NC+1][zNo] = [x_i ; T]
+//      solvers/solResultAnalysis.py:252-301, pbHomoReactor.py:3655-3661.  One thread per (instance, snapshot, node).
+extern "C" __global__ void __launch_bounds__(256) pbr_k5_unscale_n2(long N, int tNo, int zNo, const double* __restrict__ par,
+                                                                    const double* __restrict__ Y, double* __restrict__ out) {
+    const long g = (long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (g >= N*tNo*zNo) return;
+    const int z = (int)(g % zNo); const long ik = g / zNo; const long i = ik / tNo;
+    const double Cmax = par[PAR_CMAX*N + i], Tf = par[PAR_TF*N + i];
+    const double* y = Y + ik*(long)PBR_NV2*zNo + z;
+    double* o = out + ik*(long)(PBR_NC + 1)*zNo + z;
+    double C[PBR_NC], Ct = 0.0;
+#pragma unroll
+    for (int v = 0; v < PBR_NC; ++v) { C[v] = y[(long)v*zNo]*Cmax; Ct += C[v]; }
+#pragma unroll
+    for (int v = 0; v < PBR_NC; ++v) o[(long)v*zNo] = C[v]/Ct;
+    const double th = PBR_ISO ? 0.0 : y[(long)(PBR_ISO ? 0 : PBR_NC)*zNo];
+    o[(long)PBR_NC*zNo] = th*Tf + Tf;
 }
 
 // ---- FP64 pipe peak probe: dependent-free DFMA streams (roofline denominator; no FP64 number in MEASURED_PEAKS.json)

@@ -58,6 +58,9 @@ def lib():
         "pbr_solve_n1": (i, [vp, l, dp, d, d, i, i, dp, dp, ip, ip, vp]),
         "pbr_unscale_n1": (i, [vp, l, i, dp, dp, dp, vp]),
         "pbr_solve_n1_host": (i, [vp, l, dp, d, d, i, i, dp, dp, ip, ip]),
+        "pbr_solve_n2": (i, [vp, l, i, i, d, dp, d, d, i, dp, ip, ip, vp]),
+        "pbr_unscale_n2": (i, [vp, l, i, i, dp, dp, dp, vp]),
+        "pbr_solve_n2_host": (i, [vp, l, i, i, d, dp, d, d, i, dp, dp, ip, ip]),
         "pbr_fp64_peak": (i, [vp, i, C.POINTER(d)]),
         "pbr_launch_count": (l, [vp]),
     }
@@ -70,7 +73,7 @@ def lib():
 
 EXPORTS = ("pbr_create pbr_destroy pbr_last_error pbr_version pbr_set_species pbr_load_rates pbr_model_dims "
            "pbr_model_source pbr_model_cubin pbr_kernel_attr pbr_prolog pbr_rhs_n1 pbr_jac_n1 pbr_rhs_n2 pbr_solve_n1 "
-           "pbr_unscale_n1 pbr_solve_n1_host pbr_fp64_peak pbr_launch_count").split()
+           "pbr_unscale_n1 pbr_solve_n1_host pbr_solve_n2 pbr_unscale_n2 pbr_solve_n2_host pbr_fp64_peak pbr_launch_count").split()
 
 
 # ----------------------------------------------------------------------------- reaction parsing
@@ -287,6 +290,40 @@ class Model:
             prof.ctypes.data_as(C.c_void_p) if profile else None, outlet.ctypes.data_as(C.c_void_p),
             status.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p)))
         return {"dataYs": prof, "outlet": outlet, "status": status, "stats": stats}
+
+    def solve_n2(self, par, zNo, tNo, period, rtol=1e-9, atol=1e-13, max_steps=0, stats=True):
+        """K4 on device tensors. Returns dict(snaps_y [N,tNo,nv2,zNo] scaled, status [N], stats [4,N])."""
+        import torch
+        N = par.shape[1]
+        dev = par.device
+        snaps = torch.empty((N, tNo, self.nv2, zNo), dtype=torch.float64, device=dev)
+        status = torch.empty((N,), dtype=torch.int32, device=dev)
+        st = torch.empty((4, N), dtype=torch.int32, device=dev) if stats else None
+        self._check(lib().pbr_solve_n2(self._ctx, N, zNo, tNo, float(period), par.data_ptr(), rtol, atol, max_steps,
+                                       snaps.data_ptr(), status.data_ptr(), st.data_ptr() if stats else None, self._stream()))
+        return {"snaps_y": snaps, "status": status, "stats": st}
+
+    def unscale_n2(self, par, snaps_y):
+        """K5b: scaled snapshots [N,tNo,nv2,zNo] -> dataYs [N,tNo,n+1,zNo] = [x; T]."""
+        import torch
+        N, tNo, nv, zNo = snaps_y.shape
+        out = torch.empty((N, tNo, self.n + 1, zNo), dtype=torch.float64, device=snaps_y.device)
+        self._check(lib().pbr_unscale_n2(self._ctx, N, tNo, zNo, par.data_ptr(), snaps_y.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def solve_n2_host(self, inst_in, zNo, tNo, period, rtol=1e-9, atol=1e-13, max_steps=0, scaled=True):
+        """Whole N2 path through the host-buffer C-ABI call. Returns dict(dataYs [N,tNo,n+1,zNo], snaps_y, status, stats)."""
+        inst_in = np.ascontiguousarray(inst_in, dtype=np.float64)
+        N = inst_in.shape[0]
+        data = np.empty((N, tNo, self.n + 1, zNo), dtype=np.float64)
+        snaps = np.empty((N, tNo, self.nv2, zNo), dtype=np.float64) if scaled else None
+        status = np.empty((N,), dtype=np.int32)
+        stats = np.empty((4, N), dtype=np.int32)
+        self._check(lib().pbr_solve_n2_host(
+            self._ctx, N, zNo, tNo, float(period), inst_in.ctypes.data_as(C.c_void_p), rtol, atol, max_steps,
+            snaps.ctypes.data_as(C.c_void_p) if scaled else None, data.ctypes.data_as(C.c_void_p),
+            status.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p)))
+        return {"dataYs": data, "snaps_y": snaps, "status": status, "stats": stats}
 
     def fp64_peak(self, iters=8192):
         t = C.c_double()

@@ -79,3 +79,12 @@ class HostSim:
         self.L.hs_solve_n1(C.c_long(N), self._p(par), C.c_double(rtol), C.c_double(atol), C.c_int(n_out),
                            C.c_int(max_steps), self._p(prof), self._p(status), self._p(stats))
         return prof, status, stats
+
+    def solve_n2(self, par, zNo, tNo, period, rtol=1e-8, atol=1e-12, max_steps=1000000):
+        N = par.shape[1]
+        snaps = np.zeros((N, tNo, self.nv2, zNo))
+        status = np.zeros(N, dtype=np.int32)
+        stats = np.zeros((5, N), dtype=np.int32)
+        self.L.hs_solve_n2(C.c_long(N), C.c_int(zNo), C.c_int(tNo), C.c_double(period), self._p(par), C.c_double(rtol),
+                           C.c_double(atol), C.c_int(max_steps), self._p(snaps), self._p(status), self._p(stats))
+        return snaps, status, stats

@@ -75,10 +75,25 @@ void hs_solve_n1(long N, const double* par, double rtol, double atol, int n_out,
         for (int k = 0; k < PBR_NC; ++k) y0[k] = p.c0[k];
         y0[PBR_NC] = 1.0;
         if (!PBR_ISO) y0[PBR_NV1 - 1] = 0.0;
-        Strided w = {work.data(), 1};
+        Strided Dw = {work.data(), 1};
+        Strided LUw = {work.data() + PBR_DROWS*PBR_NV1, 1};
         Sink sk = {prof, N, i, n_out};
         N1Stats st;
-        status[i] = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, w, sk, st);
+        status[i] = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, Dw, LUw, sk, st);
+        stats[0*N + i] = st.nsteps; stats[1*N + i] = st.nrej; stats[2*N + i] = st.nfev; stats[3*N + i] = st.nlu; stats[4*N + i] = st.nfail;
+    }
+}
+
+// snaps: [N][tNo][NV2][zNo] scaled; stats [5][N]
+void hs_solve_n2(long N, int zNo, int tNo, double period, const double* par, double rtol, double atol, int max_steps,
+                 double* snaps, int* status, int* stats) {
+    std::vector<double> work((size_t)PBR_N2_WS_ROWS*zNo);
+    for (long i = 0; i < N; ++i) {
+        InstPar p; pbr_load_par(par, N, i, p);
+        WarpCtx w; w.lane = 0;
+        N2Ws ws = {work.data(), zNo};
+        N2Stats st;
+        status[i] = pbr_n2_solve(w, p, ws, tNo, period, rtol, atol, max_steps, snaps + i*(long)tNo*PBR_NV2*zNo, st);
         stats[0*N + i] = st.nsteps; stats[1*N + i] = st.nrej; stats[2*N + i] = st.nfev; stats[3*N + i] = st.nlu; stats[4*N + i] = st.nfail;
     }
 }

@@ -1,0 +1,94 @@
+"""GPU parity of the N2 path (K0 -> K4 -> K5b through the C-ABI) against the reference's rmtExe("N2") outputs
+(tests/golden/n2_solve.npz: SciPy BDF tightened to rtol 1e-9 / atol 1e-12) and against the oracle at the
+BASELINE config-3 grid (zNo = 100).  Tolerance 1e-6 relative on mole fractions and T over the whole
+axial x temporal profile (north_star)."""
+import numpy as np
+import pytest
+
+from oracle import pbr_oracle as O
+from pyremot_b200 import cases
+
+pytestmark = pytest.mark.gpu
+RTOL_SOLVE = 1e-6
+
+
+def relerr(a, b, floor=0.0):
+    return float(np.max(np.abs(np.asarray(a, float) - b)/(np.abs(b) + floor)))
+
+
+@pytest.mark.parametrize("tag,mk,zNo", [
+    ("readme_z20", lambda: cases.readme_case("N2"), 20),
+    ("dme_z20", cases.dme_n2_case, 20),                       # PyREMOT/tests/test_rmt_N1_DME.py
+    ("ch4_z10", cases.ch4_n2_case, 10),                       # PyREMOT/tests/test_rmt_N2_CH4.py (adiabatic, SpCoi rate)
+    ("readme_iso_z10", lambda: cases.readme_case("N2", "iso-thermal"), 10),
+])
+def test_rmtExe_n2_matches_converged_reference(golden, tag, mk, zNo):
+    import pyremot_b200
+    from pyremot_b200 import rmtExe
+    g = golden("n2_solve")
+    saved = dict(pyremot_b200.solverSetting["N2"])
+    try:
+        pyremot_b200.solverSetting["N2"]["zNo"] = zNo         # same mechanism as PyREMOT.solvers.solSetting
+        res = rmtExe(mk())["resModel"]
+    finally:
+        pyremot_b200.solverSetting["N2"].update(saved)
+    assert set(res) == {"computation-time", "dataPack"} and len(res["dataPack"]) == 5
+    for k, d in enumerate(res["dataPack"]):
+        assert set(d) == {"modelId", "processType", "successStatus", "dataShape", "labelList", "indexList", "dataTime",
+                          "dataXs", "dataYCons1", "dataYCons2", "dataYTemp1", "dataYTemp2", "dataYs"}
+        assert d["dataShape"] == () and d["labelList"][-1] == "Temperature"
+        assert abs(d["dataTime"] - g[f"{tag}_conv_dataTime"][k]) < 1e-12
+        for key in ("dataXs", "dataYCons1", "dataYCons2", "dataYTemp1", "dataYTemp2", "dataYs"):
+            ref = g[f"{tag}_conv_{key}"][k] if key != "dataXs" else g[f"{tag}_conv_dataXs"]
+            assert np.shape(d[key]) == ref.shape, (key, np.shape(d[key]), ref.shape)
+            # theta = (T-Tf)/Tf starts at 0: compare it on the scale of 1 (i.e. as T/Tf)
+            floor = 1.0 if key == "dataYTemp1" else (1e-9 if key == "dataXs" else 0.0)
+            assert relerr(d[key], ref, floor=floor) < RTOL_SOLVE, (key, k)
+        # distance to the reference's own default-tolerance output (it integrates at rtol 1e-3)
+        assert relerr(d["dataYs"], g[f"{tag}_default_dataYs"][k]) < 2e-2
+
+
+def test_n2_baseline_grid_vs_oracle():
+    """BASELINE config 3 shape (zNo = 100, tNo = 5, period 0.5 s, start-up from the feed-filled bed): 64 swept
+    instances on the GPU; two of them against the oracle (SciPy BDF on the NumPy RHS, rtol 1e-9)."""
+    import torch
+    from pyremot_b200.api import get_model
+    N, zNo, tNo = 64, 100, 5
+    rows = cases.ensemble_rows(N)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    mi = cases.readme_case("N2")
+    m = get_model(mi)
+    tab = m.instance_table(mi, sweep)
+    r = m.solve_n2_host(tab, zNo, tNo, 0.5)
+    assert (r["status"] == 0).all()
+    x = r["dataYs"][:, :, :6, :]
+    assert np.max(np.abs(x.sum(axis=2) - 1)) < 1e-12
+    idx = [0, 37]
+    ens = O.Ensemble(mi, {k: v[idx] for k, v in sweep.items()})
+    _, ref, _ = O.solve_n2(ens, zNo=zNo, tNo=tNo, method="BDF", rtol=1e-9, atol=1e-13, sparse=True)
+    assert relerr(r["dataYs"][idx], ref) < RTOL_SOLVE
+    # device-pointer path == host-buffer path; sub-batch reproduces the same rows; ragged grid (zNo not a multiple of 32)
+    par = m.prolog(torch.from_numpy(tab).cuda())
+    rd = m.solve_n2(par, zNo, tNo, 0.5)
+    assert np.array_equal(m.unscale_n2(par, rd["snaps_y"]).cpu().numpy(), r["dataYs"])
+    r2 = m.solve_n2_host(tab[10:13], zNo, tNo, 0.5)
+    assert np.array_equal(r2["dataYs"], r["dataYs"][10:13])
+
+
+def test_n2_more_instances_than_resident_warps():
+    """N larger than the persistent grid (148 SMs x 8 warps): every warp loops over several instances."""
+    from pyremot_b200.api import get_model
+    N, zNo = 3000, 12
+    rows = cases.ensemble_rows(N)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    mi = cases.readme_case("N2")
+    m = get_model(mi)
+    tab = m.instance_table(mi, sweep)
+    r = m.solve_n2_host(tab, zNo, 2, 0.2)
+    assert (r["status"] == 0).all()
+    sub = m.solve_n2_host(tab[2500:2510], zNo, 2, 0.2)
+    assert np.array_equal(sub["dataYs"], r["dataYs"][2500:2510])
+    ens = O.Ensemble(mi, {k: v[[2999]] for k, v in sweep.items()})
+    ens.period = 0.2
+    _, ref, _ = O.solve_n2(ens, zNo=zNo, tNo=2, method="BDF", rtol=1e-9, atol=1e-13, sparse=True)
+    assert relerr(r["dataYs"][[2999]], ref) < RTOL_SOLVE
