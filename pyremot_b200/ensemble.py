@@ -1,0 +1,86 @@
+"""Ensemble sharding across the GPUs of one box: one process per GPU, no data-path collective.
+
+Reactor instances are independent, so rank r simply owns a slice of the instance table and the only
+communication is ONE gather of outlet rows at the end (NCCL over NVLink when the tensors are CUDA tensors;
+gloo in the CPU tests).  ``torch.distributed`` is plumbing here; everything numerical happens in libpbr.
+
+Load balance: BDF step counts differ between easy and hot-spot reactors, so a contiguous split of a table that
+is ordered by operating point would give ranks unequal work.  ``deal()`` sorts by a stiffness proxy and deals
+the rows round-robin; ``undeal()`` restores the caller's order after the gather.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(N, rank, world):
+    """Contiguous shard [lo, hi) of rank; the first N % world ranks get one extra row."""
+    q, r = divmod(N, world)
+    lo = rank*q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def deal(proxy, world):
+    """Permutation that sorts instances by ``proxy`` and deals them round-robin to ``world`` ranks.
+
+    Returns ``perm`` such that rank r owns rows ``perm[lo_r:hi_r]`` (with shard_bounds); every rank gets the
+    same mix of easy and hard instances."""
+    N = len(proxy)
+    order = np.argsort(proxy, kind="stable")
+    perm = np.empty(N, dtype=np.int64)
+    pos = 0
+    for r in range(world):
+        mine = order[r::world]
+        perm[pos:pos + len(mine)] = mine
+        pos += len(mine)
+    return perm
+
+
+def undeal(perm, gathered):
+    """Inverse of ``deal`` on the gathered rows: out[perm[k]] = gathered[k]."""
+    out = np.empty_like(gathered)
+    out[perm] = gathered
+    return out
+
+
+def gather_rows(local, N_total, world=None, rank=None):
+    """All-gather the per-rank row blocks (torch tensor [n_r, K]) into [N_total, K] on every rank.
+
+    Shards may differ by one row: blocks are padded to the largest shard for the collective and trimmed after."""
+    import torch
+    import torch.distributed as dist
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    rank = dist.get_rank() if rank is None else rank
+    K = local.shape[1]
+    nmax = -(-N_total // world)
+    pad = torch.zeros((nmax, K), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((world*nmax, K), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_bounds(N_total, r, world)
+        parts.append(out[r*nmax:r*nmax + (hi - lo)])
+    return torch.cat(parts, dim=0)
+
+
+def solve_n1_sharded(modelInput, sweep, params=(), rtol=None, atol=None, balance=True, device=None):
+    """Solve an N1 ensemble across all ranks of the initialised process group; every rank returns the full
+    outlet table [N, nv1] (numpy) in the caller's row order, plus its local status vector."""
+    import torch
+    import torch.distributed as dist
+    from .api import rmtExeBatch
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    N = len(next(iter(sweep.values())))
+    perm = deal(np.asarray(sweep["T"]) if (balance and "T" in sweep) else np.arange(N), world) if world > 1 else np.arange(N)
+    lo, hi = shard_bounds(N, rank, world)
+    mine = perm[lo:hi]
+    local_sweep = {k: np.asarray(v)[mine] for k, v in sweep.items()}
+    dev = torch.cuda.current_device() if device is None else device
+    r = rmtExeBatch(modelInput, local_sweep, params=params, device=dev, rtol=rtol, atol=atol, return_device=True)
+    full = gather_rows(r["outlet"].contiguous(), N, world, rank)
+    return undeal(perm, full.cpu().numpy()), r["status"].cpu().numpy()

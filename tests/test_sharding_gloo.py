@@ -1,0 +1,64 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 gloo process group."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from pyremot_b200 import ensemble
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds_cover_everything():
+    for N in (0, 1, 7, 64, 65537):
+        for world in (1, 2, 3, 8):
+            b = [ensemble.shard_bounds(N, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == N
+            assert all(b[i][1] == b[i+1][0] for i in range(world-1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_deal_balances_and_inverts():
+    rng = np.random.default_rng(0)
+    proxy = rng.random(1001)
+    for world in (2, 4, 8):
+        perm = ensemble.deal(proxy, world)
+        assert sorted(perm.tolist()) == list(range(1001))
+        means = [proxy[perm[slice(*ensemble.shard_bounds(1001, r, world))]].mean() for r in range(world)]
+        assert max(means) - min(means) < 0.01          # every rank gets the same mix
+        rows = np.arange(1001)[:, None]*np.ones((1, 3))
+        assert np.array_equal(ensemble.undeal(perm, rows[perm]), rows)
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from pyremot_b200 import ensemble
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+N, K = 11, 8                      # odd N: shards of 6 and 5 rows
+table = np.arange(N*K, dtype=np.float64).reshape(N, K)
+proxy = (np.arange(N)*7) % 11
+perm = ensemble.deal(proxy, world)
+lo, hi = ensemble.shard_bounds(N, rank, world)
+local = torch.from_numpy(table[perm[lo:hi]]*2.0)          # stand-in for "solve my shard"
+full = ensemble.gather_rows(local, N, world, rank)
+out = ensemble.undeal(perm, full.numpy())
+assert np.array_equal(out, table*2.0), (rank, out)
+print("rank", rank, "ok", flush=True)
+dist.destroy_process_group()
+'''
+
+
+def test_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", str(script), ROOT],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
