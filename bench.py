@@ -239,7 +239,7 @@ def run_gpu(a):
         # secondary: standalone N2 RHS kernel (HBM-bound side of the path), zNo=100, inputs larger than L2
         rhs = bench_rhs_n2(model, mi, peaks)
         cores = os.cpu_count() or 1
-        n_cpu = max(4*cores, 32)
+        n_cpu = max(32*cores, 256)                      # ~0.35 s per solve per core -> 10-20 s of CPU work
         cpu_v, cpu_dt, _ = cpu_path(n_cpu, cores)
         line = {
             "metric": METRIC, "value": world*N*a.steps/t_dev, "unit": "solves/s", "n_gpus": world, "steps": a.steps,
@@ -296,9 +296,29 @@ def bench_rhs_n2(model, mi, peaks):
     bytes_ = 16.0*m2.nv2*zNo*N
     gbs = bytes_/(ms*1e-3)/1e9
     peak = peaks.get("hbm_gbs", 6650.0)
+    # N1 RHS (thread per reactor): 16*(n+2) B of state per eval + 8*k_par B of per-instance constants
+    N1 = 4*1024*1024
+    y = torch.rand((m2.nv1, N1), dtype=torch.float64, device="cuda")*0.1 + 0.5
+    y[m2.n] = 0.99
+    y[m2.n + 1] = 0.1
+    par1 = m2.prolog(tab[:1].repeat(N1, 1).contiguous())
+    for _ in range(3):
+        m2.rhs_n1(par1, y)
+    e0.record()
+    for _ in range(reps):
+        m2.rhs_n1(par1, y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms1 = e0.elapsed_time(e1)/reps
+    b1 = (16.0*m2.nv1 + 8.0*m2.k_par)*N1
+    src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     return {"kernel": "pbr_k3_rhs_n2", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs/peak,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-            "traffic": None, "zNo": zNo, "instances": N, "ms": ms, "rhs_evals_per_s": N/(ms*1e-3), "node_evals_per_s": N*zNo/(ms*1e-3)}
+            "peak_source": src, "traffic": None, "zNo": zNo, "instances": N, "ms": ms, "rhs_evals_per_s": N/(ms*1e-3),
+            "node_evals_per_s": N*zNo/(ms*1e-3),
+            "note": "16*(n+1)*zNo B per instance-eval; at ~650 executed FP64 ops per node this kernel sits on the FP64 side of the ridge",
+            "rhs_n1": {"kernel": "pbr_k_rhs_n1", "bound": "hbm", "achieved": b1/(ms1*1e-3)/1e9, "peak": peak, "unit": "GB/s",
+                       "frac": b1/(ms1*1e-3)/1e9/peak, "bytes_per_eval": 16*m2.nv1 + 8*m2.k_par, "instances": N1, "ms": ms1,
+                       "rhs_evals_per_s": N1/(ms1*1e-3), "state_only_GBs": 16.0*m2.nv1*N1/(ms1*1e-3)/1e9}}
 
 
 if __name__ == "__main__":

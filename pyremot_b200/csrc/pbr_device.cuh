@@ -1231,7 +1231,10 @@ extern "C" __global__ void __launch_bounds__(256) pbr_k5_unscale_n1(long N, int 
 //      Y, dYdt: [N][NV2][zNo] (the reference's var-major flatten, :3873); consecutive lanes read consecutive nodes.
 //      The Ergun pressure recurrence P[z+1] = P[z] + slope(P[z], T_z, M_z)*dz is affine in P[z]:
 //      P[z+1] = a_z P[z] + b_z, a_z = 1 - dz*E2*vs0^2*M_z/(R T_z), b_z = -dz*E1*vs0  -> warp scan of affine maps.
-extern "C" __global__ void __launch_bounds__(128) pbr_k3_rhs_n2(long N, int zNo, const double* __restrict__ par,
+#ifndef PBR_K3_MINBLOCKS
+#define PBR_K3_MINBLOCKS 4       // 4 blocks x 4 warps per SM (<=128 registers/thread)
+#endif
+extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n2(long N, int zNo, const double* __restrict__ par,
                                                                 const double* __restrict__ Y, double* __restrict__ dY) {
     const int lane = threadIdx.x & 31;
     const long inst = ((long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
