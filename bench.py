@@ -86,23 +86,33 @@ def run_reference(a):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled every ~10 ms through NVML while the timed region runs
+    (same fields as the recipe's nvidia-smi query: clocks.sm, clocks.max.sm, clocks_event_reasons.*)."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.samples, self.stop = [], False
-        self.index = index
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; NVML indexes physical devices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        self.sm, self.reasons, self.stop = [], set(), False
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        nv = self.nv
         while not self.stop:
             try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append([x.strip() for x in o])
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.01)
 
     def __enter__(self):
         self.t.start()
@@ -110,15 +120,15 @@ class ClockSampler:
 
     def __exit__(self, *a):
         self.stop = True
-        self.t.join(timeout=6)
+        self.t.join(timeout=2)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for s in self.samples if len(s) >= 6 for k in range(4) if s[2 + k].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        try:
+            mx = self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -324,7 +334,7 @@ def bench_rhs_n2(model, mi, peaks):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     a = ap.parse_args()

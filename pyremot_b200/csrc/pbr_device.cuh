@@ -47,9 +47,11 @@ struct InstPar {
     double Tf, Pf, Cmax, Ct0, vs0, eps, zf, E1, E2, rho0, Cpmix0, G, GH, Ua, Tm;
     double c0[PBR_NC];
     double rp[PBR_NPA];
+    const double* src; long srcN, srci;        // where it was loaded from (for out-of-line helpers)
 };
 
 PBR_DEV void pbr_load_par(const double* __restrict__ par, long N, long i, InstPar& p) {
+    p.src = par; p.srcN = N; p.srci = i;
     p.Tf = par[PAR_TF*N + i];       p.Pf = par[PAR_PF*N + i];     p.Cmax = par[PAR_CMAX*N + i];
     p.Ct0 = par[PAR_CT0*N + i];     p.vs0 = par[PAR_VS0*N + i];   p.eps = par[PAR_EPS*N + i];
     p.zf = par[PAR_ZF*N + i];       p.E1 = par[PAR_E1*N + i];     p.E2 = par[PAR_E2*N + i];
@@ -312,6 +314,29 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
     }
 }
 
+// Out-of-line copy of the plain N1 RHS for the integrator's rarely taken paths (initial-step probe, verification
+// Newton iterations): it reloads the instance constants from global memory so that nothing of the caller has to
+// live in local memory, and it keeps ~3300 instructions out of the solver kernel's instruction stream.
+PBR_NOINLINE void pbr_n1_rhs_ool(const double* par, long N, long i, const double* y, double* f) {
+    InstPar q; pbr_load_par(par, N, i, q);
+    double yy[PBR_NV1], ff[PBR_NV1];
+#pragma unroll
+    for (int v = 0; v < PBR_NV1; ++v) yy[v] = y[v];
+    NoStore ns;
+    pbr_n1_eval<false>(yy, q, ff, ns);
+#pragma unroll
+    for (int v = 0; v < PBR_NV1; ++v) f[v] = ff[v];
+}
+
+PBR_DEV void pbr_n1_rhs_call(const InstPar& p, const double* y, double* f) {
+    double yt[PBR_NV1], ft[PBR_NV1];           // only these temporaries are address-taken
+#pragma unroll
+    for (int v = 0; v < PBR_NV1; ++v) yt[v] = y[v];
+    pbr_n1_rhs_ool(p.src, p.srcN, p.srci, yt, ft);
+#pragma unroll
+    for (int v = 0; v < PBR_NV1; ++v) f[v] = ft[v];
+}
+
 // =====================================================================================================
 // N2: one axial node of the method-of-lines system.  modelEquationN2 :3892-4128
 //   yc[NV2] node state (unclamped), yb[NV2] upstream state (first==true: inlet BC), Pz pressure at the node.
@@ -398,17 +423,25 @@ struct Strided {            // element idx of this thread's private array lives 
 
 // In-place LU of the NxN row-major matrix a; unit-lower L below the diagonal, U on/above, diagonal stored INVERTED.
 // piv: 4 bits per column (N <= 16). Returns false if a pivot is exactly zero / non-finite.
-// Loops are kept rolled on purpose: the matrix lives in (dynamically indexable) shared memory and the solver
-// kernel is instruction-cache bound, so ~170 FMAs are not worth 1500 unrolled instructions.
+// PBR_LU_UNROLL=0 keeps the loops rolled (the matrix lives in dynamically indexable shared memory): 1400 fewer
+// instructions of code; with the block-wide barrier sharing the instruction stream the unrolled form wins.
+#ifndef PBR_LU_UNROLL
+#define PBR_LU_UNROLL 1      // measured +8 % on K2 over rolled loops (fewer dynamic instructions beat the larger code)
+#endif
+#if PBR_LU_UNROLL
+#define PBR_LU_PRAGMA _Pragma("unroll")
+#else
+#define PBR_LU_PRAGMA _Pragma("unroll 1")
+#endif
 template <int N>
 PBR_DEV bool pbr_lu_factor(const Strided& a, unsigned long long& piv) {
     piv = 0ull;
     bool ok = true;
-#pragma unroll 1
+    PBR_LU_PRAGMA
     for (int k = 0; k < N; ++k) {
         int pk = k;
         double amax = fabs(a[k*N + k]);
-#pragma unroll 1
+        PBR_LU_PRAGMA
         for (int i = k + 1; i < N; ++i) {
             const double v = fabs(a[i*N + k]);
             if (v > amax) { amax = v; pk = i; }
@@ -421,11 +454,11 @@ PBR_DEV bool pbr_lu_factor(const Strided& a, unsigned long long& piv) {
         if (!(amax > 0.0) || !(amax < 1e300)) ok = false;
         const double inv = 1.0/a[k*N + k];
         a[k*N + k] = inv;
-#pragma unroll 1
+        PBR_LU_PRAGMA
         for (int i = k + 1; i < N; ++i) {
             const double l = a[i*N + k]*inv;
             a[i*N + k] = l;
-#pragma unroll 1
+            PBR_LU_PRAGMA
             for (int j = k + 1; j < N; ++j) a[i*N + j] -= l*a[k*N + j];
         }
     }
@@ -552,12 +585,30 @@ struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
 // decided at the end of odd trips and applied lazily at the top of the next (even) trip, fused with the clip to
 // the end point (change_D composes: rescaling by f1 then f2 == rescaling by f1*f2); a lane whose attempt failed
 // on an even trip sits out the following odd trip.
+#if !defined(PBR_HOST) && defined(PBR_N1_BLOCK) && PBR_N1_BLOCK > 32
+// multi-warp blocks: all warps of the block start every step attempt together (shared instruction stream in the
+// SM's instruction caches); the loop ends when no lane of the block is active any more.
+#define PBR_TRIP_CONTINUE(active) __syncthreads_or(active)
+#endif
 #ifndef PBR_JAC_PERIOD
 #define PBR_JAC_PERIOD 1
 #endif
+#ifndef PBR_NEWTON_SKIP
+#define PBR_NEWTON_SKIP 1
+#endif
+#ifndef PBR_NEWTON_SKIP_TOL
+#define PBR_NEWTON_SKIP_TOL 0.01
+#endif
+#ifndef PBR_KAPPA_PERIOD
+#define PBR_KAPPA_PERIOD 16
+#endif
+// `live` = false marks a padding lane (block tail): it runs the loop for the barrier's sake but does nothing.
+#ifndef PBR_TRIP_CONTINUE
+#define PBR_TRIP_CONTINUE(active) (active)
+#endif
 template <class Sink>
 PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double atol, int n_out, int max_steps,
-                         const Strided& D, const Strided& LU, Sink& out, N1Stats& stt) {
+                         const Strided& D, const Strided& LU, Sink& out, N1Stats& stt, bool live = true) {
     const int NV = PBR_NV1;
     const double t_bound = 1.0;                        // DoLe = 1, pbHomoReactor.py:2856
     const double dz_out = 1.0/(double)(n_out - 1);     // np.linspace(0, 1, zNo+1), :2862
@@ -574,7 +625,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
         for (int v = 0; v < NV; ++v) { y[v] = y0[v]; scale[v] = atol + fabs(y0[v])*rtol; }
 #pragma unroll 1
         for (int s = 0; s < 2; ++s) {
-            pbr_n1_eval<false>(y, p, f, nost); stt.nfev++;
+            pbr_n1_rhs_call(p, y, f); stt.nfev++;
             if (s == 0) {
                 double d0 = 0.0;
 #pragma unroll
@@ -606,10 +657,11 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
     int order = 1, n_equal = 0, trip = 0;
     unsigned long long piv = 0ull;
     double t = 0.0, pend = 1.0;                         // pend: step-size factor decided by earlier attempts
+    double kappa = 1e300;                               // quadratic-convergence constant of the Newton iteration (unknown yet)
     int status = PBR_OK;
-    bool active = true;
+    bool active = live;
 
-    while (active) {
+    while (PBR_TRIP_CONTINUE(active)) {
         const bool refresh = (trip % PBR_JAC_PERIOD) == 0;            // warp-uniform: every lane has the same trip count
         // ---------------- 1. step size for this attempt; lazy history rescale (refresh trips only) ----------------
         bool sit_out = false;
@@ -619,15 +671,15 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             const bool clip = (t + hn > t_bound);                     // bdf.py:351-355
             if (clip) hn = t_bound - t;
             const double fac = hn/h;
-            if (fac != 1.0) {
+            if (active && fac != 1.0) {
                 if (refresh) { pbr_change_D<NV>(D, order, fac); n_equal = 0; h = hn; pend = 1.0; }
                 else sit_out = true;                                  // wait for the next refresh trip
             }
             t_new = clip ? t_bound : t + h;
         }
         trip++;
-        if (h < pbr_ulp10(t)) { status = PBR_ERR_STEP_TOO_SMALL; active = false; }
-        if (trip > max_steps) { status = PBR_ERR_MAX_STEPS; active = false; }
+        if (active && h < pbr_ulp10(t)) { status = PBR_ERR_STEP_TOO_SMALL; active = false; }
+        if (active && trip > max_steps) { status = PBR_ERR_MAX_STEPS; active = false; }
         // ---------------- 2. predictor + psi, bdf.py:360-363 ----------------
         const double alpha = pbr_bdf_alpha(order);
         const double c = h/alpha;
@@ -640,13 +692,18 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
         }
         // ---------------- 3. refresh trips: Jacobian + LU of I - cJ at the predictor (also yields f(y_pred)) ----------------
         bool lu_good = true;
-        if (refresh) {
+        if (refresh && active) {
             LuStore st = {LU, c};
             pbr_n1_eval<true>(y, p, f, st);
             lu_good = pbr_lu_factor<NV>(LU, piv);
             stt.nlu++; stt.nfev++;
         }
         // ---------------- 4. Newton, solve_bdf_system bdf.py:36-68 ----------------
+        // With the Jacobian evaluated at this very predictor the iteration converges quadratically: the second
+        // correction is ~ kappa*|dy1|^2.  kappa is measured whenever two iterations are run (at least every
+        // PBR_KAPPA_PERIOD-th trip) and, while the predicted second correction stays below PBR_NEWTON_SKIP_TOL (in
+        // units of the error tolerance; scipy itself accepts 0.03 at loose rtol), the verification iteration --
+        // a full RHS evaluation that changes nothing -- is skipped.
         bool converged = false, running = active && lu_good && !sit_out;
         const bool tried = running;
         double dy_norm_old = -1.0;
@@ -655,7 +712,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
         for (int k = 0; k < PBR_NEWTON_MAXITER; ++k) {
             if (running) {
                 n_iter = k + 1;
-                if (k > 0 || !refresh) { pbr_n1_eval<false>(y, p, f, nost); stt.nfev++; }
+                if (k > 0 || !refresh) { pbr_n1_rhs_call(p, y, f); stt.nfev++; }
                 double b[NV], nrm = 0.0;
                 bool fin = true;
 #pragma unroll
@@ -671,7 +728,10 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
                 else {
 #pragma unroll
                     for (int v = 0; v < NV; ++v) { y[v] += b[v]; d[v] += b[v]; }
-                    if (dy_norm == 0.0 || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; running = false; }
+                    if (k == 1) kappa = rate/fmax(dy_norm_old, 1e-300);
+                    const bool quad_ok = PBR_NEWTON_SKIP && k == 0 && refresh && (trip % PBR_KAPPA_PERIOD) != 0 &&
+                                         kappa*dy_norm*dy_norm < PBR_NEWTON_SKIP_TOL;
+                    if (dy_norm == 0.0 || quad_ok || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; running = false; }
                     dy_norm_old = dy_norm;
                 }
             }
@@ -1170,8 +1230,9 @@ extern "C" __global__ void __launch_bounds__(128) pbr_k_jac_n1(long N, const dou
 #define PBR_N1_SMEM_DOUBLES (PBR_NV1*PBR_NV1 + (PBR_N1_D_LOCAL ? 0 : PBR_DROWS*PBR_NV1))
 
 struct N1Sink {      // scaled state -> prof_y[k][v][N] (coalesced across the warp's instances)
-    double* prof; double* outlet; long N, i; int n_out;
+    double* prof; double* outlet; long N, i; int n_out; bool live;
     __device__ __forceinline__ void operator()(int k, const double* y) const {
+        if (!live) return;
         if (prof) {
 #pragma unroll
             for (int v = 0; v < PBR_NV1; ++v) prof[((long)k*PBR_NV1 + v)*N + i] = y[v];
@@ -1187,8 +1248,12 @@ extern "C" __global__ void __launch_bounds__(PBR_N1_BLOCK)
 pbr_k2_solve_n1(long N, const double* __restrict__ par, double rtol, double atol, int n_out, int max_steps,
                 double* __restrict__ prof_y, double* __restrict__ outlet_y, int* __restrict__ status, int* __restrict__ stats) {
     extern __shared__ double pbr_smem[];
-    const long i = (long)blockIdx.x*PBR_N1_BLOCK + threadIdx.x;
-    if (i >= N) return;
+    const long i0 = (long)blockIdx.x*PBR_N1_BLOCK + threadIdx.x;
+    const bool live = i0 < N;
+#if PBR_N1_BLOCK <= 32
+    if (!live) return;
+#endif
+    const long i = live ? i0 : N - 1;                                 // padding lanes shadow the last reactor, write nothing
     InstPar p; pbr_load_par(par, N, i, p);
     double y0[PBR_NV1];
 #pragma unroll
@@ -1202,9 +1267,10 @@ pbr_k2_solve_n1(long N, const double* __restrict__ par, double rtol, double atol
 #else
     const Strided D = {pbr_smem + (long)PBR_NV1*PBR_NV1*PBR_N1_BLOCK + threadIdx.x, PBR_N1_BLOCK};
 #endif
-    N1Sink sink = {prof_y, outlet_y, N, i, n_out};
+    N1Sink sink = {prof_y, outlet_y, N, i, n_out, live};
     N1Stats st;
-    const int rc = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, D, LU, sink, st);
+    const int rc = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, D, LU, sink, st, live);
+    if (!live) return;
     status[i] = rc;
     if (stats) { stats[0*N + i] = st.nsteps; stats[1*N + i] = st.nrej + st.nfail; stats[2*N + i] = st.nfev; stats[3*N + i] = st.nlu; }
 }
