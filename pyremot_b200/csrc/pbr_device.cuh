@@ -588,7 +588,14 @@ struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
 #if !defined(PBR_HOST) && defined(PBR_N1_BLOCK) && PBR_N1_BLOCK > 32
 // multi-warp blocks: all warps of the block start every step attempt together (shared instruction stream in the
 // SM's instruction caches); the loop ends when no lane of the block is active any more.
-#define PBR_TRIP_CONTINUE(active) __syncthreads_or(active)
+#ifndef PBR_SYNC_PERIOD
+#define PBR_SYNC_PERIOD 1
+#endif
+#ifndef PBR_MID_SYNC
+#define PBR_MID_SYNC 0            // bit mask of extra intra-trip barriers (A/B knob)
+#endif
+#define PBR_MID_BARRIER(bit) if (PBR_MID_SYNC & (bit)) __syncthreads();
+#define PBR_TRIP_CONTINUE(active, trip) ((((trip) % PBR_SYNC_PERIOD) != 0) ? true : (__syncthreads_or(active) != 0))
 #endif
 #ifndef PBR_JAC_PERIOD
 #define PBR_JAC_PERIOD 1
@@ -604,7 +611,10 @@ struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
 #endif
 // `live` = false marks a padding lane (block tail): it runs the loop for the barrier's sake but does nothing.
 #ifndef PBR_TRIP_CONTINUE
-#define PBR_TRIP_CONTINUE(active) (active)
+#define PBR_TRIP_CONTINUE(active, trip) (active)
+#endif
+#ifndef PBR_MID_BARRIER
+#define PBR_MID_BARRIER(bit)
 #endif
 template <class Sink>
 PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double atol, int n_out, int max_steps,
@@ -661,7 +671,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
     int status = PBR_OK;
     bool active = live;
 
-    while (PBR_TRIP_CONTINUE(active)) {
+    while (PBR_TRIP_CONTINUE(active, trip)) {
         const bool refresh = (trip % PBR_JAC_PERIOD) == 0;            // warp-uniform: every lane has the same trip count
         // ---------------- 1. step size for this attempt; lazy history rescale (refresh trips only) ----------------
         bool sit_out = false;
@@ -690,6 +700,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             y[v] = yp; psi[v] = ps/alpha; d[v] = 0.0;
             scale[v] = atol + rtol*fabs(yp);
         }
+        PBR_MID_BARRIER(2)
         // ---------------- 3. refresh trips: Jacobian + LU of I - cJ at the predictor (also yields f(y_pred)) ----------------
         bool lu_good = true;
         if (refresh && active) {
@@ -698,6 +709,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             lu_good = pbr_lu_factor<NV>(LU, piv);
             stt.nlu++; stt.nfev++;
         }
+        PBR_MID_BARRIER(1)
         // ---------------- 4. Newton, solve_bdf_system bdf.py:36-68 ----------------
         // With the Jacobian evaluated at this very predictor the iteration converges quadratically: the second
         // correction is ~ kappa*|dy1|^2.  kappa is measured whenever two iterations are run (at least every
@@ -736,6 +748,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
                 }
             }
         }
+        PBR_MID_BARRIER(4)
         // ---------------- 5. error test, bdf.py:381-404 ----------------
         const double safety = 0.9*(2*PBR_NEWTON_MAXITER + 1)/(double)(2*PBR_NEWTON_MAXITER + n_iter);
         double err_norm = 0.0;
@@ -1046,7 +1059,7 @@ PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, 
             for (int r = 2; r < PBR_DROWS; ++r) ws.D(r, v)[z] = 0.0;
         }
     int order = 1, n_equal = 0, trip = 0;
-    double t = t0, pend = 1.0;
+    double t = t0, pend = 1.0, kappa = 1e300;
     int status = PBR_OK;
     bool active = true;
 
@@ -1093,7 +1106,11 @@ PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, 
                         (rate >= 0.0 && (rate >= 1.0 || pbr_ipow(rate, PBR_NEWTON_MAXITER - k)/(1.0 - rate)*dy_norm > newton_tol));
                     if (diverge) running = false;
                     else {
-                        if (dy_norm == 0.0 || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; running = false; }
+                        // same quadratic-convergence shortcut as in pbr_n1_solve (the Jacobian blocks are current)
+                        if (k == 1) kappa = rate/fmax(dy_norm_old, 1e-300);
+                        const bool quad_ok = PBR_NEWTON_SKIP && k == 0 && (trip % PBR_KAPPA_PERIOD) != 0 &&
+                                             kappa*dy_norm*dy_norm < PBR_NEWTON_SKIP_TOL;
+                        if (dy_norm == 0.0 || quad_ok || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; running = false; }
                         dy_norm_old = dy_norm;
                     }
                 }
@@ -1293,72 +1310,88 @@ extern "C" __global__ void __launch_bounds__(256) pbr_k5_unscale_n1(long N, int 
     if (!PBR_ISO) { const double th = y[((long)k*PBR_NV1 + PBR_NC + (PBR_ISO ? 0 : 1))*N + i]; o[(long)(PBR_NC + 1)*K] = th*Tf + Tf; }
 }
 
-// ---- K3: fused N2 RHS. One warp per reactor instance, lanes over axial nodes.
-//      Y, dYdt: [N][NV2][zNo] (the reference's var-major flatten, :3873); consecutive lanes read consecutive nodes.
-//      The Ergun pressure recurrence P[z+1] = P[z] + slope(P[z], T_z, M_z)*dz is affine in P[z]:
-//      P[z+1] = a_z P[z] + b_z, a_z = 1 - dz*E2*vs0^2*M_z/(R T_z), b_z = -dz*E1*vs0  -> warp scan of affine maps.
+// ---- K3: fused N2 RHS.  Y, dYdt: [N][NV2][zNo] (the reference's var-major flatten, :3873).
+//      A block of 128 threads owns G consecutive reactors and walks their G*zNo nodes in flattened order, one node
+//      per thread per round, so consecutive lanes touch consecutive nodes (coalesced) and no lane idles on ragged
+//      grids (G is chosen by the host so that G*zNo nearly fills whole rounds).
+//      The Ergun pressure recurrence P[z+1] = P[z] + slope(P[z], T_z, M_z)*dz (:3970-3979) is affine in P[z]:
+//      P[z+1] = a_z P[z] + b_z, a_z = 1 - dz*E2*vs0^2*M_z/(R T_z), b_z = -dz*E1*vs0.  Node 0 of every reactor is encoded
+//      as the constant map (0, a_0 Pf + b_0), which turns the per-reactor recurrences into ONE block-wide scan of affine
+//      maps (warp shuffles + a 4-entry shared-memory hand-over between warps and rounds).
+//      Per-reactor constants are staged in shared memory; the upstream neighbour is re-read through L1.
 #ifndef PBR_K3_MINBLOCKS
 #define PBR_K3_MINBLOCKS 4       // 4 blocks x 4 warps per SM (<=128 registers/thread)
 #endif
-extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n2(long N, int zNo, const double* __restrict__ par,
-                                                                const double* __restrict__ Y, double* __restrict__ dY) {
-    const int lane = threadIdx.x & 31;
-    const long inst = ((long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-    if (inst >= N) return;
-    InstPar p; pbr_load_par(par, N, inst, p);
-    const double dz = 1.0/(double)(zNo - 1);                          // :3439
-    const double inv_dz = (double)(zNo - 1);
-    const double* Yi = Y + inst*(long)PBR_NV2*zNo;
-    double* dYi = dY + inst*(long)PBR_NV2*zNo;
-    double Pcarry = p.Pf;                                             // P_z[0] = P0, :3848
-    double prev_last[PBR_NV2];                                        // state of the last node of the previous chunk
-#pragma unroll
-    for (int v = 0; v < PBR_NV2; ++v) prev_last[v] = 0.0;
+#define PBR_K3_MAXG 16
+extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n2(long N, int zNo, int G, const double* __restrict__ par,
+                                                                                  const double* __restrict__ Y, double* __restrict__ dY) {
+    __shared__ double s_par[PBR_K3_MAXG*PBR_KPAR];
+    __shared__ double s_wa[4], s_wb[4], s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long g0 = (long)blockIdx.x*G;
+    const int Gb = (int)((N - g0 < G) ? (N - g0) : G);                // reactors in this block
+    for (int k = tid; k < Gb*PBR_KPAR; k += 128) { const int g = k / PBR_KPAR, r = k % PBR_KPAR; s_par[k] = par[(long)r*N + g0 + g]; }
+    if (tid == 0) s_carry = 0.0;
+    __syncthreads();
+    const double dz = 1.0/(double)(zNo - 1), inv_dz = (double)(zNo - 1);   // :3439
+    const int total = Gb*zNo;
     NoStore ns;
-    for (int z0 = 0; z0 < zNo; z0 += 32) {
-        const int z = z0 + lane;
-        const bool act = z < zNo;
+    for (int q0 = 0; q0 < total; q0 += 128) {
+        const int q = q0 + tid;
+        const bool act = q < total;
+        const int g = act ? q / zNo : 0, z = act ? q - g*zNo : 1;
+        const double* sp = s_par + g*PBR_KPAR;
+        InstPar pp;
+        pp.Tf = sp[PAR_TF]; pp.Pf = sp[PAR_PF]; pp.Cmax = sp[PAR_CMAX]; pp.Ct0 = sp[PAR_CT0]; pp.vs0 = sp[PAR_VS0]; pp.eps = sp[PAR_EPS];
+        pp.zf = sp[PAR_ZF]; pp.E1 = sp[PAR_E1]; pp.E2 = sp[PAR_E2]; pp.rho0 = sp[PAR_RHO0]; pp.Cpmix0 = sp[PAR_CPMIX0]; pp.G = sp[PAR_G];
+        pp.GH = sp[PAR_GH]; pp.Ua = sp[PAR_UA]; pp.Tm = sp[PAR_TM];
+#pragma unroll
+        for (int k = 0; k < PBR_NC; ++k) pp.c0[k] = sp[PAR_C0 + k];
+#pragma unroll
+        for (int k = 0; k < PBR_NP; ++k) pp.rp[k] = sp[PAR_RP + k];
+        const double* Yi = Y + (g0 + g)*(long)PBR_NV2*zNo;
         double yc[PBR_NV2], yb[PBR_NV2];
 #pragma unroll
-        for (int v = 0; v < PBR_NV2; ++v) yc[v] = act ? Yi[(long)v*zNo + z] : 1.0;
-        // affine map of this node
+        for (int v = 0; v < PBR_NV2; ++v) {
+            yc[v] = act ? Yi[(long)v*zNo + z] : 1.0;
+            yb[v] = (act && z > 0) ? Yi[(long)v*zNo + z - 1] : 0.0;
+        }
+        // affine map of this node (identity for idle lanes, constant map for a reactor's first node)
         double a = 1.0, b = 0.0;
         if (act) {
             double Ct = 0.0, M = 0.0;
 #pragma unroll
-            for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yc[i], PBR_EPS)*p.Cmax; Ct += C; M += C*PBR_MW[i]; }
+            for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yc[i], PBR_EPS)*pp.Cmax; Ct += C; M += C*PBR_MW[i]; }
             M = (M/Ct)*1e-3;
             const double th = PBR_ISO ? 0.0 : yc[PBR_ISO ? 0 : PBR_NC];
-            const double T = th*p.Tf + p.Tf;
-            a = 1.0 - dz*p.E2*p.vs0*p.vs0*M/(PBR_R*T);
-            b = -dz*p.E1*p.vs0;
+            a = 1.0 - dz*pp.E2*pp.vs0*pp.vs0*M/(PBR_R*(th*pp.Tf + pp.Tf));
+            b = -dz*pp.E1*pp.vs0;
+            if (z == 0) { b = a*pp.Pf + b; a = 0.0; }                 // P_z[0] = P0 (:3848): the map forgets what came before
         }
-        // inclusive scan of (a,b) under composition (a2,b2)o(a1,b1) = (a2 a1, a2 b1 + b2)
+        // inclusive warp scan under composition (a2,b2)o(a1,b1) = (a2 a1, a2 b1 + b2)
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const double a1 = __shfl_up_sync(0xffffffffu, a, off);
             const double b1 = __shfl_up_sync(0xffffffffu, b, off);
             if (lane >= off) { b = a*b1 + b; a = a*a1; }
         }
-        // exclusive: pressure AT node z = map of nodes z0..z-1 applied to Pcarry
+        if (lane == 31) { s_wa[wid] = a; s_wb[wid] = b; }
         double ae = __shfl_up_sync(0xffffffffu, a, 1), be = __shfl_up_sync(0xffffffffu, b, 1);
         if (lane == 0) { ae = 1.0; be = 0.0; }
-        const double Pz = ae*Pcarry + be;
-        const double Pnext = __shfl_sync(0xffffffffu, a*Pcarry + b, 31);     // pressure entering the next chunk
-        // upstream neighbour
-#pragma unroll
-        for (int v = 0; v < PBR_NV2; ++v) {
-            const double up = __shfl_up_sync(0xffffffffu, yc[v], 1);
-            yb[v] = (lane == 0) ? prev_last[v] : up;
-            prev_last[v] = __shfl_sync(0xffffffffu, yc[v], 31);
-        }
+        __syncthreads();
+        // pressure entering this warp = maps of the earlier warps of the round applied to the round's carry
+        double Pin = s_carry;
+        for (int w2 = 0; w2 < wid; ++w2) Pin = s_wa[w2]*Pin + s_wb[w2];
+        const double Pz = (z == 0) ? pp.Pf : ae*Pin + be;
+        __syncthreads();
+        if (tid == 127) s_carry = a*Pin + b;                         // pressure after the round's last node
         if (act) {
             double f[PBR_NV2];
-            pbr_n2_node<false>(yc, yb, z == 0, Pz, inv_dz, p, f, ns, (double*)0);
+            pbr_n2_node<false>(yc, yb, z == 0, Pz, inv_dz, pp, f, ns, (double*)0);
+            double* dYi = dY + (g0 + g)*(long)PBR_NV2*zNo;
 #pragma unroll
             for (int v = 0; v < PBR_NV2; ++v) dYi[(long)v*zNo + z] = f[v];
         }
-        Pcarry = Pnext;
     }
 }
 

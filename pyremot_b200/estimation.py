@@ -1,0 +1,42 @@
+"""Parameter-estimation support (BASELINE config 5): finite-difference sensitivities of the N1 outlet with respect to
+kinetic constants, evaluated as ONE ensemble launch.
+
+The reference has no estimation code ("parameter estimation" appears only as prose in `README.md:8`); what an
+estimator needs from this path is the outlet vector of many reactors under perturbed kinetic constants.  The constants are
+scalar entries of the ``VARS`` dict promoted to per-instance runtime parameters (``params=``), so the base case and all
+perturbed variants of all reactors run through the same compiled kernel without recompiling.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def perturbation_table(model, modelInput, sweep, theta, rel=1e-4):
+    """inst_in rows for N base reactors followed by len(theta) blocks of N rows with theta_k*(1+rel).
+
+    ``theta``: ordered names of scalar VARS entries (must be the model's ``params``).  Returns (table, steps[k])."""
+    base = model.instance_table(modelInput, sweep)
+    N = base.shape[0]
+    cols = [9 + model.n + model.params.index(name) for name in theta]
+    blocks, steps = [base], []
+    for c in cols:
+        t = base.copy()
+        h = t[:, c]*rel
+        t[:, c] += h
+        blocks.append(t)
+        steps.append(h)
+    return np.concatenate(blocks, axis=0), np.stack(steps, axis=1), N
+
+
+def outlet_jacobian_fd(modelInput, sweep, theta, rel=1e-4, rtol=1e-11, atol=1e-15, device=0):
+    """d(outlet)/d(theta_k) [N, nv1, p] by forward differences; solver tolerance tight enough that integration
+    noise stays below the perturbation.  Also returns the base outlets [N, nv1]."""
+    from .api import get_model
+    model = get_model(modelInput, params=tuple(theta), device=device)
+    tab, steps, N = perturbation_table(model, modelInput, sweep, theta, rel)
+    r = model.solve_n1_host(tab, rtol=rtol, atol=atol, n_out=2, profile=False)
+    if (r["status"] != 0).any():
+        raise RuntimeError(f"{int((r['status'] != 0).sum())} of {len(tab)} perturbed solves failed")
+    out = r["outlet"].reshape(1 + len(theta), N, model.nv1)
+    J = (out[1:] - out[0][None])/np.moveaxis(steps, 1, 0)[:, :, None]
+    return np.moveaxis(J, 0, 2), out[0]

@@ -89,3 +89,18 @@ def test_instance_table_and_reaction_tables():
     assert np.array_equal(S2, [[1, 1, -1]]) and np.isclose(dH2[0], -41160)
     from pyremot_b200 import rmtCom
     assert rmtCom() == "CO2,H2,CH3OH,H2O,CO,DME,N2,CH4,C2H4,C3H6,C3H8,C4H10"
+
+
+def test_perturbation_table_for_parameter_estimation():
+    from pyremot_b200 import estimation
+    mi = cases.readme_case("N1", theta_as_vars=True)
+    theta = list(cases.MEOH_DME_THETA)
+    m = engine.Model(mi, params=theta, device=None)
+    rows = cases.ensemble_rows(5)
+    tab, steps, N = estimation.perturbation_table(m, mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}, theta, 1e-4)
+    assert tab.shape == (5*7, 21) and N == 5 and steps.shape == (5, 6)
+    assert np.array_equal(tab[:5], tab[5:10][:, :].copy()*0 + tab[:5])            # base block untouched
+    for k in range(6):
+        blk = tab[5*(k+1):5*(k+2)]
+        diff = blk - tab[:5]
+        assert np.count_nonzero(diff) == 5 and np.allclose(diff[:, 15 + k], tab[:5, 15 + k]*1e-4, rtol=1e-12)

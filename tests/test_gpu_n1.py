@@ -200,3 +200,27 @@ def test_full_size_ensemble_properties(torch_cuda):
     ens = O.Ensemble(mi, {k: v[idx] for k, v in sweep.items()})
     _, ref, _ = O.solve_n1(ens, method="BDF", rtol=1e-11, atol=1e-14)
     assert relerr(out["outlet"][idx], ref[:, :, -1]) < RTOL_SOLVE
+
+
+def test_parameter_estimation_fd_jacobian(torch_cuda):
+    """BASELINE config 5 mechanism: d(outlet)/d(theta) for the six kinetic constants from one ensemble launch
+    (N x 7 solves), against the oracle differentiated the same way (SciPy at converged tolerance)."""
+    from pyremot_b200 import estimation
+    mi = cases.readme_case("N1", theta_as_vars=True)
+    theta = list(cases.MEOH_DME_THETA)
+    rows = cases.ensemble_rows(512)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    J, base = estimation.outlet_jacobian_fd(mi, sweep, theta, rel=1e-4)
+    assert J.shape == (512, 8, 6) and np.isfinite(J).all()
+    i = 17
+    sw1 = {k: v[[i]] for k, v in sweep.items()}
+    _, ref0, _ = O.solve_n1(O.Ensemble(mi, sw1), method="BDF", rtol=1e-12, atol=1e-15)
+    assert relerr(base[i], ref0[0, :, -1]) < RTOL_SOLVE
+    for k in (0, 2, 5):                  # K1, K3 pre-exponentials and the CO adsorption constant
+        h = cases.MEOH_DME_THETA[theta[k]]*1e-4
+        sw = dict(sw1)
+        sw["VARS:" + theta[k]] = np.array([cases.MEOH_DME_THETA[theta[k]] + h])
+        _, refk, _ = O.solve_n1(O.Ensemble(mi, sw), method="BDF", rtol=1e-12, atol=1e-15)
+        Jref = (refk[0, :, -1] - ref0[0, :, -1])/h
+        scale = np.max(np.abs(Jref[:6]))
+        assert np.max(np.abs(J[i, :6, k] - Jref[:6])) < 2e-3*scale        # FD noise: 1e-11/1e-4 relative
