@@ -106,7 +106,7 @@ int pbr_solve_n1_host(pbr_ctx* ctx, long N, const double* inst_in_host, double r
  * (:3609) restarted from the previous end state; variable-order BDF, one warp per reactor, block lower-bidiagonal
  * Newton matrix (per-node LU + forward substitution along the bed).  IV = feed-filled bed (:3483-3497).
  *   snaps_y_dev [N][tNo][nv2][zNo] scaled state at the interval ends;  status_dev [N];  stats_dev [4][N] or NULL.
- * Scratch ((13*nv2 + nv2^2 + 1)*zNo doubles per resident warp) is owned by the context. */
+ * Scratch ((13*nv2 + 2*nv2^2 + 1)*zNo doubles per resident warp) is owned by the context. */
 int pbr_solve_n2(pbr_ctx* ctx, long N, int zNo, int tNo, double period, const double* inst_par_dev, double rtol,
                  double atol, int max_steps, double* snaps_y_dev, int* status_dev, int* stats_dev, void* stream);
 

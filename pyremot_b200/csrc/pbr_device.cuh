@@ -600,6 +600,12 @@ struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
 #ifndef PBR_JAC_PERIOD
 #define PBR_JAC_PERIOD 1
 #endif
+// Order / step-size selection is only allowed on every PBR_SEL_PERIOD-th trip (same trips for all lanes): the
+// history rescale that follows is ~600 instructions and, decided per lane, would run on almost every trip for a
+// handful of lanes (measured: 17 % of the warp instructions executed with 4-7 active lanes).
+#ifndef PBR_SEL_PERIOD
+#define PBR_SEL_PERIOD 6
+#endif
 #ifndef PBR_NEWTON_SKIP
 #define PBR_NEWTON_SKIP 1
 #endif
@@ -799,7 +805,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
                 next_out++;
             }
             // order / step selection (bdf.py:426-455) only where the change can be applied on the very next trip
-            if (n_equal >= order + 1 && (trip % PBR_JAC_PERIOD) == 0) {
+            if (n_equal >= order + 1 && (trip % PBR_SEL_PERIOD) == 0) {
                 const double fm = (order > 1) ? pbr_fpow(sqrt(em/NV), -1.0/order) : 0.0;
                 const double f0 = pbr_fpow(err_norm, -1.0/(order + 1));      // err_norm == 0 -> inf, as in scipy
                 const double fp = (order < PBR_MAXORD) ? pbr_fpow(sqrt(ep/NV), -1.0/(order + 2)) : 0.0;
@@ -831,11 +837,14 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
 // marched along the bed, the owner lane of node z solving and broadcasting x_z to the warp.
 //
 // Scratch (global memory, private to the warp, element (k, z) at ws[k*zNo + z]):
-//   D[PBR_DROWS][NV2] | y[NV2] | d[NV2] | psi[NV2] | scl[NV2] | b[NV2] | sub[NV2] | LU[NV2*NV2] | piv[1]
+//   D[PBR_DROWS][NV2] | y[NV2] | d[NV2] | psi[NV2] | scl[NV2] | b[NV2] | sub[NV2] | LU[NV2*NV2] | piv[1] | G[NV2*NV2]
+//   with G_z = A_z^{-1} c diag(sub_z), so that the serial part of the march is one small mat-vec per node.
 // =====================================================================================================
-#define PBR_N2_WS_ROWS ((PBR_DROWS + 6)*PBR_NV2 + PBR_NV2*PBR_NV2 + 1)
+#define PBR_N2_WS_ROWS ((PBR_DROWS + 6)*PBR_NV2 + 2*PBR_NV2*PBR_NV2 + 1)
 
+#define PBR_N2_TILE_ROWS (PBR_NV2*PBR_NV2 + 2*PBR_NV2)     // per node: G block, g = A^{-1} b, scl (staged in shared memory)
 struct WarpCtx {
+    double* tile;           // [PBR_N2_TILE_ROWS][NL] staging area of the warp (shared memory on the device)
 #ifdef PBR_HOST
     int lane; enum { NL = 1 };
     double sum(double x) const { return x; }
@@ -874,6 +883,7 @@ struct N2Ws {            // views into the warp's scratch
     PBR_DEV double* vec(int which, int v) const { return base + (long)((PBR_DROWS + which)*PBR_NV2 + v)*zNo; }   // 0 y,1 d,2 psi,3 scl,4 b,5 sub
     PBR_DEV double* lu() const { return base + (long)(PBR_DROWS + 6)*PBR_NV2*zNo; }
     PBR_DEV double* piv() const { return lu() + (long)PBR_NV2*PBR_NV2*zNo; }
+    PBR_DEV double* G() const { return piv() + zNo; }
 };
 
 struct Lu2Store {        // Jacobian entries of one node -> I - c*J in the node's strided LU block
@@ -914,7 +924,9 @@ PBR_DEV bool pbr_n2_sweep_eval(const WarpCtx& w, const InstPar& p, const N2Ws& w
         if (act) {
             double f[PBR_NV2], sub[PBR_NV2];
             if (JAC) {
-                const Strided blk = {ws.lu() + z, zNo};
+                // the node's Newton block is built, factorised and used out of the warp's shared-memory tile (this
+                // lane's column); LU and G go to the global scratch afterwards with coalesced, fire-and-forget stores
+                const Strided blk = {w.tile + w.lane, WarpCtx::NL};
                 Lu2Store st = {blk, c};
                 pbr_n2_node<true>(yc, yb, z == 0, Pz, inv_dz, p, f, st, sub);
                 unsigned long long piv;
@@ -922,6 +934,20 @@ PBR_DEV bool pbr_n2_sweep_eval(const WarpCtx& w, const InstPar& p, const N2Ws& w
                 ws.piv()[z] = (double)piv;
 #pragma unroll
                 for (int v = 0; v < PBR_NV2; ++v) ws.vec(5, v)[z] = sub[v];
+                // G_z = A_z^{-1} c diag(sub_z): column k is the solve of c*sub_k*e_k (zero for the inlet node / clamped upstream)
+                double* Gz = ws.G() + z;
+#pragma unroll 1
+                for (int k = 0; k < PBR_NV2; ++k) {
+                    double col[PBR_NV2];
+#pragma unroll
+                    for (int i = 0; i < PBR_NV2; ++i) col[i] = (i == k) ? c*sub[k] : 0.0;
+                    if (sub[k] != 0.0) pbr_lu_solve<PBR_NV2>(blk, piv, col);
+#pragma unroll
+                    for (int i = 0; i < PBR_NV2; ++i) Gz[(long)(i*PBR_NV2 + k)*zNo] = col[i];
+                }
+                double* lu = ws.lu() + z;
+#pragma unroll 7
+                for (int e = 0; e < PBR_NV2*PBR_NV2; ++e) lu[(long)e*zNo] = blk[e];
             } else {
                 NoStore ns;
                 pbr_n2_node<false>(yc, yb, z == 0, Pz, inv_dz, p, f, ns, (double*)0);
@@ -938,34 +964,64 @@ PBR_DEV bool pbr_n2_sweep_eval(const WarpCtx& w, const InstPar& p, const N2Ws& w
     return w.sum(bad) == 0.0;
 }
 
-// Block forward substitution: dy_z = A_z^{-1}(b_z + c sub_z*dy_{z-1}); applies the Newton update y += dy, d += dy
-// and returns sum_z sum_v (dy/scale)^2.
+// Block forward substitution: dy_z = A_z^{-1}(b_z + c sub_z*dy_{z-1}) = g_z + G_z dy_{z-1}; applies the Newton update
+// y += dy, d += dy and returns sum_z sum_v (dy/scale)^2.  The march is serial in z, so everything that does not depend
+// on dy_{z-1} is done in parallel first: per chunk of 32 nodes every lane solves g_z = A_z^{-1} b_z for its node and
+// stages g_z, G_z and the scale into the warp's shared-memory tile; the owner lanes then only do a 7x7 mat-vec out of
+// shared memory and hand dy_z to the next lane by shuffle.
 PBR_DEV double pbr_n2_newton_solve(const WarpCtx& w, const N2Ws& ws, double c) {
     const int zNo = ws.zNo;
+    const int NL = WarpCtx::NL, NV = PBR_NV2;
     double xprev[PBR_NV2];
 #pragma unroll
-    for (int v = 0; v < PBR_NV2; ++v) xprev[v] = 0.0;
+    for (int v = 0; v < NV; ++v) xprev[v] = 0.0;
     double nrm = 0.0;
-    for (int z = 0; z < zNo; ++z) {
-        const int owner = z % WarpCtx::NL;
-        double x[PBR_NV2];
+    const Strided T = {w.tile + w.lane, NL};
+    for (int z0 = 0; z0 < zNo; z0 += NL) {
+        const int z = z0 + w.lane;
+        const bool act = z < zNo;
+        w.sync();
+        if (act) {
+            // stage this node's LU block into the lane's tile column, solve g = A^{-1} b out of shared memory, then
+            // replace the block by G (only this lane reads its column before the barrier below)
+            double g[PBR_NV2];
+            const double* lu = ws.lu() + z;
+#pragma unroll 7
+            for (int e = 0; e < NV*NV; ++e) T[e] = lu[(long)e*zNo];
 #pragma unroll
-        for (int v = 0; v < PBR_NV2; ++v) x[v] = 0.0;
-        if (w.lane == owner) {
+            for (int v = 0; v < NV; ++v) g[v] = ws.vec(4, v)[z];
+            pbr_lu_solve<PBR_NV2>(T, (unsigned long long)ws.piv()[z], g);
+            const double* Gz = ws.G() + z;
+#pragma unroll 7
+            for (int e = 0; e < NV*NV; ++e) T[e] = Gz[(long)e*zNo];
 #pragma unroll
-            for (int v = 0; v < PBR_NV2; ++v) x[v] = ws.vec(4, v)[z] + c*ws.vec(5, v)[z]*xprev[v];
-            const Strided blk = {ws.lu() + z, zNo};
-            pbr_lu_solve<PBR_NV2>(blk, (unsigned long long)ws.piv()[z], x);
-#pragma unroll
-            for (int v = 0; v < PBR_NV2; ++v) {
-                ws.vec(0, v)[z] += x[v];
-                ws.vec(1, v)[z] += x[v];
-                const double e = x[v]/ws.vec(3, v)[z];
-                nrm += e*e;
-            }
+            for (int v = 0; v < NV; ++v) { T[NV*NV + v] = g[v]; T[NV*NV + NV + v] = ws.vec(3, v)[z]; }
         }
+        w.sync();
+        const int nact = (zNo - z0 < NL) ? (zNo - z0) : NL;
+        for (int l = 0; l < nact; ++l) {
+            double x[PBR_NV2];
 #pragma unroll
-        for (int v = 0; v < PBR_NV2; ++v) xprev[v] = w.bcast(x[v], owner);
+            for (int v = 0; v < NV; ++v) x[v] = 0.0;
+            if (w.lane == l) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    double acc = T[NV*NV + i];
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) acc += T[i*NV + k]*xprev[k];
+                    x[i] = acc;
+                }
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    ws.vec(0, v)[z] += x[v];
+                    ws.vec(1, v)[z] += x[v];
+                    const double e = x[v]/T[NV*NV + NV + v];
+                    nrm += e*e;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < NV; ++v) xprev[v] = w.bcast(x[v], l);
+        }
     }
     return w.sum(nrm);
 }
@@ -1399,9 +1455,11 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
 extern "C" __global__ void __launch_bounds__(128) pbr_k4_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                   double rtol, double atol, int max_steps, double* __restrict__ work,
                                                                   double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
+    extern __shared__ double pbr_smem[];
     const long gw = ((long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     const long G = ((long)gridDim.x*blockDim.x) >> 5;
     WarpCtx w; w.lane = threadIdx.x & 31;
+    w.tile = pbr_smem + (long)(threadIdx.x >> 5)*PBR_N2_TILE_ROWS*32;
     const N2Ws ws = {work + gw*(long)PBR_N2_WS_ROWS*zNo, zNo};
     for (long inst = gw; inst < N; inst += G) {
         InstPar p; pbr_load_par(par, N, inst, p);

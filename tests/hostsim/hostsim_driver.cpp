@@ -90,7 +90,8 @@ void hs_solve_n2(long N, int zNo, int tNo, double period, const double* par, dou
     std::vector<double> work((size_t)PBR_N2_WS_ROWS*zNo);
     for (long i = 0; i < N; ++i) {
         InstPar p; pbr_load_par(par, N, i, p);
-        WarpCtx w; w.lane = 0;
+        std::vector<double> tile(PBR_N2_TILE_ROWS);
+        WarpCtx w; w.lane = 0; w.tile = tile.data();
         N2Ws ws = {work.data(), zNo};
         N2Stats st;
         status[i] = pbr_n2_solve(w, p, ws, tNo, period, rtol, atol, max_steps, snaps + i*(long)tNo*PBR_NV2*zNo, st);

@@ -1,0 +1,24 @@
+"""Short N2 solve for ncu: python tools/prof_n2.py [N] [zNo] [tNo] [period]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from pyremot_b200 import cases  # noqa: E402
+from pyremot_b200.api import get_model  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
+zNo = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+tNo = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+period = float(sys.argv[4]) if len(sys.argv) > 4 else 0.1
+mi = cases.readme_case("N2")
+m = get_model(mi)
+rows = cases.ensemble_rows(N)
+tab = torch.from_numpy(m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]})).cuda()
+par = m.prolog(tab)
+for _ in range(2):
+    r = m.solve_n2(par, zNo, tNo, period)
+torch.cuda.synchronize()
+st = r["stats"].cpu().numpy()
+print("N2", N, zNo, "failed", int((r["status"] != 0).sum()), "mean steps", st[0].mean(), "nfev", st[2].mean())
