@@ -146,29 +146,39 @@ def rmtExe(modelInput, device=0):
 
 
 def rmtExeBatch(modelInput, sweep, params=(), device=0, rtol=None, atol=None, profile=False, n_out=None,
-                return_device=False):
+                return_device=False, strict=False):
     """Ensemble entry (new): solve N reactor instances that share ``modelInput``'s static part.
 
-    ``sweep``: dict of per-instance arrays (see ``engine.Model.instance_table``).  N1 only for now.
-    Returns dict(outlet [N, nv1] = last column of each instance's dataYs, dataYs [N, nv1, K] if profile,
-    status [N], stats [4, N]) as numpy arrays (torch CUDA tensors if ``return_device``).
+    ``sweep``: dict of per-instance arrays (see ``engine.Model.instance_table``).
+    N1: returns dict(outlet [N, nv1] = last column of each instance's dataYs, dataYs [N, nv1, K] if profile,
+    status [N], stats [4, N]).  N2: dict(dataYs [N, tNo, n+1, zNo], snaps_y (scaled), status, stats); grid sizes from
+    ``solverSetting['N2']``.  numpy arrays (torch CUDA tensors if ``return_device``, N1 only).
+    Per-instance failures are reported in ``status`` (engine codes PBR_INST_*); ``strict=True`` raises instead.
     """
     import torch
-    if modelInput["model"] != "N1":
-        raise NotImplementedError("rmtExeBatch: N1 only")
     r0, a0 = _tolerances(modelInput)
     rtol = r0 if rtol is None else rtol
     atol = a0 if atol is None else atol
     model = get_model(modelInput, params=params, device=device)
-    K = n_out or (solverSetting["N1"]["zNo"] + 1)
     tab = model.instance_table(modelInput, sweep)
-    if not return_device:
-        r = model.solve_n1_host(tab, rtol=rtol, atol=atol, n_out=K, profile=profile)
-        return r
-    tab = torch.from_numpy(tab).to(model._dev())
-    par = model.prolog(tab)
-    res = model.solve_n1(par, rtol=rtol, atol=atol, n_out=K, profile=profile)
-    out = {"outlet": model.unscale_n1(par, res["outlet_y"][None])[:, :, 0], "status": res["status"], "stats": res["stats"]}
-    if profile:
-        out["dataYs"] = model.unscale_n1(par, res["prof_y"])
-    return out
+    if modelInput["model"] == "N2":
+        s2 = solverSetting["N2"]
+        r = model.solve_n2_host(tab, s2["zNo"], s2["tNo"], modelInput["operating-conditions"]["period"], rtol=rtol, atol=atol)
+    elif modelInput["model"] == "N1":
+        K = n_out or (solverSetting["N1"]["zNo"] + 1)
+        if not return_device:
+            r = model.solve_n1_host(tab, rtol=rtol, atol=atol, n_out=K, profile=profile)
+        else:
+            tab = torch.from_numpy(tab).to(model._dev())
+            par = model.prolog(tab)
+            res = model.solve_n1(par, rtol=rtol, atol=atol, n_out=K, profile=profile)
+            r = {"outlet": model.unscale_n1(par, res["outlet_y"][None])[:, :, 0], "status": res["status"], "stats": res["stats"]}
+            if profile:
+                r["dataYs"] = model.unscale_n1(par, res["prof_y"])
+    else:
+        raise NotImplementedError("rmtExeBatch: models N1 and N2 only")
+    if strict:
+        bad = int((r["status"] != 0).sum())
+        if bad:
+            raise RuntimeError(f"{bad} of {len(tab)} reactor instances failed to integrate")
+    return r

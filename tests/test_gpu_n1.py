@@ -224,3 +224,28 @@ def test_parameter_estimation_fd_jacobian(torch_cuda):
         Jref = (refk[0, :, -1] - ref0[0, :, -1])/h
         scale = np.max(np.abs(Jref[:6]))
         assert np.max(np.abs(J[i, :6, k] - Jref[:6])) < 2e-3*scale        # FD noise: 1e-11/1e-4 relative
+
+
+def test_failures_are_reported_per_instance_not_hung(torch_cuda):
+    """Broken inputs must terminate with a status code (bounded step attempts), and must not disturb their neighbours."""
+    from pyremot_b200 import rmtExeBatch
+    mi = cases.readme_case("N1")
+    rows = cases.ensemble_rows(64)
+    sweep = {"T": rows["T"].copy(), "P": rows["P"].copy(), "conc": rows["conc"].copy(), "Tm": rows["T"].copy()}
+    good = rmtExeBatch(mi, sweep)
+    sweep["T"][5] = float("nan")
+    sweep["conc"][9] = 0.0                       # empty feed: Ct0 = 0 -> non-finite constants
+    sweep["P"][33] = -5e6
+    out = rmtExeBatch(mi, sweep)
+    bad = {5, 9, 33}
+    assert all(out["status"][i] != 0 for i in bad)
+    ok = [i for i in range(64) if i not in bad]
+    assert (out["status"][ok] == 0).all()
+    assert np.array_equal(out["outlet"][ok], good["outlet"][ok])
+    with pytest.raises(RuntimeError, match="3 of 64"):
+        rmtExeBatch(mi, sweep, strict=True)
+    # N = 1 and an N that is not a multiple of the block size
+    one = rmtExeBatch(mi, {k: v[:1] for k, v in sweep.items()})
+    assert np.array_equal(one["outlet"], good["outlet"][:1])
+    odd = rmtExeBatch(mi, {k: v[10:33] for k, v in sweep.items()})
+    assert np.array_equal(odd["outlet"], good["outlet"][10:33])

@@ -92,3 +92,22 @@ def test_n2_more_instances_than_resident_warps():
     ens.period = 0.2
     _, ref, _ = O.solve_n2(ens, zNo=zNo, tNo=2, method="BDF", rtol=1e-9, atol=1e-13, sparse=True)
     assert relerr(r["dataYs"][[2999]], ref) < RTOL_SOLVE
+
+
+def test_rmtExeBatch_n2_and_failure_status():
+    import pyremot_b200
+    from pyremot_b200 import rmtExeBatch
+    mi = cases.readme_case("N2")
+    rows = cases.ensemble_rows(8)
+    sweep = {"T": rows["T"].copy(), "P": rows["P"].copy(), "conc": rows["conc"].copy(), "Tm": rows["T"].copy()}
+    saved = dict(pyremot_b200.solverSetting["N2"])
+    try:
+        pyremot_b200.solverSetting["N2"].update({"zNo": 16, "tNo": 2})
+        good = rmtExeBatch(mi, sweep)
+        sweep["T"][3] = float("nan")
+        out = rmtExeBatch(mi, sweep)
+    finally:
+        pyremot_b200.solverSetting["N2"].update(saved)
+    assert good["dataYs"].shape == (8, 2, 7, 16) and (good["status"] == 0).all()
+    assert out["status"][3] != 0 and (np.delete(out["status"], 3) == 0).all()
+    assert np.array_equal(np.delete(out["dataYs"], 3, axis=0), np.delete(good["dataYs"], 3, axis=0))
