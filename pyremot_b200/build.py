@@ -18,21 +18,21 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 
 
 def _embed():
-    src = open(os.path.join(CSRC, "pbr_device.cuh")).read()
-    assert ')PBRSRC"' not in src
-    out = os.path.join(CSRC, "pbr_device_src.inc")
-    txt = 'R"PBRSRC(' + src + ')PBRSRC"\n'
-    if not os.path.exists(out) or open(out).read() != txt:
-        with open(out, "w") as f:
-            f.write(txt)
-    return out
+    for name in ("pbr_device", "pbr_math"):
+        src = open(os.path.join(CSRC, name + ".cuh")).read()
+        assert ')PBRSRC"' not in src
+        out = os.path.join(CSRC, name + "_src.inc")
+        txt = 'R"PBRSRC(' + src + ')PBRSRC"\n'
+        if not os.path.exists(out) or open(out).read() != txt:
+            with open(out, "w") as f:
+                f.write(txt)
 
 
 def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, "pbr_api.cu"), os.path.join(CSRC, "pbr_device.cuh"),
+    deps = [os.path.join(CSRC, "pbr_api.cu"), os.path.join(CSRC, "pbr_device.cuh"), os.path.join(CSRC, "pbr_math.cuh"),
             os.path.join(os.path.dirname(HERE), "include", "pbr.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 

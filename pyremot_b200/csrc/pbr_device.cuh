@@ -48,7 +48,16 @@ struct InstPar {
     double c0[PBR_NC];
     double rp[PBR_NPA];
     const double* src; long srcN, srci;        // where it was loaded from (for out-of-line helpers)
+    // per-instance reciprocals / ratios, derived once at load time (an FP64 divide is ~15 instructions per use)
+    double iG, iGH, irho0, iCp0, F1, zP, vz;
 };
+
+PBR_DEV void pbr_derive_par(InstPar& p) {
+    p.iG = 1.0/p.G; p.iGH = 1.0/p.GH; p.irho0 = 1.0/p.rho0; p.iCp0 = 1.0/p.Cpmix0;
+    p.F1 = 1.0/(p.eps*(p.zf/p.vs0));           // :4075
+    p.zP = p.zf/p.Pf;                          // :3219
+    p.vz = p.vs0/p.zf;
+}
 
 PBR_DEV void pbr_load_par(const double* __restrict__ par, long N, long i, InstPar& p) {
     p.src = par; p.srcN = N; p.srci = i;
@@ -62,6 +71,7 @@ PBR_DEV void pbr_load_par(const double* __restrict__ par, long N, long i, InstPa
     for (int k = 0; k < PBR_NC; ++k) p.c0[k] = par[(PAR_C0 + k)*N + i];
 #pragma unroll
     for (int k = 0; k < PBR_NP; ++k) p.rp[k] = par[(PAR_RP + k)*N + i];
+    pbr_derive_par(p);
 }
 
 #ifdef PBR_HOST
@@ -239,22 +249,22 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
     pbr_point<JAC>(y, T, P, p, e);
     const double w = (e.Ct/p.Ct0)*(p.Pf/P);                            // :3180 v/v0 (interstitial == superficial ratio)
     const double vs = p.vs0*w;                                         // :3184
-    const double zP = p.zf/p.Pf;                                       // :3219
+    const double zP = p.zP;                                            // :3219
     f[n] = -(p.E1*vs + p.E2*e.rho*vs*vs)*zP;                           // :3214-3220
     const double invGw = 1.0/(p.G*w);                                  // :3283, :3288
 #pragma unroll
     for (int i = 0; i < n; ++i) f[i] = e.ri[i]*invGw;
     double Den = 1.0, fth = 0.0;
     if (!PBR_ISO) {
-        const double Num = (-e.Hsum + e.Q)/p.GH;                       // :3298
-        Den = (e.rho/p.rho0)*((e.Cpmix/p.Cpmix0)*p.eps)*w;             // :3284
+        const double Num = (-e.Hsum + e.Q)*p.iGH;                      // :3298
+        Den = (e.rho*p.irho0)*((e.Cpmix*p.iCp0)*p.eps)*w;              // :3284
         fth = Num/Den;
         f[n + 1] = fth;
     }
     if (JAC) {
         // reciprocals once: an FP64 divide costs ~12 instructions and the columns below would need ~40 of them
         const double cmct = p.Cmax*e.invCt;
-        const double iGH = 1.0/p.GH, iDen = 1.0/Den, irho = 1.0/e.rho, iCp = PBR_ISO ? 1.0 : 1.0/e.Cpmix, ipr = 1.0/pr;
+        const double iGH = p.iGH, iDen = 1.0/Den, irho = 1.0/e.rho, iCp = PBR_ISO ? 1.0 : 1.0/e.Cpmix, ipr = 1.0/pr;
         const double dfp_dw = -zP*(p.E1*p.vs0 + 2.0*p.E2*e.rho*p.vs0*p.vs0*w);
         const double dfp_drho = -zP*(p.E2*vs*vs);
         const double rhoM = e.rho/e.M;
@@ -355,8 +365,8 @@ PBR_DEV double pbr_n2_node(const double* yc, const double* yb, bool first, doubl
     PointEval e;
     pbr_point<JAC>(c, T, Pz, p, e);
     const double slope = -(p.E1*p.vs0 + p.E2*e.rho*p.vs0*p.vs0);                // :3970-3974 (v == vs0, :3937)
-    const double F1 = 1.0/(p.eps*(p.zf/p.vs0));                                 // :4075
-    const double invG = 1.0/p.G;
+    const double F1 = p.F1;                                                     // :4075
+    const double invG = p.iG;
 #pragma unroll
     for (int i = 0; i < n; ++i) {
         const double cb = first ? p.c0[i] : fmax(yb[i], PBR_EPS);              // :4088-4093
@@ -365,17 +375,17 @@ PBR_DEV double pbr_n2_node(const double* yc, const double* yb, bool first, doubl
     }
     double D2 = 1.0, heat = 0.0, rs = 1.0, cps = 1.0;
     if (!PBR_ISO) {
-        rs = e.rho/p.rho0; cps = e.Cpmix/p.Cpmix0;
-        D2 = rs*cps*p.eps*(p.zf/p.vs0);                                         // 1/const_T2 :4077
+        rs = e.rho*p.irho0; cps = e.Cpmix*p.iCp0;
+        D2 = rs*cps*p.eps/p.vz;                                                 // 1/const_T2 :4077
         const double thb = first ? 0.0 : yb[n];                                 // :4106-4111
         const double conv = -1.0*rs*(cps*p.eps)*((th - thb)*inv_dz);            // :4116
-        heat = (1.0/p.GH)*(-e.Hsum) + (1.0/p.GH)*e.Q;                           // :4118-4120
+        heat = p.iGH*(-e.Hsum) + p.iGH*e.Q;                                     // :4118-4120
         f[n] = (conv + heat)/D2;                                                // :4125
-        if (JAC) sub[n] = first ? 0.0 : (p.vs0/p.zf)*inv_dz;
+        if (JAC) sub[n] = first ? 0.0 : p.vz*inv_dz;
     }
     if (JAC) {
         double drk[PBR_NR], dri[PBR_NC];
-        const double iGH = 1.0/p.GH, iD2 = 1.0/D2, iM = 1.0/e.M, iCp = PBR_ISO ? 1.0 : 1.0/e.Cpmix;
+        const double iGH = p.iGH, iD2 = 1.0/D2, iM = 1.0/e.M, iCp = PBR_ISO ? 1.0 : 1.0/e.Cpmix;
         const double hD2 = heat*iD2;
 #pragma unroll
         for (int k = 0; k < n; ++k) {
@@ -407,7 +417,7 @@ PBR_DEV double pbr_n2_node(const double* yc, const double* yb, bool first, doubl
             const double dQ = (p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
             const double dheat = (-s + dQ)*iGH;
             const double dD2 = D2*(-p.Tf/T + p.Tf*e.dCpmixT*iCp);
-            st(n, n, -(p.vs0/p.zf)*inv_dz + (dheat - hD2*dD2)*iD2);
+            st(n, n, -p.vz*inv_dz + (dheat - hD2*dD2)*iD2);
         }
     }
     return slope;
@@ -915,9 +925,8 @@ PBR_DEV bool pbr_n2_sweep_eval(const WarpCtx& w, const InstPar& p, const N2Ws& w
             double Ct = 0.0, M = 0.0;
 #pragma unroll
             for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yc[i], PBR_EPS)*p.Cmax; Ct += C; M += C*PBR_MW[i]; }
-            M = (M/Ct)*1e-3;
             const double th = PBR_ISO ? 0.0 : yc[PBR_ISO ? 0 : PBR_NC];
-            a = 1.0 - dz*p.E2*p.vs0*p.vs0*M/(PBR_R*(th*p.Tf + p.Tf));
+            a = 1.0 - dz*p.E2*p.vs0*p.vs0*(M*1e-3)/(Ct*(PBR_R*(th*p.Tf + p.Tf)));
             b = -dz*p.E1*p.vs0;
         }
         const double Pz = w.scan_affine(a, b, Pcarry);
@@ -1379,15 +1388,26 @@ extern "C" __global__ void __launch_bounds__(256) pbr_k5_unscale_n1(long N, int 
 #define PBR_K3_MINBLOCKS 4       // 4 blocks x 4 warps per SM (<=128 registers/thread)
 #endif
 #define PBR_K3_MAXG 16
+#define PBR_K3_SPAR (PBR_KPAR + 7)      // staged constants per reactor: the table rows + the derived reciprocals
 extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n2(long N, int zNo, int G, const double* __restrict__ par,
                                                                                   const double* __restrict__ Y, double* __restrict__ dY) {
-    __shared__ double s_par[PBR_K3_MAXG*PBR_KPAR];
+    __shared__ double s_par[PBR_K3_MAXG*PBR_K3_SPAR];
     __shared__ double s_wa[4], s_wb[4], s_carry;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long g0 = (long)blockIdx.x*G;
     const int Gb = (int)((N - g0 < G) ? (N - g0) : G);                // reactors in this block
-    for (int k = tid; k < Gb*PBR_KPAR; k += 128) { const int g = k / PBR_KPAR, r = k % PBR_KPAR; s_par[k] = par[(long)r*N + g0 + g]; }
+    for (int k = tid; k < Gb*PBR_KPAR; k += 128) { const int g = k / PBR_KPAR, r = k % PBR_KPAR; s_par[g*PBR_K3_SPAR + r] = par[(long)r*N + g0 + g]; }
     if (tid == 0) s_carry = 0.0;
+    __syncthreads();
+    if (tid < Gb) {                                                    // derived reciprocals once per reactor
+        double* sp = s_par + tid*PBR_K3_SPAR;
+        InstPar q;
+        q.G = sp[PAR_G]; q.GH = sp[PAR_GH]; q.rho0 = sp[PAR_RHO0]; q.Cpmix0 = sp[PAR_CPMIX0]; q.eps = sp[PAR_EPS];
+        q.zf = sp[PAR_ZF]; q.vs0 = sp[PAR_VS0]; q.Pf = sp[PAR_PF];
+        pbr_derive_par(q);
+        sp[PBR_KPAR + 0] = q.iG; sp[PBR_KPAR + 1] = q.iGH; sp[PBR_KPAR + 2] = q.irho0; sp[PBR_KPAR + 3] = q.iCp0;
+        sp[PBR_KPAR + 4] = q.F1; sp[PBR_KPAR + 5] = q.zP; sp[PBR_KPAR + 6] = q.vz;
+    }
     __syncthreads();
     const double dz = 1.0/(double)(zNo - 1), inv_dz = (double)(zNo - 1);   // :3439
     const int total = Gb*zNo;
@@ -1396,7 +1416,7 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
         const int q = q0 + tid;
         const bool act = q < total;
         const int g = act ? q / zNo : 0, z = act ? q - g*zNo : 1;
-        const double* sp = s_par + g*PBR_KPAR;
+        const double* sp = s_par + g*PBR_K3_SPAR;
         InstPar pp;
         pp.Tf = sp[PAR_TF]; pp.Pf = sp[PAR_PF]; pp.Cmax = sp[PAR_CMAX]; pp.Ct0 = sp[PAR_CT0]; pp.vs0 = sp[PAR_VS0]; pp.eps = sp[PAR_EPS];
         pp.zf = sp[PAR_ZF]; pp.E1 = sp[PAR_E1]; pp.E2 = sp[PAR_E2]; pp.rho0 = sp[PAR_RHO0]; pp.Cpmix0 = sp[PAR_CPMIX0]; pp.G = sp[PAR_G];
@@ -1405,6 +1425,8 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
         for (int k = 0; k < PBR_NC; ++k) pp.c0[k] = sp[PAR_C0 + k];
 #pragma unroll
         for (int k = 0; k < PBR_NP; ++k) pp.rp[k] = sp[PAR_RP + k];
+        pp.iG = sp[PBR_KPAR + 0]; pp.iGH = sp[PBR_KPAR + 1]; pp.irho0 = sp[PBR_KPAR + 2]; pp.iCp0 = sp[PBR_KPAR + 3];
+        pp.F1 = sp[PBR_KPAR + 4]; pp.zP = sp[PBR_KPAR + 5]; pp.vz = sp[PBR_KPAR + 6];
         const double* Yi = Y + (g0 + g)*(long)PBR_NV2*zNo;
         double yc[PBR_NV2], yb[PBR_NV2];
 #pragma unroll
@@ -1418,9 +1440,8 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
             double Ct = 0.0, M = 0.0;
 #pragma unroll
             for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yc[i], PBR_EPS)*pp.Cmax; Ct += C; M += C*PBR_MW[i]; }
-            M = (M/Ct)*1e-3;
             const double th = PBR_ISO ? 0.0 : yc[PBR_ISO ? 0 : PBR_NC];
-            a = 1.0 - dz*pp.E2*pp.vs0*pp.vs0*M/(PBR_R*(th*pp.Tf + pp.Tf));
+            a = 1.0 - dz*pp.E2*pp.vs0*pp.vs0*(M*1e-3)/(Ct*(PBR_R*(th*pp.Tf + pp.Tf)));
             b = -dz*pp.E1*pp.vs0;
             if (z == 0) { b = a*pp.Pf + b; a = 0.0; }                 // P_z[0] = P0 (:3848): the map forgets what came before
         }

@@ -225,11 +225,11 @@ class Model:
         self._check(lib().pbr_prolog(self._ctx, N, inst_in.data_ptr(), par.data_ptr(), self._stream()))
         return par
 
-    def rhs_n1(self, par, y):
+    def rhs_n1(self, par, y, out=None):
         import torch
         N = par.shape[1]
         assert y.shape == (self.nv1, N) and y.is_contiguous() and y.dtype == torch.float64
-        f = torch.empty_like(y)
+        f = torch.empty_like(y) if out is None else out
         self._check(lib().pbr_rhs_n1(self._ctx, N, par.data_ptr(), y.data_ptr(), f.data_ptr(), self._stream()))
         return f
 

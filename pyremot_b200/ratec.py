@@ -455,6 +455,28 @@ def _lit(v):
     return s if ("e" in s or "." in s) else s + ".0"
 
 
+class _ConstTable:
+    """Literals of the rate expressions go to a __constant__ table (PBR_K[i]) instead of the instruction stream:
+    a c[bank][offset] operand is free, a 64-bit immediate costs two extra move instructions on sm_100a."""
+
+    def __init__(self):
+        self.vals, self.idx = [], {}
+
+    def ref(self, v):
+        v = float(v)
+        if v in (0.0, 1.0, 2.0, -1.0, 0.5):          # exactly representable in the 32-bit immediate forms
+            return "(" + _lit(v) + ")" if v < 0 else _lit(v)
+        i = self.idx.get(v)
+        if i is None:
+            i = self.idx[v] = len(self.vals)
+            self.vals.append(v)
+        return f"PBR_K[{i}]"
+
+    def emit(self):
+        body = ", ".join(_lit(v) for v in self.vals) if self.vals else "0.0"
+        return f"PBR_CTABLE double PBR_K[{max(1, len(self.vals))}] = {{{body}}};"
+
+
 def _children(n):
     op = n[0]
     if op in ("const", "in"):
@@ -464,7 +486,7 @@ def _children(n):
     return (n[1],)   # neg, powi (n[2] is the integer exponent), exp, log, log10, sqrt
 
 
-def _emit_body(g, needed, lines, names):
+def _emit_body(g, needed, lines, names, ktab=None):
     """Emit SSA statements for all nodes reachable from ``needed`` (ids), in topological (= id) order."""
     live = set()
     stack = list(needed)
@@ -480,7 +502,7 @@ def _emit_body(g, needed, lines, names):
         if i in names:
             continue
         if op == "const":
-            names[i] = "(" + _lit(n[1]) + ")" if n[1] < 0 else _lit(n[1])
+            names[i] = ktab.ref(n[1]) if ktab is not None else ("(" + _lit(n[1]) + ")" if n[1] < 0 else _lit(n[1]))
             continue
         if op == "in":
             names[i] = {"T": "T", "P": "P"}.get(n[1]) or {"X": "x", "C": "C", "PAR": "par"}[n[1]] + f"[{n[2]}]"
@@ -500,9 +522,11 @@ def _emit_body(g, needed, lines, names):
                 rhs = f"1.0 / ({rhs})"
         elif op == "pow":
             if g.is_const(n[1], 10.0):
-                rhs = f"exp10({names[n[2]]})"
+                rhs = f"pbr_exp10({names[n[2]]})"
             else:
                 rhs = f"pow({a}, {names[n[2]]})"
+        elif op == "exp":
+            rhs = f"pbr_exp({a})"
         else:
             rhs = f"{op}({a})"
         names[i] = f"t{i}"
@@ -531,9 +555,11 @@ def _emit(cr):
     src.append(f"// {n0} primal nodes, {len(g.nodes)} with derivatives; params: {cr.params}")
     src.append(f"#define PBR_NP {len(cr.params)}")
     sig = "double T, double P, const double* x, const double* C, const double* par"
+    ktab = _ConstTable()
+    head = len(src)
     # values only
     lines, names = [], {}
-    _emit_body(g, outs, lines, names)
+    _emit_body(g, outs, lines, names, ktab)
     src.append(f"PBR_DEV void pbr_rates({sig}, double* r) {{")
     src.extend(lines)
     for j, o in enumerate(outs):
@@ -544,7 +570,7 @@ def _emit(cr):
     need = list(outs)
     for dj in derivs:
         need.extend(dj.values())
-    _emit_body(g, need, lines, names)
+    _emit_body(g, need, lines, names, ktab)
     src.append(f"PBR_DEV void pbr_rates_jac({sig}, double* r, double* drT, double* drP, "
                f"double (*drx)[PBR_NC], double (*drC)[PBR_NC]) {{")
     src.extend(lines)
@@ -557,4 +583,5 @@ def _emit(cr):
             src.append(f"    drx[{j}][{i}] = {names[dj[('X', i)]] if ('X', i) in dj else '0.0'};")
             src.append(f"    drC[{j}][{i}] = {names[dj[('C', i)]] if ('C', i) in dj else '0.0'};")
     src.append("}")
+    src.insert(head, ktab.emit())
     return "\n".join(src) + "\n"
