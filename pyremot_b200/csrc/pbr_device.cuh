@@ -53,10 +53,10 @@ struct InstPar {
 };
 
 PBR_DEV void pbr_derive_par(InstPar& p) {
-    p.iG = 1.0/p.G; p.iGH = 1.0/p.GH; p.irho0 = 1.0/p.rho0; p.iCp0 = 1.0/p.Cpmix0;
-    p.F1 = 1.0/(p.eps*(p.zf/p.vs0));           // :4075
-    p.zP = p.zf/p.Pf;                          // :3219
-    p.vz = p.vs0/p.zf;
+    p.iG = pbr_rcp(p.G); p.iGH = pbr_rcp(p.GH); p.irho0 = pbr_rcp(p.rho0); p.iCp0 = pbr_rcp(p.Cpmix0);
+    p.vz = p.vs0*pbr_rcp(p.zf);
+    p.F1 = p.vz*pbr_rcp(p.eps);                // 1/(eps*(zf/vs0)), :4075
+    p.zP = p.zf*pbr_rcp(p.Pf);                 // :3219
 }
 
 PBR_DEV void pbr_load_par(const double* __restrict__ par, long N, long i, InstPar& p) {
@@ -173,12 +173,12 @@ PBR_DEV void pbr_point(const double* c, double T, double P, const InstPar& p, Po
     double Ct = 0.0;
 #pragma unroll
     for (int i = 0; i < PBR_NC; ++i) { e.C[i] = c[i]*p.Cmax; Ct += e.C[i]; }      // :3161-3167
-    e.Ct = Ct; e.invCt = 1.0/Ct; e.T = T; e.P = P;
+    e.Ct = Ct; e.invCt = pbr_rcp(Ct); e.T = T; e.P = P;
     double M = 0.0;
 #pragma unroll
     for (int i = 0; i < PBR_NC; ++i) { e.x[i] = e.C[i]*e.invCt; M += e.x[i]*PBR_MW[i]; }   // :3176, :3202
     e.M = M*1e-3;
-    e.rho = P*e.M/(PBR_R*T);                                                      // rmtThermo.py:353-369
+    e.rho = P*e.M*pbr_rcp(PBR_R*T);                                               // rmtThermo.py:353-369
     if (JAC) pbr_rates_jac(T, P, e.x, e.C, p.rp, e.r, e.drT, e.drP, e.drx, e.drC);
     else     pbr_rates(T, P, e.x, e.C, p.rp, e.r);                                // rmtReaction.py:11-61
 #pragma unroll
@@ -247,27 +247,27 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
     const double P = pr*p.Pf;                                          // :3173
     PointEval e;
     pbr_point<JAC>(y, T, P, p, e);
-    const double w = (e.Ct/p.Ct0)*(p.Pf/P);                            // :3180 v/v0 (interstitial == superficial ratio)
+    const double w = (e.Ct*p.Pf)*pbr_rcp(p.Ct0*P);                     // :3180 v/v0 (interstitial == superficial ratio)
     const double vs = p.vs0*w;                                         // :3184
     const double zP = p.zP;                                            // :3219
     f[n] = -(p.E1*vs + p.E2*e.rho*vs*vs)*zP;                           // :3214-3220
-    const double invGw = 1.0/(p.G*w);                                  // :3283, :3288
+    const double invGw = pbr_rcp(p.G*w);                               // :3283, :3288
 #pragma unroll
     for (int i = 0; i < n; ++i) f[i] = e.ri[i]*invGw;
     double Den = 1.0, fth = 0.0;
     if (!PBR_ISO) {
         const double Num = (-e.Hsum + e.Q)*p.iGH;                      // :3298
         Den = (e.rho*p.irho0)*((e.Cpmix*p.iCp0)*p.eps)*w;              // :3284
-        fth = Num/Den;
+        fth = Num*pbr_rcp(Den);
         f[n + 1] = fth;
     }
     if (JAC) {
         // reciprocals once: an FP64 divide costs ~12 instructions and the columns below would need ~40 of them
         const double cmct = p.Cmax*e.invCt;
-        const double iGH = p.iGH, iDen = 1.0/Den, irho = 1.0/e.rho, iCp = PBR_ISO ? 1.0 : 1.0/e.Cpmix, ipr = 1.0/pr;
+        const double iGH = p.iGH, iDen = pbr_rcp(Den), irho = pbr_rcp(e.rho), iCp = PBR_ISO ? 1.0 : pbr_rcp(e.Cpmix), ipr = pbr_rcp(pr);
         const double dfp_dw = -zP*(p.E1*p.vs0 + 2.0*p.E2*e.rho*p.vs0*p.vs0*w);
         const double dfp_drho = -zP*(p.E2*vs*vs);
-        const double rhoM = e.rho/e.M;
+        const double rhoM = e.rho*pbr_rcp(e.M);
         double drk[PBR_NR], dri[PBR_NC];
         // ---- species columns
 #pragma unroll
@@ -309,7 +309,7 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
 #pragma unroll
             for (int j = 0; j < PBR_NR; ++j) drk[j] = p.Tf*e.drT[j];
             pbr_dri(drk, dri);
-            const double drho = -e.rho*p.Tf/T;
+            const double drho = -e.rho*p.Tf*pbr_rcp(T);
 #pragma unroll
             for (int i = 0; i < n; ++i) st(i, n + 1, dri[i]*invGw);
             st(n, n + 1, dfp_drho*drho);
@@ -376,16 +376,16 @@ PBR_DEV double pbr_n2_node(const double* yc, const double* yb, bool first, doubl
     double D2 = 1.0, heat = 0.0, rs = 1.0, cps = 1.0;
     if (!PBR_ISO) {
         rs = e.rho*p.irho0; cps = e.Cpmix*p.iCp0;
-        D2 = rs*cps*p.eps/p.vz;                                                 // 1/const_T2 :4077
+        D2 = rs*cps*p.eps*pbr_rcp(p.vz);                                        // 1/const_T2 :4077
         const double thb = first ? 0.0 : yb[n];                                 // :4106-4111
         const double conv = -1.0*rs*(cps*p.eps)*((th - thb)*inv_dz);            // :4116
         heat = p.iGH*(-e.Hsum) + p.iGH*e.Q;                                     // :4118-4120
-        f[n] = (conv + heat)/D2;                                                // :4125
+        f[n] = (conv + heat)*pbr_rcp(D2);                                       // :4125
         if (JAC) sub[n] = first ? 0.0 : p.vz*inv_dz;
     }
     if (JAC) {
         double drk[PBR_NR], dri[PBR_NC];
-        const double iGH = p.iGH, iD2 = 1.0/D2, iM = 1.0/e.M, iCp = PBR_ISO ? 1.0 : 1.0/e.Cpmix;
+        const double iGH = p.iGH, iD2 = pbr_rcp(D2), iM = pbr_rcp(e.M), iCp = PBR_ISO ? 1.0 : pbr_rcp(e.Cpmix);
         const double hD2 = heat*iD2;
 #pragma unroll
         for (int k = 0; k < n; ++k) {
@@ -416,7 +416,7 @@ PBR_DEV double pbr_n2_node(const double* yc, const double* yb, bool first, doubl
             for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j] + p.Tf*e.r[j]*e.dHdT[j];
             const double dQ = (p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
             const double dheat = (-s + dQ)*iGH;
-            const double dD2 = D2*(-p.Tf/T + p.Tf*e.dCpmixT*iCp);
+            const double dD2 = D2*(-p.Tf*pbr_rcp(T) + p.Tf*e.dCpmixT*iCp);
             st(n, n, -p.vz*inv_dz + (dheat - hD2*dD2)*iD2);
         }
     }
@@ -462,7 +462,7 @@ PBR_DEV bool pbr_lu_factor(const Strided& a, unsigned long long& piv) {
             for (int j = 0; j < N; ++j) { const double t = a[k*N + j]; a[k*N + j] = a[pk*N + j]; a[pk*N + j] = t; }
         }
         if (!(amax > 0.0) || !(amax < 1e300)) ok = false;
-        const double inv = 1.0/a[k*N + k];
+        const double inv = pbr_rcp(a[k*N + k]);
         a[k*N + k] = inv;
         PBR_LU_PRAGMA
         for (int i = k + 1; i < N; ++i) {
@@ -640,7 +640,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
     const double dz_out = 1.0/(double)(n_out - 1);     // np.linspace(0, 1, zNo+1), :2862
     const double newton_tol = fmax(10.0*2.220446049250313e-16/rtol, fmin(0.03, sqrt(rtol)));   // bdf.py:217
     NoStore nost;
-    double y[NV], f[NV], d[NV], scale[NV], psi[NV];
+    double y[NV], f[NV], d[NV], iscale[NV], psi[NV];      // iscale = 1/(atol + rtol|y|): norms multiply, never divide
     stt.nsteps = stt.nrej = stt.nfev = stt.nlu = stt.nfail = 0;
 
     // ---- initial step, scipy common.py:68-140 (order 1): f0 = f(y0), f1 = f(y0 + h0 f0); one evaluation site
@@ -648,14 +648,14 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
     {
         double h0 = 0.0, d1 = 0.0;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) { y[v] = y0[v]; scale[v] = atol + fabs(y0[v])*rtol; }
+        for (int v = 0; v < NV; ++v) { y[v] = y0[v]; iscale[v] = pbr_rcp(atol + fabs(y0[v])*rtol); }
 #pragma unroll 1
         for (int s = 0; s < 2; ++s) {
             pbr_n1_rhs_call(p, y, f); stt.nfev++;
             if (s == 0) {
                 double d0 = 0.0;
 #pragma unroll
-                for (int v = 0; v < NV; ++v) { d0 += (y[v]/scale[v])*(y[v]/scale[v]); d1 += (f[v]/scale[v])*(f[v]/scale[v]); }
+                for (int v = 0; v < NV; ++v) { d0 += (y[v]*iscale[v])*(y[v]*iscale[v]); d1 += (f[v]*iscale[v])*(f[v]*iscale[v]); }
                 d0 = sqrt(d0/NV); d1 = sqrt(d1/NV);
                 h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
                 h0 = fmin(h0, t_bound);
@@ -664,7 +664,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             } else {
                 double d2 = 0.0;
 #pragma unroll
-                for (int v = 0; v < NV; ++v) { const double df = f[v] - D[1*NV + v]; d2 += (df/scale[v])*(df/scale[v]); }
+                for (int v = 0; v < NV; ++v) { const double df = f[v] - D[1*NV + v]; d2 += (df*iscale[v])*(df*iscale[v]); }
                 d2 = sqrt(d2/NV)/h0;
                 const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0*1e-3) : sqrt(0.01/fmax(d1, d2));
                 h = fmin(fmin(100.0*h0, h1), t_bound);
@@ -707,14 +707,14 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
         if (active && h < pbr_ulp10(t)) { status = PBR_ERR_STEP_TOO_SMALL; active = false; }
         if (active && trip > max_steps) { status = PBR_ERR_MAX_STEPS; active = false; }
         // ---------------- 2. predictor + psi, bdf.py:360-363 ----------------
-        const double alpha = pbr_bdf_alpha(order);
-        const double c = h/alpha;
+        const double ialpha = pbr_rcp(pbr_bdf_alpha(order));
+        const double c = h*ialpha;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             double yp = D[v], ps = 0.0;
             for (int r = 1; r <= PBR_MAXORD; ++r) if (r <= order) { const double Dr = D[r*NV + v]; yp += Dr; ps += Dr*pbr_bdf_gamma(r); }
-            y[v] = yp; psi[v] = ps/alpha; d[v] = 0.0;
-            scale[v] = atol + rtol*fabs(yp);
+            y[v] = yp; psi[v] = ps*ialpha; d[v] = 0.0;
+            iscale[v] = pbr_rcp(atol + rtol*fabs(yp));
         }
         PBR_MID_BARRIER(2)
         // ---------------- 3. refresh trips: Jacobian + LU of I - cJ at the predictor (also yields f(y_pred)) ----------------
@@ -747,7 +747,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
                 for (int v = 0; v < NV; ++v) { b[v] = c*f[v] - psi[v] - d[v]; fin = fin && (fabs(b[v]) < 1e300); }
                 pbr_lu_solve<NV>(LU, piv, b);
 #pragma unroll
-                for (int v = 0; v < NV; ++v) nrm += (b[v]/scale[v])*(b[v]/scale[v]);
+                for (int v = 0; v < NV; ++v) nrm += (b[v]*iscale[v])*(b[v]*iscale[v]);
                 const double dy_norm = sqrt(nrm/NV);
                 const double rate = (dy_norm_old >= 0.0) ? dy_norm/dy_norm_old : -1.0;
                 const bool diverge = !fin || !(dy_norm == dy_norm) ||
@@ -773,8 +773,8 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             double en = 0.0;
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
-                scale[v] = atol + rtol*fabs(y[v]);
-                const double ev = errc*d[v]/scale[v]; en += ev*ev;
+                iscale[v] = pbr_rcp(atol + rtol*fabs(y[v]));
+                const double ev = errc*d[v]*iscale[v]; en += ev*ev;
             }
             err_norm = sqrt(en/NV);
         }
@@ -796,8 +796,8 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
                 D[(order + 1)*NV + v] = d[v];
                 double acc = d[v];
                 for (int r = PBR_MAXORD; r >= 0; --r) if (r <= order) { acc += D[r*NV + v]; D[r*NV + v] = acc; }
-                if (order > 1) { const double e1 = pbr_bdf_errc(order - 1)*D[order*NV + v]/scale[v]; em += e1*e1; }
-                if (order < PBR_MAXORD) { const double e2 = pbr_bdf_errc(order + 1)*(d[v] - Dk1)/scale[v]; ep += e2*e2; }
+                if (order > 1) { const double e1 = pbr_bdf_errc(order - 1)*D[order*NV + v]*iscale[v]; em += e1*e1; }
+                if (order < PBR_MAXORD) { const double e2 = pbr_bdf_errc(order + 1)*(d[v] - Dk1)*iscale[v]; ep += e2*e2; }
             }
             // dense output on (t_old, t], BdfDenseOutput bdf.py:462-484
             while (next_out < n_out && ((next_out == n_out - 1) ? 1.0 : next_out*dz_out) <= t) {
@@ -847,7 +847,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
 // marched along the bed, the owner lane of node z solving and broadcasting x_z to the warp.
 //
 // Scratch (global memory, private to the warp, element (k, z) at ws[k*zNo + z]):
-//   D[PBR_DROWS][NV2] | y[NV2] | d[NV2] | psi[NV2] | scl[NV2] | b[NV2] | sub[NV2] | LU[NV2*NV2] | piv[1] | G[NV2*NV2]
+//   D[PBR_DROWS][NV2] | y[NV2] | d[NV2] | psi[NV2] | 1/scale[NV2] | b[NV2] | sub[NV2] | LU[NV2*NV2] | piv[1] | G[NV2*NV2]
 //   with G_z = A_z^{-1} c diag(sub_z), so that the serial part of the march is one small mat-vec per node.
 // =====================================================================================================
 #define PBR_N2_WS_ROWS ((PBR_DROWS + 6)*PBR_NV2 + 2*PBR_NV2*PBR_NV2 + 1)
@@ -926,7 +926,7 @@ PBR_DEV bool pbr_n2_sweep_eval(const WarpCtx& w, const InstPar& p, const N2Ws& w
 #pragma unroll
             for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yc[i], PBR_EPS)*p.Cmax; Ct += C; M += C*PBR_MW[i]; }
             const double th = PBR_ISO ? 0.0 : yc[PBR_ISO ? 0 : PBR_NC];
-            a = 1.0 - dz*p.E2*p.vs0*p.vs0*(M*1e-3)/(Ct*(PBR_R*(th*p.Tf + p.Tf)));
+            a = 1.0 - dz*p.E2*p.vs0*p.vs0*(M*1e-3)*pbr_rcp(Ct*(PBR_R*(th*p.Tf + p.Tf)));
             b = -dz*p.E1*p.vs0;
         }
         const double Pz = w.scan_affine(a, b, Pcarry);
@@ -1024,7 +1024,7 @@ PBR_DEV double pbr_n2_newton_solve(const WarpCtx& w, const N2Ws& ws, double c) {
                 for (int v = 0; v < NV; ++v) {
                     ws.vec(0, v)[z] += x[v];
                     ws.vec(1, v)[z] += x[v];
-                    const double e = x[v]/T[NV*NV + NV + v];
+                    const double e = x[v]*T[NV*NV + NV + v];
                     nrm += e*e;
                 }
             }
@@ -1086,7 +1086,7 @@ PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, 
         double h0 = 0.0, d1 = 0.0;
         for (int z = w.lane; z < zNo; z += WarpCtx::NL)
 #pragma unroll
-            for (int v = 0; v < PBR_NV2; ++v) { const double y = ws.D(0, v)[z]; ws.vec(0, v)[z] = y; ws.vec(3, v)[z] = atol + fabs(y)*rtol; }
+            for (int v = 0; v < PBR_NV2; ++v) { const double y = ws.D(0, v)[z]; ws.vec(0, v)[z] = y; ws.vec(3, v)[z] = pbr_rcp(atol + fabs(y)*rtol); }
 #pragma unroll 1
         for (int s = 0; s < 2; ++s) {
             if (!pbr_n2_sweep_eval<false>(w, p, ws, 0.0, false)) return PBR_ERR_NONFINITE;
@@ -1097,7 +1097,7 @@ PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, 
 #pragma unroll
                     for (int v = 0; v < PBR_NV2; ++v) {
                         const double sc = ws.vec(3, v)[z], y = ws.vec(0, v)[z], f = ws.vec(4, v)[z];
-                        a0 += (y/sc)*(y/sc); a1 += (f/sc)*(f/sc);
+                        a0 += (y*sc)*(y*sc); a1 += (f*sc)*(f*sc);
                         ws.D(1, v)[z] = f;
                     }
                 const double d0 = sqrt(w.sum(a0)/nTot);
@@ -1110,7 +1110,7 @@ PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, 
             } else {
                 for (int z = w.lane; z < zNo; z += WarpCtx::NL)
 #pragma unroll
-                    for (int v = 0; v < PBR_NV2; ++v) { const double df = (ws.vec(4, v)[z] - ws.D(1, v)[z])/ws.vec(3, v)[z]; a0 += df*df; }
+                    for (int v = 0; v < PBR_NV2; ++v) { const double df = (ws.vec(4, v)[z] - ws.D(1, v)[z])*ws.vec(3, v)[z]; a0 += df*df; }
                 const double d2 = sqrt(w.sum(a0)/nTot)/h0;
                 const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0*1e-3) : sqrt(0.01/fmax(d1, d2));
                 h = fmin(fmin(100.0*h0, h1), span);
@@ -1141,15 +1141,15 @@ PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, 
         if (h < pbr_ulp10(t)) { status = PBR_ERR_STEP_TOO_SMALL; break; }
         if (trip > max_steps) { status = PBR_ERR_MAX_STEPS; break; }
         // ---- 2. predictor, psi, scale, d = 0
-        const double alpha = pbr_bdf_alpha(order);
-        const double c = h/alpha;
+        const double ialpha = pbr_rcp(pbr_bdf_alpha(order));
+        const double c = h*ialpha;
         for (int z = w.lane; z < zNo; z += WarpCtx::NL)
 #pragma unroll
             for (int v = 0; v < PBR_NV2; ++v) {
                 double yp = ws.D(0, v)[z], ps = 0.0;
                 for (int r = 1; r <= order; ++r) { const double Dr = ws.D(r, v)[z]; yp += Dr; ps += Dr*pbr_bdf_gamma(r); }
-                ws.vec(0, v)[z] = yp; ws.vec(1, v)[z] = 0.0; ws.vec(2, v)[z] = ps/alpha;
-                ws.vec(3, v)[z] = atol + rtol*fabs(yp);
+                ws.vec(0, v)[z] = yp; ws.vec(1, v)[z] = 0.0; ws.vec(2, v)[z] = ps*ialpha;
+                ws.vec(3, v)[z] = pbr_rcp(atol + rtol*fabs(yp));
             }
         // ---- 3./4. Jacobian blocks + LU at the predictor, then Newton (bdf.py:36-68)
         bool converged = false;
@@ -1190,9 +1190,9 @@ PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, 
             for (int z = w.lane; z < zNo; z += WarpCtx::NL)
 #pragma unroll
                 for (int v = 0; v < PBR_NV2; ++v) {
-                    const double sc = atol + rtol*fabs(ws.vec(0, v)[z]);
+                    const double sc = pbr_rcp(atol + rtol*fabs(ws.vec(0, v)[z]));
                     ws.vec(3, v)[z] = sc;
-                    const double ev = errc*ws.vec(1, v)[z]/sc; en += ev*ev;
+                    const double ev = errc*ws.vec(1, v)[z]*sc; en += ev*ev;
                 }
             err_norm = sqrt(w.sum(en)/nTot);
         }
@@ -1216,8 +1216,8 @@ PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, 
                     ws.D(order + 1, v)[z] = dv;
                     double acc = dv;
                     for (int r = order; r >= 0; --r) { acc += ws.D(r, v)[z]; ws.D(r, v)[z] = acc; }
-                    if (order > 1) { const double e1 = pbr_bdf_errc(order - 1)*ws.D(order, v)[z]/sc; em += e1*e1; }
-                    if (order < PBR_MAXORD) { const double e2 = pbr_bdf_errc(order + 1)*(dv - Dk1)/sc; ep += e2*e2; }
+                    if (order > 1) { const double e1 = pbr_bdf_errc(order - 1)*ws.D(order, v)[z]*sc; em += e1*e1; }
+                    if (order < PBR_MAXORD) { const double e2 = pbr_bdf_errc(order + 1)*(dv - Dk1)*sc; ep += e2*e2; }
                 }
             if (n_equal >= order + 1) {
                 em = w.sum(em); ep = w.sum(ep);
@@ -1441,7 +1441,7 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
 #pragma unroll
             for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yc[i], PBR_EPS)*pp.Cmax; Ct += C; M += C*PBR_MW[i]; }
             const double th = PBR_ISO ? 0.0 : yc[PBR_ISO ? 0 : PBR_NC];
-            a = 1.0 - dz*pp.E2*pp.vs0*pp.vs0*(M*1e-3)/(Ct*(PBR_R*(th*pp.Tf + pp.Tf)));
+            a = 1.0 - dz*pp.E2*pp.vs0*pp.vs0*(M*1e-3)*pbr_rcp(Ct*(PBR_R*(th*pp.Tf + pp.Tf)));
             b = -dz*pp.E1*pp.vs0;
             if (z == 0) { b = a*pp.Pf + b; a = 0.0; }                 // P_z[0] = P0 (:3848): the map forgets what came before
         }

@@ -60,3 +60,23 @@ PBR_DEV double pbr_exp(double x) {
 
 PBR_DEV double pbr_exp10(double x) { return pbr_exp(x*PBR_EXPC[18]); }
 #endif
+
+// pbr_rcp: 1/x without the IEEE division routine.  A double-precision divide compiles to MUFU.RCP64H + Newton steps +
+// range check + a branch to an out-of-line fix-up (~15 issued instructions and a basic-block split per divide; the RHS
+// evaluates ~12-25 of them).  Here: rcp.approx.ftz.f64 (about 20 good bits) and two Newton steps in FMA form -- 6
+// instructions, branch-free, result within 1 ulp for normal x.  x = 0 or subnormal gives NaN/inf garbage (the reference
+// raises ZeroDivisionError there); NaN propagates.  PBR_FAST_RCP=0 falls back to the IEEE divide.
+#ifndef PBR_FAST_RCP
+#define PBR_FAST_RCP 1
+#endif
+PBR_DEV double pbr_rcp(double x) {
+#if defined(PBR_HOST) || !PBR_FAST_RCP
+    return 1.0/x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+#endif
+}

@@ -514,7 +514,7 @@ def _emit_body(g, needed, lines, names, ktab=None):
         elif op == "neg":
             rhs = f"-{a}"
         elif op == "rcp":
-            rhs = f"1.0 / {a}"
+            rhs = f"pbr_rcp({a})"
         elif op == "powi":
             e = n[2]
             rhs = _powi(a, abs(e))
