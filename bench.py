@@ -262,7 +262,10 @@ def run_gpu(a):
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"kernel": "pbr_k2_solve_n1", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved/fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved/fp64_peak if fp64_peak else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size, ncu --set full
+                         # (profiles/r1e_k2_v6_block224_and_k3_v2.txt): 11.32 MB + 1.07 MB
+                         "traffic": 12.39e6, "traffic_unit": "B/launch (ncu, profiles/)",
                          "peak_source": "DFMA probe pbr_k_dfma_peak measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                          "kernel_ms": 1e3*t_k2, "algorithmic_flops_per_launch": flops, "flops_per_unit": per_unit,
                          "mean_steps": float(stats[0].mean()), "mean_nfev": float(stats[2].mean()), "mean_nlu": float(stats[3].mean()),
@@ -324,7 +327,9 @@ def bench_rhs_n2(model, mi, peaks):
     b1 = (16.0*m2.nv1 + 8.0*m2.k_par)*N1
     src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     return {"kernel": "pbr_k3_rhs_n2", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs/peak,
-            "peak_source": src, "traffic": None, "zNo": zNo, "instances": N, "ms": ms, "rhs_evals_per_s": N/(ms*1e-3),
+            "peak_source": src, "zNo": zNo, "instances": N, "ms": ms, "rhs_evals_per_s": N/(ms*1e-3),
+            # ncu at 16,384 instances: 94.7 MB read + 51.5 MB written to DRAM by kernel end (algorithmic 91.8 + 91.8 MB)
+            "traffic": None,
             "node_evals_per_s": N*zNo/(ms*1e-3),
             "note": "16*(n+1)*zNo B per instance-eval; at ~650 executed FP64 ops per node this kernel sits on the FP64 side of the ridge",
             "rhs_n1": {"kernel": "pbr_k_rhs_n1", "bound": "hbm", "achieved": b1/(ms1*1e-3)/1e9, "peak": peak, "unit": "GB/s",
