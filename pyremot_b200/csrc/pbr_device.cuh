@@ -501,6 +501,54 @@ PBR_DEV void pbr_lu_solve(const Strided& a, unsigned long long piv, double* b) {
     }
 }
 
+// In-place inverse of the NxN row-major matrix a by Gauss-Jordan elimination with partial pivoting (row swaps, undone
+// as column swaps at the end).  Returns false if a pivot is zero / non-finite.  Used where the block is applied many
+// times per factorisation and a temporary for the inverse would not fit in registers (K4b).
+template <int N>
+PBR_DEV bool pbr_invert(const Strided& a) {
+    unsigned long long piv = 0ull;
+    bool ok = true;
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+        int pk = k;
+        double amax = fabs(a[k*N + k]);
+#pragma unroll 1
+        for (int i = k + 1; i < N; ++i) {
+            const double v = fabs(a[i*N + k]);
+            if (v > amax) { amax = v; pk = i; }
+        }
+        piv |= (unsigned long long)pk << (4*k);
+        if (pk != k) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) { const double t = a[k*N + j]; a[k*N + j] = a[pk*N + j]; a[pk*N + j] = t; }
+        }
+        if (!(amax > 0.0) || !(amax < 1e300)) ok = false;
+        const double pinv = pbr_rcp(a[k*N + k]);
+        a[k*N + k] = 1.0;
+        double rowk[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) { rowk[j] = a[k*N + j]*pinv; a[k*N + j] = rowk[j]; }
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+            if (i != k) {
+                const double f = a[i*N + k];
+                a[i*N + k] = 0.0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) a[i*N + j] -= f*rowk[j];
+            }
+        }
+    }
+#pragma unroll 1
+    for (int k = N - 1; k >= 0; --k) {
+        const int pk = (int)((piv >> (4*k)) & 15ull);
+        if (pk != k) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) { const double t = a[i*N + k]; a[i*N + k] = a[i*N + pk]; a[i*N + pk] = t; }
+        }
+    }
+    return ok;
+}
+
 struct LuStore {            // receives Jacobian entries, stores the Newton matrix I - c*J
     Strided a; double c;
     PBR_DEV void operator()(int i, int k, double v) const { a[i*PBR_NV1 + k] = (i == k ? 1.0 : 0.0) - c*v; }
@@ -1491,6 +1539,359 @@ extern "C" __global__ void __launch_bounds__(128) pbr_k4_solve_n2(long N, int zN
             if (stats) { stats[0*N + inst] = st.nsteps; stats[1*N + inst] = st.nrej + st.nfail; stats[2*N + inst] = st.nfev; stats[3*N + inst] = st.nlu; }
         }
         __syncwarp();
+    }
+}
+
+// ---- K4b: fused N2 solver, ONE BLOCK PER REACTOR, ONE THREAD PER AXIAL NODE, all integrator state on chip.
+//      Used when the reactor's working set fits shared memory (119*zNo doubles: zNo <= ~230); larger grids use K4.
+//      Shared memory (element e of node z at base[e*zNo + z], conflict-free): BDF history D[7][NV2], inverse of the
+//      node's Newton block Ainv[NV2*NV2], current iterate Y[NV2] (for the upwind neighbour), psi[NV2], 1/scale[NV2].
+//      Same BDF / Newton logic as pbr_n2_interval; the control scalars are computed redundantly by every thread from
+//      block-wide reductions, so they are uniform.  Linear solve: x_z = Ainv_z (b_z + c sub_z * x_{z-1}) marched warp
+//      by warp (shuffles inside a warp, one shared-memory hand-over + barrier between warps).
+struct BlkCtx {
+    double* red;          // [32] reduction / hand-over scratch
+    int tid, lane, wid, nw;
+    __device__ __forceinline__ double sum(double x) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        __syncthreads();                                  // previous use of red[] is over
+        if (lane == 0) red[wid] = x;
+        __syncthreads();
+        double t = 0.0;
+        for (int k = 0; k < nw; ++k) t += red[k];         // same order in every thread: bitwise-uniform result
+        return t;
+    }
+    // pressure at this thread's node from the affine maps of all earlier nodes (node 0 carries Pf)
+    __device__ __forceinline__ double scan_affine(double a, double b, double Pf) const {
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double a1 = __shfl_up_sync(0xffffffffu, a, off);
+            const double b1 = __shfl_up_sync(0xffffffffu, b, off);
+            if (lane >= off) { b = a*b1 + b; a = a*a1; }
+        }
+        double ae = __shfl_up_sync(0xffffffffu, a, 1), be = __shfl_up_sync(0xffffffffu, b, 1);
+        if (lane == 0) { ae = 1.0; be = 0.0; }
+        __syncthreads();
+        if (lane == 31) { red[wid] = a; red[16 + wid] = b; }
+        __syncthreads();
+        double Pin = Pf;
+        for (int k = 0; k < wid; ++k) Pin = red[k]*Pin + red[16 + k];
+        return ae*Pin + be;
+    }
+};
+
+struct SmStore {         // Jacobian entries of this thread's node -> I - c*J in its shared-memory column
+    Strided a; double c;
+    __device__ __forceinline__ void operator()(int i, int k, double v) const { a[i*PBR_NV2 + k] = (i == k ? 1.0 : 0.0) - c*v; }
+};
+
+// f(Y) at this thread's node from the iterate y[] (registers); with JAC also leaves Ainv in shared memory and sub[].
+template <bool JAC>
+__device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p, int zNo, bool act, const double* y, double c,
+                                             double* Ysm, double* Asm, double* f, double* sub) {
+    const int z = cx.tid;
+    const double dz = 1.0/(double)(zNo - 1), inv_dz = (double)(zNo - 1);
+    __syncthreads();
+    if (act) {
+#pragma unroll
+        for (int v = 0; v < PBR_NV2; ++v) Ysm[v*zNo + z] = y[v];
+    }
+    __syncthreads();
+    double yb[PBR_NV2];
+#pragma unroll
+    for (int v = 0; v < PBR_NV2; ++v) yb[v] = (act && z > 0) ? Ysm[v*zNo + z - 1] : 0.0;
+    double a = 1.0, b = 0.0;
+    if (act) {
+        double Ct = 0.0, M = 0.0;
+#pragma unroll
+        for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(y[i], PBR_EPS)*p.Cmax; Ct += C; M += C*PBR_MW[i]; }
+        const double th = PBR_ISO ? 0.0 : y[PBR_ISO ? 0 : PBR_NC];
+        a = 1.0 - dz*p.E2*p.vs0*p.vs0*(M*1e-3)*pbr_rcp(Ct*(PBR_R*(th*p.Tf + p.Tf)));
+        b = -dz*p.E1*p.vs0;
+    }
+    const double Pz = cx.scan_affine(a, b, p.Pf);
+    double bad = 0.0;
+    if (act) {
+        if (JAC) {
+            const Strided blk = {Asm + z, zNo};
+            SmStore st = {blk, c};
+            pbr_n2_node<true>(y, yb, z == 0, Pz, inv_dz, p, f, st, sub);
+            if (!pbr_invert<PBR_NV2>(blk)) bad = 1.0;          // Ainv replaces I - c*J in place
+        } else {
+            NoStore ns;
+            pbr_n2_node<false>(y, yb, z == 0, Pz, inv_dz, p, f, ns, (double*)0);
+        }
+#pragma unroll
+        for (int v = 0; v < PBR_NV2; ++v) if (!(fabs(f[v]) < 1e300)) bad = 1.0;
+    }
+    return cx.sum(bad) == 0.0;
+}
+
+// x_z = Ainv_z (b_z + cs_z * x_{z-1}) for all nodes; b (registers) is overwritten by x.
+__device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool act, const double* Asm, const double* cs, double* b) {
+    const int z = cx.tid;
+    const int nwz = (zNo + 31) >> 5;                       // warps that own nodes
+#ifndef PBR_K4B_PRELOAD
+#define PBR_K4B_PRELOAD 1       // 1: every lane pulls its node's inverse block into registers before the serial march
+#endif
+#if PBR_K4B_PRELOAD
+    double Ai[PBR_NV2*PBR_NV2];
+    if (act) {
+#pragma unroll
+        for (int e = 0; e < PBR_NV2*PBR_NV2; ++e) Ai[e] = Asm[e*zNo + z];
+    }
+#define PBR_AI(e) Ai[e]
+#else
+    const double* Ai = Asm + (act ? z : 0);                  // this node's inverse block, element e at Ai[e*zNo]
+#define PBR_AI(e) Ai[(e)*zNo]
+#endif
+    for (int wv = 0; wv < nwz; ++wv) {
+        if (cx.wid == wv) {
+            double xp[PBR_NV2];
+#pragma unroll
+            for (int v = 0; v < PBR_NV2; ++v) xp[v] = (wv == 0) ? 0.0 : cx.red[v];
+            const int nact = (zNo - wv*32 < 32) ? (zNo - wv*32) : 32;
+            for (int l = 0; l < nact; ++l) {
+                double x[PBR_NV2];
+#pragma unroll
+                for (int v = 0; v < PBR_NV2; ++v) x[v] = 0.0;
+                if (cx.lane == l) {
+                    double r[PBR_NV2];
+#pragma unroll
+                    for (int v = 0; v < PBR_NV2; ++v) r[v] = b[v] + cs[v]*xp[v];
+#pragma unroll
+                    for (int i = 0; i < PBR_NV2; ++i) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < PBR_NV2; ++k) acc += PBR_AI(i*PBR_NV2 + k)*r[k];
+                        x[i] = acc;
+                    }
+#pragma unroll
+                    for (int v = 0; v < PBR_NV2; ++v) b[v] = x[v];
+                }
+#pragma unroll
+                for (int v = 0; v < PBR_NV2; ++v) xp[v] = __shfl_sync(0xffffffffu, x[v], l);
+            }
+            if (cx.lane == 0) {
+#pragma unroll
+                for (int v = 0; v < PBR_NV2; ++v) cx.red[v] = xp[v];      // x of this warp's last node
+            }
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(256) pbr_k4b_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+                                                                   double rtol, double atol, int max_steps,
+                                                                   double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
+    extern __shared__ double pbr_smem[];
+    const int NV = PBR_NV2;
+    double* Dsm = pbr_smem;                                // [PBR_DROWS*NV][zNo]
+    double* Asm = Dsm + (long)PBR_DROWS*NV*zNo;            // [NV*NV][zNo]
+    double* Ysm = Asm + (long)NV*NV*zNo;                   // [NV][zNo]
+    double* Psm = Ysm + (long)NV*zNo;                      // psi
+    double* Ism = Psm + (long)NV*zNo;                      // 1/scale
+    BlkCtx cx; cx.red = Ism + (long)NV*zNo; cx.tid = threadIdx.x; cx.lane = threadIdx.x & 31; cx.wid = threadIdx.x >> 5; cx.nw = blockDim.x >> 5;
+    const int z = threadIdx.x;
+    const bool act = z < zNo;
+    const Strided D = {Dsm + (act ? z : 0), zNo};
+    const double nTot = (double)(NV*zNo);
+    const double newton_tol = fmax(10.0*2.220446049250313e-16/rtol, fmin(0.03, sqrt(rtol)));
+
+    for (long inst = blockIdx.x; inst < N; inst += gridDim.x) {
+        InstPar p; pbr_load_par(par, N, inst, p);
+        int nsteps = 0, nrejf = 0, nfev = 0, nlu = 0;
+        int rc = PBR_OK;
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int v = 0; v < PBR_NC; ++v) D[0*NV + v] = p.c0[v];                 // IV, :3483-3497
+            if (!PBR_ISO) D[0*NV + (PBR_ISO ? 0 : PBR_NC)] = 0.0;
+        }
+        for (int kint = 0; kint < tNo && rc == PBR_OK; ++kint) {
+            const double t0 = (kint == 0) ? 0.0 : period*((double)kint/(double)tNo);  // np.linspace(0, opT, tNo+1)
+            const double t1 = (kint == tNo - 1) ? period : period*((double)(kint + 1)/(double)tNo);
+            const double span = t1 - t0;
+            double y[PBR_NV2], d[PBR_NV2], f[PBR_NV2], sub[PBR_NV2], b[PBR_NV2];
+            // ---- initial step (scipy common.py:68-140), restart at every interval (:3589-3685)
+            double h = 0.0;
+            {
+                double h0 = 0.0, d1 = 0.0, f0[PBR_NV2];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) { y[v] = act ? D[0*NV + v] : 1.0; sub[v] = 0.0; f[v] = 0.0; f0[v] = 0.0; }
+                bool ok = pbr_k4b_eval<false>(cx, p, zNo, act, y, 0.0, Ysm, Asm, f, sub); nfev++;
+                double a0 = 0.0, a1 = 0.0;
+                if (act) {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const double sc = pbr_rcp(atol + fabs(y[v])*rtol);
+                        Ism[v*zNo + z] = sc;
+                        a0 += (y[v]*sc)*(y[v]*sc); a1 += (f[v]*sc)*(f[v]*sc);
+                        f0[v] = f[v];
+                    }
+                }
+                const double d0 = sqrt(cx.sum(a0)/nTot);
+                d1 = sqrt(cx.sum(a1)/nTot);
+                h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
+                h0 = fmin(h0, span);
+                double y1[PBR_NV2];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) y1[v] = y[v] + h0*f0[v];
+                ok = pbr_k4b_eval<false>(cx, p, zNo, act, y1, 0.0, Ysm, Asm, f, sub) && ok; nfev++;
+                a0 = 0.0;
+                if (act) {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) { const double df = (f[v] - f0[v])*Ism[v*zNo + z]; a0 += df*df; }
+                }
+                const double d2 = sqrt(cx.sum(a0)/nTot)/h0;
+                const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0*1e-3) : sqrt(0.01/fmax(d1, d2));
+                h = fmin(fmin(100.0*h0, h1), span);
+                if (!ok) rc = PBR_ERR_NONFINITE;
+                if (act) {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        D[1*NV + v] = f0[v]*h;
+                        for (int r = 2; r < PBR_DROWS; ++r) D[r*NV + v] = 0.0;
+                    }
+                }
+            }
+            int order = 1, n_equal = 0, trip = 0;
+            double t = t0, pend = 1.0, kappa = 1e300;
+            bool active = (rc == PBR_OK);
+            while (active) {
+                // ---- 1. step size, lazy history rescale
+                double hn = h*pend;
+                const bool clip = (t + hn > t1) || (t1 - (t + hn) < 1e-13*span);
+                if (clip) hn = t1 - t;
+                const double t_new = clip ? t1 : t + hn;
+                const double fac = hn/h;
+                if (fac != 1.0) { if (act) pbr_change_D<PBR_NV2>(D, order, fac); n_equal = 0; }
+                h = hn; pend = 1.0;
+                trip++;
+                if (h < pbr_ulp10(t)) { rc = PBR_ERR_STEP_TOO_SMALL; break; }
+                if (trip > max_steps) { rc = PBR_ERR_MAX_STEPS; break; }
+                // ---- 2. predictor, psi, 1/scale
+                const double ialpha = pbr_rcp(pbr_bdf_alpha(order));
+                const double c = h*ialpha;
+                if (act) {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        double yp = D[0*NV + v], ps = 0.0;
+                        for (int r = 1; r <= order; ++r) { const double Dr = D[r*NV + v]; yp += Dr; ps += Dr*pbr_bdf_gamma(r); }
+                        y[v] = yp; d[v] = 0.0;
+                        Psm[v*zNo + z] = ps*ialpha;
+                        Ism[v*zNo + z] = pbr_rcp(atol + rtol*fabs(yp));
+                    }
+                }
+                // ---- 3./4. Jacobian blocks + inverses at the predictor, Newton (bdf.py:36-68)
+                bool converged = false;
+                bool running = pbr_k4b_eval<true>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub);
+                nlu++; nfev++;
+                double cs[PBR_NV2];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) cs[v] = c*sub[v];
+                double dy_norm_old = -1.0;
+                int n_iter = 0;
+#pragma unroll 1
+                for (int k = 0; k < PBR_NEWTON_MAXITER; ++k) {
+                    if (running) {
+                        n_iter = k + 1;
+                        bool fin = true;
+                        if (k > 0) { fin = pbr_k4b_eval<false>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub); nfev++; }
+                        if (!fin) running = false;
+                        else {
+                            if (act) {
+#pragma unroll
+                                for (int v = 0; v < NV; ++v) b[v] = c*f[v] - Psm[v*zNo + z] - d[v];
+                            }
+                            pbr_k4b_march(cx, zNo, act, Asm, cs, b);
+                            double nrm = 0.0;
+                            if (act) {
+#pragma unroll
+                                for (int v = 0; v < NV; ++v) { y[v] += b[v]; d[v] += b[v]; const double e = b[v]*Ism[v*zNo + z]; nrm += e*e; }
+                            }
+                            const double dy_norm = sqrt(cx.sum(nrm)/nTot);
+                            const double rate = (dy_norm_old >= 0.0) ? dy_norm/dy_norm_old : -1.0;
+                            const bool diverge = !(dy_norm == dy_norm) ||
+                                (rate >= 0.0 && (rate >= 1.0 || pbr_ipow(rate, PBR_NEWTON_MAXITER - k)/(1.0 - rate)*dy_norm > newton_tol));
+                            if (diverge) running = false;
+                            else {
+                                if (k == 1) kappa = rate/fmax(dy_norm_old, 1e-300);
+                                const bool quad_ok = PBR_NEWTON_SKIP && k == 0 && (trip % PBR_KAPPA_PERIOD) != 0 &&
+                                                     kappa*dy_norm*dy_norm < PBR_NEWTON_SKIP_TOL;
+                                if (dy_norm == 0.0 || quad_ok || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; running = false; }
+                                dy_norm_old = dy_norm;
+                            }
+                        }
+                    }
+                }
+                // ---- 5. error test
+                const double safety = 0.9*(2*PBR_NEWTON_MAXITER + 1)/(double)(2*PBR_NEWTON_MAXITER + n_iter);
+                double err_norm = 0.0;
+                if (converged) {
+                    const double errc = pbr_bdf_errc(order);
+                    double en = 0.0;
+                    if (act) {
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            const double sc = pbr_rcp(atol + rtol*fabs(y[v]));
+                            Ism[v*zNo + z] = sc;
+                            const double ev = errc*d[v]*sc; en += ev*ev;
+                        }
+                    }
+                    err_norm = sqrt(cx.sum(en)/nTot);
+                }
+                const bool accepted = converged && (err_norm <= 1.0);
+                if (!converged) { pend = 0.5; nrejf++; }
+                else if (!accepted) {
+                    pend = (err_norm == err_norm) ? fmax(PBR_MIN_FACTOR, safety*pbr_fpow(err_norm, -1.0/(order + 1))) : 0.5;
+                    nrejf++;
+                }
+                // ---- 6. accepted: history update, order / step selection
+                if (accepted) {
+                    n_equal++; nsteps++;
+                    t = t_new;
+                    double em = 0.0, ep = 0.0;
+                    if (act) {
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            const double dv = d[v], sc = Ism[v*zNo + z];
+                            const double Dk1 = D[(order + 1)*NV + v];
+                            if (order < PBR_MAXORD) D[(order + 2)*NV + v] = dv - Dk1;
+                            D[(order + 1)*NV + v] = dv;
+                            double acc = dv;
+                            for (int r = order; r >= 0; --r) { acc += D[r*NV + v]; D[r*NV + v] = acc; }
+                            if (order > 1) { const double e1 = pbr_bdf_errc(order - 1)*D[order*NV + v]*sc; em += e1*e1; }
+                            if (order < PBR_MAXORD) { const double e2 = pbr_bdf_errc(order + 1)*(dv - Dk1)*sc; ep += e2*e2; }
+                        }
+                    }
+                    if (n_equal >= order + 1) {
+                        em = cx.sum(em); ep = cx.sum(ep);
+                        const double fm = (order > 1) ? pbr_fpow(sqrt(em/nTot), -1.0/order) : 0.0;
+                        const double f0 = pbr_fpow(err_norm, -1.0/(order + 1));
+                        const double fp = (order < PBR_MAXORD) ? pbr_fpow(sqrt(ep/nTot), -1.0/(order + 2)) : 0.0;
+                        double fmaxv = f0; int dord = 0;
+                        if (fm > fmaxv) { fmaxv = fm; dord = -1; }
+                        if (fp > fmaxv) { fmaxv = fp; dord = +1; }
+                        order += dord;
+                        pend = fmin(PBR_MAX_FACTOR, safety*fmaxv);
+                        n_equal = 0;
+                    }
+                    if (!(t < t1)) active = false;
+                }
+            }
+            __syncthreads();
+            if (act) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) snaps[(inst*tNo + kint)*(long)NV*zNo + (long)v*zNo + z] = D[0*NV + v];
+            }
+        }
+        if (threadIdx.x == 0) {
+            status[inst] = rc;
+            if (stats) { stats[0*N + inst] = nsteps; stats[1*N + inst] = nrejf; stats[2*N + inst] = nfev; stats[3*N + inst] = nlu; }
+        }
+        __syncthreads();
     }
 }
 

@@ -106,6 +106,11 @@ void hs_lu_test(int n_unused, double* A /*NV1 x NV1 row-major, overwritten*/, do
     pbr_lu_solve<PBR_NV1>(a, piv, b);
 }
 
+void hs_invert_test(double* A /*NV1 x NV1 row-major, overwritten by its inverse*/) {
+    Strided a = {A, 1};
+    pbr_invert<PBR_NV1>(a);
+}
+
 void hs_change_D(double* D, int order, double factor) { Strided d = {D, 1}; pbr_change_D<PBR_NV1>(d, order, factor); }
 
 }

@@ -111,3 +111,29 @@ def test_rmtExeBatch_n2_and_failure_status():
     assert good["dataYs"].shape == (8, 2, 7, 16) and (good["status"] == 0).all()
     assert out["status"][3] != 0 and (np.delete(out["status"], 3) == 0).all()
     assert np.array_equal(np.delete(out["dataYs"], 3, axis=0), np.delete(good["dataYs"], 3, axis=0))
+
+
+def test_n2_both_kernels_agree_and_large_grid():
+    """K4b (block per reactor, zNo <= 256) and K4 (warp per reactor, any zNo) integrate the same equations: they must agree
+    to integration tolerance; zNo = 400 (BASELINE config 4 grid) runs through K4 and is checked against the oracle."""
+    import os
+    from pyremot_b200.api import get_model
+    mi = cases.readme_case("N2")
+    m = get_model(mi)
+    rows = cases.ensemble_rows(6)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    tab = m.instance_table(mi, sweep)
+    blk = m.solve_n2_host(tab, 64, 2, 0.2)
+    os.environ["PBR_N2_KERNEL"] = "warp"
+    try:
+        wrp = m.solve_n2_host(tab, 64, 2, 0.2)
+    finally:
+        del os.environ["PBR_N2_KERNEL"]
+    assert (blk["status"] == 0).all() and (wrp["status"] == 0).all()
+    assert relerr(blk["dataYs"], wrp["dataYs"]) < 1e-7
+    big = m.solve_n2_host(tab[:2], 400, 1, 0.05)
+    assert (big["status"] == 0).all()
+    ens = O.Ensemble(mi, {k: v[:1] for k, v in sweep.items()})
+    ens.period = 0.05
+    _, ref, _ = O.solve_n2(ens, zNo=400, tNo=1, method="BDF", rtol=1e-9, atol=1e-13, sparse=True)
+    assert relerr(big["dataYs"][:1], ref) < RTOL_SOLVE
