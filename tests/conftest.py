@@ -22,3 +22,11 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
     return load
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """libpbr.so is a build artefact (git-ignored): build it in-tree if it is missing or stale (nvcc cross-compiles
+    for sm_100a without a GPU).  The product itself never builds implicitly; this is for a fresh checkout under pytest."""
+    from pyremot_b200 import build
+    build.build_lib()
