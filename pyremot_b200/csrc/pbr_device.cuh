@@ -1460,10 +1460,13 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
     const double dz = 1.0/(double)(zNo - 1), inv_dz = (double)(zNo - 1);   // :3439
     const int total = Gb*zNo;
     NoStore ns;
+    int gq = tid / zNo, zq = tid - gq*zNo;                            // (reactor, node) of flattened index q, advanced without divisions
     for (int q0 = 0; q0 < total; q0 += 128) {
         const int q = q0 + tid;
         const bool act = q < total;
-        const int g = act ? q / zNo : 0, z = act ? q - g*zNo : 1;
+        const int g = act ? gq : 0, z = act ? zq : 1;
+        zq += 128;
+        while (zq >= zNo) { zq -= zNo; ++gq; }
         const double* sp = s_par + g*PBR_K3_SPAR;
         InstPar pp;
         pp.Tf = sp[PAR_TF]; pp.Pf = sp[PAR_PF]; pp.Cmax = sp[PAR_CMAX]; pp.Ct0 = sp[PAR_CT0]; pp.vs0 = sp[PAR_VS0]; pp.eps = sp[PAR_EPS];

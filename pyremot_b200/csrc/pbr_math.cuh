@@ -80,3 +80,65 @@ PBR_DEV double pbr_rcp(double x) {
     return r;
 #endif
 }
+
+// pbr_log / pbr_sqrt: branch-free replacements for libdevice's log() / sqrt() (each of those carries a range check and a
+// branch to an out-of-line slow path).  PBR_FAST_LOG=0 falls back to the library versions.
+//   log:  x = m 2^e with m in [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1), log m = 2s(1 + z/3 + z^2/5 + ... + z^10/21), z = s^2
+//         (|s| <= 0.1716, truncation 2e-17); e ln2 added in two parts.  Normal positive x: <= 1.5 ulp (host test).
+//         x = 0 -> -inf, x < 0 or NaN -> NaN, +inf -> +inf by selects; subnormal x is treated as 0.
+//   sqrt: rsqrt.approx.ftz.f64 + two Newton steps + one correction of the product; x = 0 -> 0.
+#ifndef PBR_FAST_LOG
+#define PBR_FAST_LOG 1
+#endif
+PBR_CTABLE double PBR_LOGC[14] = {
+    2.0/3.0, 2.0/5.0, 2.0/7.0, 2.0/9.0, 2.0/11.0, 2.0/13.0, 2.0/15.0, 2.0/17.0, 2.0/19.0, 2.0/21.0,
+    6.93147180369123816490e-01, 1.90821492927058770002e-10,      // [10] ln2 hi, [11] ln2 lo
+    0.4342944819032518,                                          // [12] log10(e)
+    0.0};
+
+PBR_DEV double pbr_log(double x) {
+#if defined(PBR_HOST) || !PBR_FAST_LOG
+    return log(x);
+#else
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;                         // m in [1, 2)
+    const int big = (hi >= 0x3ff6a09e) ? 1 : 0;                  // m >= ~sqrt(2): halve it
+    hi -= big << 20; e += big;
+    const double m = __hiloint2double(hi, lo);
+    const double f = m - 1.0;
+    const double s = f*pbr_rcp(2.0 + f);
+    const double z = s*s;
+    double pz = PBR_LOGC[9];
+#pragma unroll
+    for (int k = 8; k >= 0; --k) pz = fma(pz, z, PBR_LOGC[k]);
+    const double ef = (double)e;
+    double r = fma(s*z, pz, ef*PBR_LOGC[11]);                    // s z P(z) + e ln2_lo
+    r = r + 2.0*s;
+    r = fma(ef, PBR_LOGC[10], r);
+    r = (x > 1.7976931348623157e308) ? x : r;                    // +inf
+    r = (x < 2.2250738585072014e-308) ? ((x < 0.0) ? __longlong_as_double(0x7ff8000000000000ll) : -__longlong_as_double(0x7ff0000000000000ll)) : r;
+    return (x != x) ? x : r;
+#endif
+}
+PBR_DEV double pbr_log10(double x) {
+#if defined(PBR_HOST) || !PBR_FAST_LOG
+    return log10(x);
+#else
+    return pbr_log(x)*PBR_LOGC[12];
+#endif
+}
+PBR_DEV double pbr_sqrt(double x) {
+#if defined(PBR_HOST) || !PBR_FAST_LOG
+    return sqrt(x);
+#else
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = y*fma(-0.5*x, y*y, 1.5);
+    y = y*fma(-0.5*x, y*y, 1.5);
+    double r = x*y;
+    r = fma(fma(-r, r, x), 0.5*y, r);
+    return (x == 0.0) ? 0.0 : r;
+#endif
+}

@@ -525,8 +525,8 @@ def _emit_body(g, needed, lines, names, ktab=None):
                 rhs = f"pbr_exp10({names[n[2]]})"
             else:
                 rhs = f"pow({a}, {names[n[2]]})"
-        elif op == "exp":
-            rhs = f"pbr_exp({a})"
+        elif op in ("exp", "log", "log10", "sqrt"):
+            rhs = f"pbr_{op}({a})"
         else:
             rhs = f"{op}({a})"
         names[i] = f"t{i}"
