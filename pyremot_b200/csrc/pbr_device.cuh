@@ -1631,24 +1631,26 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
     return cx.sum(bad) == 0.0;
 }
 
-// x_z = Ainv_z (b_z + cs_z * x_{z-1}) for all nodes; b (registers) is overwritten by x.
+// x_z = Ainv_z (b_z + cs_z * x_{z-1}) = g_z + G_z x_{z-1} for all nodes; b (registers) is overwritten by x.
+// Everything that does not depend on x_{z-1} is done by all lanes up front (g_z = Ainv_z b_z, G_z = Ainv_z diag(cs_z) in
+// registers); the serial chain per node is then one 7x7 mat-vec evaluated as a pairwise tree (depth 4 instead of a
+// 7-long FMA chain) plus the shuffle that hands x_z to the next lane.  Every lane evaluates the mat-vec in every
+// iteration (no divergence); only the owner's result is taken.  Warps hand over through shared memory + barrier.
 __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool act, const double* Asm, const double* cs, double* b) {
     const int z = cx.tid;
     const int nwz = (zNo + 31) >> 5;                       // warps that own nodes
-#ifndef PBR_K4B_PRELOAD
-#define PBR_K4B_PRELOAD 1       // 1: every lane pulls its node's inverse block into registers before the serial march
-#endif
-#if PBR_K4B_PRELOAD
-    double Ai[PBR_NV2*PBR_NV2];
-    if (act) {
+    double G[PBR_NV2*PBR_NV2], g[PBR_NV2];
 #pragma unroll
-        for (int e = 0; e < PBR_NV2*PBR_NV2; ++e) Ai[e] = Asm[e*zNo + z];
+    for (int i = 0; i < PBR_NV2; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < PBR_NV2; ++k) {
+            const double a = act ? Asm[(i*PBR_NV2 + k)*zNo + z] : 0.0;
+            acc += a*b[k];
+            G[i*PBR_NV2 + k] = a*cs[k];
+        }
+        g[i] = acc;
     }
-#define PBR_AI(e) Ai[e]
-#else
-    const double* Ai = Asm + (act ? z : 0);                  // this node's inverse block, element e at Ai[e*zNo]
-#define PBR_AI(e) Ai[(e)*zNo]
-#endif
     for (int wv = 0; wv < nwz; ++wv) {
         if (cx.wid == wv) {
             double xp[PBR_NV2];
@@ -1658,18 +1660,20 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
             for (int l = 0; l < nact; ++l) {
                 double x[PBR_NV2];
 #pragma unroll
-                for (int v = 0; v < PBR_NV2; ++v) x[v] = 0.0;
+                for (int i = 0; i < PBR_NV2; ++i) {
+                    double t[PBR_NV2];
+#pragma unroll
+                    for (int k = 0; k < PBR_NV2; ++k) t[k] = G[i*PBR_NV2 + k]*xp[k];
+                    double s = g[i];
+#pragma unroll
+                    for (int k = 0; k + 1 < PBR_NV2; k += 2) t[k] += t[k + 1];
+#pragma unroll
+                    for (int k = 0; k + 2 < PBR_NV2; k += 4) t[k] += t[k + 2];
+#pragma unroll
+                    for (int k = 0; k < PBR_NV2; k += 4) s += t[k];
+                    x[i] = s;
+                }
                 if (cx.lane == l) {
-                    double r[PBR_NV2];
-#pragma unroll
-                    for (int v = 0; v < PBR_NV2; ++v) r[v] = b[v] + cs[v]*xp[v];
-#pragma unroll
-                    for (int i = 0; i < PBR_NV2; ++i) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int k = 0; k < PBR_NV2; ++k) acc += PBR_AI(i*PBR_NV2 + k)*r[k];
-                        x[i] = acc;
-                    }
 #pragma unroll
                     for (int v = 0; v < PBR_NV2; ++v) b[v] = x[v];
                 }
