@@ -62,3 +62,24 @@ def test_gather_world_size_2_gloo(tmp_path):
                          capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_result_shards_roundtrip(tmp_path):
+    from pyremot_b200 import io
+    rng = np.random.default_rng(3)
+    N = 11
+    full = {"outlet": rng.random((N, 8)), "status": np.zeros(N, np.int32), "stats": rng.integers(0, 900, (4, N)).astype(np.int32)}
+    for rank in range(2):
+        lo, hi = ensemble.shard_bounds(N, rank, 2)
+        part = {"outlet": full["outlet"][lo:hi], "status": full["status"][lo:hi], "stats": full["stats"][:, lo:hi]}
+        io.save_shard(str(tmp_path), part, lo, hi, rank=rank, meta={"model": "N1", "rtol": 1e-9})
+    got, meta = io.load_shards(str(tmp_path))
+    assert meta == {"model": "N1", "rtol": 1e-9}
+    for k in full:
+        assert np.array_equal(got[k], full[k])
+    os.remove(str(tmp_path / "shard_0000.npz"))
+    try:
+        io.load_shards(str(tmp_path))
+        assert False, "a gap in the row range must be detected"
+    except ValueError:
+        pass
