@@ -59,6 +59,25 @@ def cpu_path(n_inst, cores=None, tol=None):
     return n_inst/dt, dt, sum(r[1] for r in res)
 
 
+def cpu_rhs_rates():
+    """RHS evaluations per second of the CPU path, one core, called the way the reference calls its callbacks
+    (one reactor per call): modelEquationN1 and modelEquationN2 at zNo = 100 (oracle port)."""
+    from oracle import pbr_oracle as O
+    from pyremot_b200 import cases
+    e1 = O.Ensemble(cases.readme_case("N1"))
+    y1 = e1.iv_n1()
+    e2 = O.Ensemble(cases.readme_case("N2"))
+    Y2 = e2.iv_n2(100)
+    out = {}
+    for name, f, n in (("n1", lambda: e1.rhs_n1(y1), 300), ("n2_z100", lambda: e2.rhs_n2(Y2), 60)):
+        f()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            f()
+        out[name] = n/(time.perf_counter() - t0)
+    return out
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -271,7 +290,7 @@ def run_gpu(a):
                          "mean_steps": float(stats[0].mean()), "mean_nfev": float(stats[2].mean()), "mean_nlu": float(stats[3].mean()),
                          "max_over_mean_nfev": float(stats[2].max()/stats[2].mean())},
             "rhs_n2_roofline": rhs,
-            "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cores, "kind": "port", "rhs_evals_per_s_per_core": cpu_rhs_rates(),
                              "sample": f"rows 0..{n_cpu-1} of the same table, SciPy LSODA at the reference's default rtol 1e-3/atol 1e-6 "
                                        f"on the NumPy RHS restatement, {cores} processes, {cpu_dt:.1f} s"},
         }
