@@ -249,7 +249,7 @@ class Model:
         self._check(lib().pbr_rhs_n2(self._ctx, N, zNo, par.data_ptr(), Y.data_ptr(), dY.data_ptr(), self._stream()))
         return dY
 
-    def solve_n1(self, par, rtol=1e-8, atol=1e-12, n_out=101, profile=True, max_steps=0, stats=True):
+    def solve_n1(self, par, rtol=1e-9, atol=1e-13, n_out=101, profile=True, max_steps=0, stats=True):
         """K2 on device tensors. Returns dict(prof_y [n_out,nv1,N] or None, outlet_y [nv1,N], status [N], stats [4,N])."""
         import torch
         N = par.shape[1]
@@ -271,7 +271,7 @@ class Model:
         self._check(lib().pbr_unscale_n1(self._ctx, N, K, par.data_ptr(), y.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
-    def solve_n1_host(self, inst_in, rtol=1e-8, atol=1e-12, n_out=101, profile=True, max_steps=0, out=None):
+    def solve_n1_host(self, inst_in, rtol=1e-9, atol=1e-13, n_out=101, profile=True, max_steps=0, out=None):
         """Whole N1 path through the host-buffer C-ABI call (H2D, K0, K2, K5, D2H inside).
 
         inst_in: numpy [N,k_in].  Returns dict(dataYs [N,nv1,n_out] or None, outlet [N,nv1], status [N], stats [4,N]).
