@@ -290,6 +290,7 @@ def run_gpu(a):
                          "mean_steps": float(stats[0].mean()), "mean_nfev": float(stats[2].mean()), "mean_nlu": float(stats[3].mean()),
                          "max_over_mean_nfev": float(stats[2].max()/stats[2].mean())},
             "rhs_n2_roofline": rhs,
+            "n2_config3": bench_n2_config3(model),
             "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cores, "kind": "port", "rhs_evals_per_s_per_core": cpu_rhs_rates(),
                              "sample": f"rows 0..{n_cpu-1} of the same table, SciPy LSODA at the reference's default rtol 1e-3/atol 1e-6 "
                                        f"on the NumPy RHS restatement, {cores} processes, {cpu_dt:.1f} s"},
@@ -298,6 +299,31 @@ def run_gpu(a):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_n2_config3(model):
+    """BASELINE configs[2]: dynamic model, 100 axial nodes, 4,096 instances, start-up transient (tNo = 5, period 0.5 s).
+    Secondary figure (the headline metric is configs[1]); one warm-up pass, one timed pass with CUDA events."""
+    import torch
+    from pyremot_b200 import cases
+    from pyremot_b200.api import get_model
+    mi2 = cases.readme_case("N2")
+    m2 = get_model(mi2, device=model.device)
+    N, zNo, tNo, period = 4096, 100, 5, 0.5
+    rows = cases.ensemble_rows(N)
+    tab = torch.from_numpy(m2.instance_table(mi2, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]})).cuda()
+    par = m2.prolog(tab)
+    r = m2.solve_n2(par, zNo, tNo, period, rtol=RTOL, atol=ATOL)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = m2.solve_n2(par, zNo, tNo, period, rtol=RTOL, atol=ATOL)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    st = r["stats"].cpu().numpy()
+    return {"kernel": "pbr_k4b_solve_n2", "workload": "N2 dynamic model, zNo=100, tNo=5, period 0.5 s, 4096 instances (BASELINE configs[2])",
+            "ms": ms, "solves_per_s": N/(ms*1e-3), "failed": int((r["status"] != 0).sum().item()), "mean_steps": float(st[0].mean()),
+            "node_steps_per_s": float(st[0].sum())*zNo/(ms*1e-3), "rtol": RTOL}
 
 
 def bench_rhs_n2(model, mi, peaks):
