@@ -1631,54 +1631,49 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
     return cx.sum(bad) == 0.0;
 }
 
-// x_z = Ainv_z (b_z + cs_z * x_{z-1}) = g_z + G_z x_{z-1} for all nodes; b (registers) is overwritten by x.
-// Everything that does not depend on x_{z-1} is done by all lanes up front (g_z = Ainv_z b_z, G_z = Ainv_z diag(cs_z) in
-// registers); the serial chain per node is then one 7x7 mat-vec evaluated as a pairwise tree (depth 4 instead of a
-// 7-long FMA chain) plus the shuffle that hands x_z to the next lane.  Every lane evaluates the mat-vec in every
-// iteration (no divergence); only the owner's result is taken.  Warps hand over through shared memory + barrier.
-__device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool act, const double* Asm, const double* cs, double* b) {
+// x_z = Ainv_z (b_z + cs_z * x_{z-1}) = g_z + Ainv_z (cs_z * x_{z-1}) for all nodes; b (registers) is overwritten by x.
+// g_z = Ainv_z b_z does not depend on the march and is computed by all lanes up front (into gsm = the iterate-exchange
+// array, idle at this point).  The serial chain per node is then split over lanes: lane j < NV2 of the marching warp
+// computes row j of the 7x7 mat-vec straight out of the node's inverse block in shared memory, and NV2 shuffles gather
+// x_z for the next node.  ~60 issued instructions and ~100 cycles of latency per node, leaving the issue slots to the
+// SM's other block.  Warps hand over through shared memory + barrier.
+__device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool act, const double* Asm, double* gsm,
+                                              const double* cs, double* b) {
     const int z = cx.tid;
     const int nwz = (zNo + 31) >> 5;                       // warps that own nodes
-    double G[PBR_NV2*PBR_NV2], g[PBR_NV2];
+    __syncthreads();                                       // gsm (= Ysm) is no longer read as the iterate
+    if (act) {
 #pragma unroll
-    for (int i = 0; i < PBR_NV2; ++i) {
-        double acc = 0.0;
+        for (int i = 0; i < PBR_NV2; ++i) {
+            double acc = 0.0;
 #pragma unroll
-        for (int k = 0; k < PBR_NV2; ++k) {
-            const double a = act ? Asm[(i*PBR_NV2 + k)*zNo + z] : 0.0;
-            acc += a*b[k];
-            G[i*PBR_NV2 + k] = a*cs[k];
+            for (int k = 0; k < PBR_NV2; ++k) acc += Asm[(i*PBR_NV2 + k)*zNo + z]*b[k];
+            gsm[i*zNo + z] = acc;
         }
-        g[i] = acc;
     }
+    __syncthreads();
+    const int row = (cx.lane < PBR_NV2) ? cx.lane : 0;     // the mat-vec row this lane contributes
     for (int wv = 0; wv < nwz; ++wv) {
         if (cx.wid == wv) {
             double xp[PBR_NV2];
 #pragma unroll
             for (int v = 0; v < PBR_NV2; ++v) xp[v] = (wv == 0) ? 0.0 : cx.red[v];
-            const int nact = (zNo - wv*32 < 32) ? (zNo - wv*32) : 32;
+            const int zb = wv*32;
+            const int nact = (zNo - zb < 32) ? (zNo - zb) : 32;
             for (int l = 0; l < nact; ++l) {
-                double x[PBR_NV2];
+                const int zl = zb + l;
+                double arow[PBR_NV2];
 #pragma unroll
-                for (int i = 0; i < PBR_NV2; ++i) {
-                    double t[PBR_NV2];
+                for (int k = 0; k < PBR_NV2; ++k) arow[k] = Asm[(row*PBR_NV2 + k)*zNo + zl];
+                double acc = gsm[row*zNo + zl];
 #pragma unroll
-                    for (int k = 0; k < PBR_NV2; ++k) t[k] = G[i*PBR_NV2 + k]*xp[k];
-                    double s = g[i];
+                for (int k = 0; k < PBR_NV2; ++k) acc += arow[k]*(__shfl_sync(0xffffffffu, cs[k], l)*xp[k]);
 #pragma unroll
-                    for (int k = 0; k + 1 < PBR_NV2; k += 2) t[k] += t[k + 1];
-#pragma unroll
-                    for (int k = 0; k + 2 < PBR_NV2; k += 4) t[k] += t[k + 2];
-#pragma unroll
-                    for (int k = 0; k < PBR_NV2; k += 4) s += t[k];
-                    x[i] = s;
-                }
+                for (int v = 0; v < PBR_NV2; ++v) xp[v] = __shfl_sync(0xffffffffu, acc, v);
                 if (cx.lane == l) {
 #pragma unroll
-                    for (int v = 0; v < PBR_NV2; ++v) b[v] = x[v];
+                    for (int v = 0; v < PBR_NV2; ++v) b[v] = xp[v];
                 }
-#pragma unroll
-                for (int v = 0; v < PBR_NV2; ++v) xp[v] = __shfl_sync(0xffffffffu, x[v], l);
             }
             if (cx.lane == 0) {
 #pragma unroll
@@ -1812,7 +1807,7 @@ extern "C" __global__ void __launch_bounds__(256) pbr_k4b_solve_n2(long N, int z
 #pragma unroll
                                 for (int v = 0; v < NV; ++v) b[v] = c*f[v] - Psm[v*zNo + z] - d[v];
                             }
-                            pbr_k4b_march(cx, zNo, act, Asm, cs, b);
+                            pbr_k4b_march(cx, zNo, act, Asm, Ysm, cs, b);
                             double nrm = 0.0;
                             if (act) {
 #pragma unroll
