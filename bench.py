@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — reactor-solves/sec on BASELINE.json configs[1] (N1 steady-state ensemble, 65,536 reactors per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--extras]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch: K0 prolog -> K2 fused BDF solve -> K5 un-scale of the
@@ -290,7 +290,7 @@ def run_gpu(a):
                          "mean_steps": float(stats[0].mean()), "mean_nfev": float(stats[2].mean()), "mean_nlu": float(stats[3].mean()),
                          "max_over_mean_nfev": float(stats[2].max()/stats[2].mean())},
             "rhs_n2_roofline": rhs,
-            "n2_config3": bench_n2_config3(model),
+            **({"n2_config3": bench_n2_config3(model)} if a.extras else {}),
             "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cores, "kind": "port", "rhs_evals_per_s_per_core": cpu_rhs_rates(),
                              "sample": f"rows 0..{n_cpu-1} of the same table, SciPy LSODA at the reference's default rtol 1e-3/atol 1e-6 "
                                        f"on the NumPy RHS restatement, {cores} processes, {cpu_dt:.1f} s"},
@@ -388,6 +388,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--extras", action="store_true", help="also time BASELINE configs[2] (N2, 4096 x zNo=100) after the timed region")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
