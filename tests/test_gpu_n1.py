@@ -249,3 +249,31 @@ def test_failures_are_reported_per_instance_not_hung(torch_cuda):
     assert np.array_equal(one["outlet"], good["outlet"][:1])
     odd = rmtExeBatch(mi, {k: v[10:33] for k, v in sweep.items()})
     assert np.array_equal(odd["outlet"], good["outlet"][10:33])
+
+
+def test_other_kinetics_and_process_types_vs_oracle(torch_cuda):
+    """Model shapes other than the methanol/DME non-iso-thermal one: the CH4 coupling kinetics of
+    PyREMOT/tests/test_rmt_N2_CH4.py run as N1 (3 species, 1 reaction, SpCoi-based rate, adiabatic Tm = 0: nv1 = 5,
+    256-thread blocks) and an iso-thermal methanol/DME sweep (nv1 = 7), both against the oracle at converged tolerance."""
+    from pyremot_b200 import rmtExeBatch
+    mi = cases.ch4_n2_case()
+    mi["model"] = "N1"
+    N = 300                                             # not a multiple of the block size
+    rng = np.random.default_rng(5)
+    sweep = {"T": 900 + 150*rng.random(N), "P": 2e5 + 2e5*rng.random(N)}
+    sweep["conc"] = np.array([0.9, 0.05, 0.05])[None, :]*(sweep["P"]/(cases.R_CONST*sweep["T"]))[:, None]
+    out = rmtExeBatch(mi, sweep, profile=True)
+    assert (out["status"] == 0).all() and out["dataYs"].shape == (N, 5, 101)
+    idx = [0, 150, 299]
+    ens = O.Ensemble(mi, {k: v[idx] for k, v in sweep.items()})
+    _, ref, _ = O.solve_n1(ens, method="BDF", rtol=1e-11, atol=1e-14)
+    assert relerr(out["dataYs"][idx], ref) < RTOL_SOLVE
+    mi = cases.readme_case("N1", "iso-thermal")
+    rows = cases.ensemble_rows(200)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"]}
+    out = rmtExeBatch(mi, sweep, profile=True)
+    assert (out["status"] == 0).all() and out["dataYs"].shape == (200, 7, 101)
+    idx = [3, 199]
+    ens = O.Ensemble(mi, {k: v[idx] for k, v in sweep.items()})
+    _, ref, _ = O.solve_n1(ens, method="BDF", rtol=1e-11, atol=1e-14)
+    assert relerr(out["dataYs"][idx], ref) < RTOL_SOLVE
