@@ -1684,13 +1684,17 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
     }
 }
 
-extern "C" __global__ void __launch_bounds__(256) pbr_k4b_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
-                                                                   double rtol, double atol, int max_steps,
-                                                                   double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
+// The body is shared by two kernels: pbr_k4b_solve_n2 (<= 256 threads, history in shared memory) and pbr_k4c_solve_n2
+// (<= 512 threads = up to 512 nodes, history in a global scratch slab per block that stays L2-resident; launch bounds
+// cap it at 128 registers, so it spills, but it keeps the block-per-reactor structure for BASELINE config 4's zNo = 400).
+template <bool D_GLOBAL>
+__device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+                                             double rtol, double atol, int max_steps, double* __restrict__ gwork,
+                                             double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
     extern __shared__ double pbr_smem[];
     const int NV = PBR_NV2;
-    double* Dsm = pbr_smem;                                // [PBR_DROWS*NV][zNo]
-    double* Asm = Dsm + (long)PBR_DROWS*NV*zNo;            // [NV*NV][zNo]
+    double* Dsm = D_GLOBAL ? gwork + (long)blockIdx.x*PBR_DROWS*NV*zNo : pbr_smem;     // [PBR_DROWS*NV][zNo]
+    double* Asm = D_GLOBAL ? pbr_smem : Dsm + (long)PBR_DROWS*NV*zNo;                  // [NV*NV][zNo]
     double* Ysm = Asm + (long)NV*NV*zNo;                   // [NV][zNo]
     double* Psm = Ysm + (long)NV*zNo;                      // psi
     double* Ism = Psm + (long)NV*zNo;                      // 1/scale
@@ -1895,6 +1899,18 @@ extern "C" __global__ void __launch_bounds__(256) pbr_k4b_solve_n2(long N, int z
         }
         __syncthreads();
     }
+}
+
+extern "C" __global__ void __launch_bounds__(256) pbr_k4b_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+                                                                   double rtol, double atol, int max_steps,
+                                                                   double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
+    pbr_k4b_body<false>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats);
+}
+
+extern "C" __global__ void __launch_bounds__(512) pbr_k4c_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+                                                                   double rtol, double atol, int max_steps, double* __restrict__ gwork,
+                                                                   double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
+    pbr_k4b_body<true>(N, zNo, tNo, period, par, rtol, atol, max_steps, gwork, snaps, status, stats);
 }
 
 // ---- K5b epilog (N2): scaled snapshots [N][tNo][NV2][zNo] -> dataYs [N][tNo][NC+1][zNo] = [x_i ; T]
