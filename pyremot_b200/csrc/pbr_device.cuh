@@ -633,16 +633,15 @@ struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
 // Storage: D = Strided array of PBR_DROWS*NV doubles (difference history), LU = Strided NV*NV (Newton matrix).
 //
 // Control flow is FLAT: one trip of the main loop = one step attempt, and every trip runs the same sequence
-//   [even trips: rescale history, Jacobian + LU at the predictor] -> predictor -> <=4 Newton iterations ->
-//   error test -> [accept: history update, dense output; odd trips: order/step selection]
-// with per-lane predicates only (no break/continue), so the 32 reactors of a warp stay converged although each
-// has its own step size, order and acceptance history.  The trip counter is the same for every lane, which is
-// what makes the schedule warp-uniform.  Differences from scipy's BDF driver, all forced by that layout:
-// (i) the Jacobian is analytic and is refreshed together with the LU factorisation on every EVEN trip for all
-// lanes (scipy keeps J/LU until Newton fails or h changes: bdf.py:365-379); (ii) step-size / order changes are
-// decided at the end of odd trips and applied lazily at the top of the next (even) trip, fused with the clip to
-// the end point (change_D composes: rescaling by f1 then f2 == rescaling by f1*f2); a lane whose attempt failed
-// on an even trip sits out the following odd trip.
+//   rescale history -> predictor -> Jacobian + LU at the predictor -> <=4 Newton iterations -> error test ->
+//   [accept: history update, dense output, every PBR_SEL_PERIOD-th trip: order/step selection]
+// with per-lane predicates only (no break/continue), so the reactors of a warp (and, with multi-warp blocks, of the
+// block) stay converged although each has its own step size, order and acceptance history.  The trip counter is the
+// same for every lane, which is what makes the schedule uniform.  Differences from scipy's BDF driver, all forced
+// by that layout: (i) the Jacobian is analytic and is refreshed together with the LU factorisation at EVERY step
+// attempt (scipy keeps J/LU until Newton fails or h changes, bdf.py:365-379; a refresh on every 2nd-4th trip only
+// was measured and rejected); (ii) step-size / order changes are applied lazily at the top of the
+// next trip, fused with the clip to the end point (change_D composes: rescaling by f1 then f2 == rescaling by f1*f2).
 #if !defined(PBR_HOST) && defined(PBR_N1_BLOCK) && PBR_N1_BLOCK > 32
 // multi-warp blocks: all warps of the block start every step attempt together (shared instruction stream in the
 // SM's instruction caches); the loop ends when no lane of the block is active any more.
@@ -654,9 +653,6 @@ struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
 #endif
 #define PBR_MID_BARRIER(bit) if (PBR_MID_SYNC & (bit)) __syncthreads();
 #define PBR_TRIP_CONTINUE(active, trip) ((((trip) % PBR_SYNC_PERIOD) != 0) ? true : (__syncthreads_or(active) != 0))
-#endif
-#ifndef PBR_JAC_PERIOD
-#define PBR_JAC_PERIOD 1
 #endif
 // Order / step-size selection is only allowed on every PBR_SEL_PERIOD-th trip (same trips for all lanes): the
 // history rescale that follows is ~600 instructions and, decided per lane, would run on almost every trip for a
@@ -736,9 +732,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
     bool active = live;
 
     while (PBR_TRIP_CONTINUE(active, trip)) {
-        const bool refresh = (trip % PBR_JAC_PERIOD) == 0;            // warp-uniform: every lane has the same trip count
-        // ---------------- 1. step size for this attempt; lazy history rescale (refresh trips only) ----------------
-        bool sit_out = false;
+        // ---------------- 1. step size for this attempt; lazy history rescale ----------------
         double t_new;
         {
             double hn = h*pend;
@@ -746,8 +740,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             if (clip) hn = t_bound - t;
             const double fac = hn/h;
             if (active && fac != 1.0) {
-                if (refresh) { pbr_change_D<NV>(D, order, fac); n_equal = 0; h = hn; pend = 1.0; }
-                else sit_out = true;                                  // wait for the next refresh trip
+                pbr_change_D<NV>(D, order, fac); n_equal = 0; h = hn; pend = 1.0;
             }
             t_new = clip ? t_bound : t + h;
         }
@@ -765,9 +758,9 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             iscale[v] = pbr_rcp(atol + rtol*fabs(yp));
         }
         PBR_MID_BARRIER(2)
-        // ---------------- 3. refresh trips: Jacobian + LU of I - cJ at the predictor (also yields f(y_pred)) ----------------
+        // ---------------- 3. Jacobian + LU of I - cJ at the predictor (also yields f(y_pred)) ----------------
         bool lu_good = true;
-        if (refresh && active) {
+        if (active) {
             LuStore st = {LU, c};
             pbr_n1_eval<true>(y, p, f, st);
             lu_good = pbr_lu_factor<NV>(LU, piv);
@@ -780,7 +773,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
         // PBR_KAPPA_PERIOD-th trip) and, while the predicted second correction stays below PBR_NEWTON_SKIP_TOL (in
         // units of the error tolerance; scipy itself accepts 0.03 at loose rtol), the verification iteration --
         // a full RHS evaluation that changes nothing -- is skipped.
-        bool converged = false, running = active && lu_good && !sit_out;
+        bool converged = false, running = active && lu_good;
         const bool tried = running;
         double dy_norm_old = -1.0;
         int n_iter = 0;
@@ -788,7 +781,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
         for (int k = 0; k < PBR_NEWTON_MAXITER; ++k) {
             if (running) {
                 n_iter = k + 1;
-                if (k > 0 || !refresh) { pbr_n1_rhs_call(p, y, f); stt.nfev++; }
+                if (k > 0) { pbr_n1_rhs_call(p, y, f); stt.nfev++; }
                 double b[NV], nrm = 0.0;
                 bool fin = true;
 #pragma unroll
@@ -805,7 +798,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
 #pragma unroll
                     for (int v = 0; v < NV; ++v) { y[v] += b[v]; d[v] += b[v]; }
                     if (k == 1) kappa = rate/fmax(dy_norm_old, 1e-300);
-                    const bool quad_ok = PBR_NEWTON_SKIP && k == 0 && refresh && (trip % PBR_KAPPA_PERIOD) != 0 &&
+                    const bool quad_ok = PBR_NEWTON_SKIP && k == 0 && (trip % PBR_KAPPA_PERIOD) != 0 &&
                                          kappa*dy_norm*dy_norm < PBR_NEWTON_SKIP_TOL;
                     if (dy_norm == 0.0 || quad_ok || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; running = false; }
                     dy_norm_old = dy_norm;
