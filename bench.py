@@ -157,10 +157,10 @@ def algorithmic_flops(model, stats):
     Per-unit figures: every +,-,*,/ and every exp/log/log10/pow/sqrt counts 1.
     rate DAG ops are counted exactly from the compiled expressions; the balance / linear-algebra terms are
     hand counts of the formulas in csrc/pbr_device.cuh."""
-    nv, n, R = model.nv1, model.n, model.n_rxn
+    nv, n, R = model.n1_vars, model.n, model.n_rxn   # nv: integrated variables (extent coordinates: R + 2)
     ops_r, ops_rj = model.rates.op_counts()
     rhs = ops_r + (16*n + 14*R + 40)                 # balances: scaling, x_i, M, rho, Ergun, S^T r, Cp, dH, energy
-    jac = ops_rj + (16*n + 14*R + 40) + nv*(4*R*n//2 + 6*n + 30)    # chain rule per column + stores
+    jac = ops_rj + (16*n + 14*R + 40) + (n + 2)*(4*R*n//2 + 6*n + 30)    # chain rule per species / p / theta + stores
     lu = (2*nv**3)//3 + nv*nv
     solve = 2*nv*nv + 6*nv                           # triangular solves + Newton update / norms
     step = 30*nv                                     # predictor, psi, error norms, D update (per accepted step)

@@ -68,6 +68,9 @@ int pbr_set_species(pbr_ctx* ctx, int n_comp, int n_rxn, const double* MW, const
 int pbr_load_rates(pbr_ctx* ctx, const char* cuda_src, int n_par, const char* cache_dir, const char** log);
 
 int pbr_model_dims(pbr_ctx* ctx, int* n_comp, int* n_rxn, int* n_par, int* nv1, int* nv2, int* k_in, int* k_par);
+/* How K2 integrates N1: n_vars = number of integrated variables (n_rxn+2 in reaction-extent coordinates when
+ * n_rxn < n_comp, else nv1), threads per block and dynamic shared memory per block.  Informational (roofline counts). */
+int pbr_n1_layout(pbr_ctx* ctx, int* n_vars, int* block_threads, int* smem_bytes);
 const char* pbr_model_source(pbr_ctx* ctx);          /* full program text handed to NVRTC */
 int pbr_model_cubin(pbr_ctx* ctx, const void** data, unsigned long* size);
 int pbr_kernel_attr(pbr_ctx* ctx, const char* kernel, int* regs, int* static_smem, int* local_bytes);

@@ -22,6 +22,19 @@
 #define PBR_NV1 (PBR_NC + (PBR_ISO ? 1 : 2))   // N1 state: c_1..c_n, p, [theta]
 #endif
 #define PBR_NV2 (PBR_NC + (PBR_ISO ? 0 : 1))   // N2 per-node state: c_1..c_n, [theta]
+// N1 is INTEGRATED in reaction-extent coordinates when there are fewer reactions than species: every species balance is
+// dc_i/dz = sum_j nu_ji r_j / (G w) with the same factor 1/(G w) (pbHomoReactor.py:3283-3289, GaMaCoTe0 identical for all i
+// under the "MAX" setting), so c(z) = c0 + S^T x(z) exactly, with dx_j/dz = r_j/(G w).  The integrated vector is
+// x = [x_1..x_R, p, theta] (NX = R+2 instead of n+2): 5x5 instead of 8x8 Newton matrices and 40 % less history for the
+// methanol/DME system.  Error control is unchanged: all norms are taken on the reconstructed [c, p, theta].
+#ifndef PBR_N1_REDUCED
+#if PBR_NR < PBR_NC
+#define PBR_N1_REDUCED 1
+#else
+#define PBR_N1_REDUCED 0
+#endif
+#endif
+#define PBR_NX ((PBR_N1_REDUCED ? PBR_NR : PBR_NC) + (PBR_ISO ? 1 : 2))
 #define PBR_NPA (PBR_NP > 0 ? PBR_NP : 1)
 
 #define PBR_R 8.314472          // core/constants.py:8
@@ -324,27 +337,175 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
     }
 }
 
+// ---- extent coordinates: x[NX] <-> full scaled state y[NV1] = [c_1..c_n, p, theta]
+PBR_DEV void pbr_n1x_expand(const double* x, const InstPar& p, double* y) {
+#if PBR_N1_REDUCED
+#pragma unroll
+    for (int i = 0; i < PBR_NC; ++i) y[i] = p.c0[i];
+#define PBR_ACC(j, i, nu) y[i] += (nu)*x[j];
+    PBR_S_NNZ(PBR_ACC)
+#undef PBR_ACC
+    y[PBR_NC] = x[PBR_NR];
+    if (!PBR_ISO) y[PBR_NC + (PBR_ISO ? 0 : 1)] = x[PBR_NR + (PBR_ISO ? 0 : 1)];
+#else
+#pragma unroll
+    for (int i = 0; i < PBR_NV1; ++i) y[i] = x[i];
+#endif
+}
+
+// sum_i ((M v)_i * iscale_i)^2 with M the linear map x-increment -> [dc, dp, dtheta]
+PBR_DEV double pbr_n1x_norm2(const double* v, const double* iscale) {
+    double full[PBR_NV1];
+#if PBR_N1_REDUCED
+#pragma unroll
+    for (int i = 0; i < PBR_NC; ++i) full[i] = 0.0;
+#define PBR_ACC(j, i, nu) full[i] += (nu)*v[j];
+    PBR_S_NNZ(PBR_ACC)
+#undef PBR_ACC
+    full[PBR_NC] = v[PBR_NR];
+    if (!PBR_ISO) full[PBR_NC + (PBR_ISO ? 0 : 1)] = v[PBR_NR + (PBR_ISO ? 0 : 1)];
+#else
+#pragma unroll
+    for (int i = 0; i < PBR_NV1; ++i) full[i] = v[i];
+#endif
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < PBR_NV1; ++i) { const double e = full[i]*iscale[i]; s += e*e; }
+    return s;
+}
+
+PBR_DEV void pbr_n1x_iscale(const double* x, const InstPar& p, double rtol, double atol, double* iscale) {
+    double y[PBR_NV1];
+    pbr_n1x_expand(x, p, y);
+#pragma unroll
+    for (int i = 0; i < PBR_NV1; ++i) iscale[i] = pbr_rcp(atol + rtol*fabs(y[i]));
+}
+
+// N1 right-hand side and Jacobian in the integrated coordinates.  Not reduced: identical to pbr_n1_eval.
+template <bool JAC, class Store>
+PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& st) {
+#if !PBR_N1_REDUCED
+    pbr_n1_eval<JAC>(x, p, f, st);
+#else
+    const int n = PBR_NC, R = PBR_NR;
+    double y[PBR_NV1];
+    pbr_n1x_expand(x, p, y);
+    const double pr = y[n];
+    const double th = PBR_ISO ? 0.0 : y[n + (PBR_ISO ? 0 : 1)];
+    const double T = th*p.Tf + p.Tf;
+    const double P = pr*p.Pf;
+    PointEval e;
+    pbr_point<JAC>(y, T, P, p, e);
+    const double w = (e.Ct*p.Pf)*pbr_rcp(p.Ct0*P);
+    const double vs = p.vs0*w;
+    const double zP = p.zP;
+    f[R] = -(p.E1*vs + p.E2*e.rho*vs*vs)*zP;
+    const double invGw = pbr_rcp(p.G*w);
+#pragma unroll
+    for (int j = 0; j < R; ++j) f[j] = e.r[j]*invGw;                 // d x_j / dz = r_j / (G w)
+    double Den = 1.0, fth = 0.0;
+    if (!PBR_ISO) {
+        const double Num = (-e.Hsum + e.Q)*p.iGH;
+        Den = (e.rho*p.irho0)*((e.Cpmix*p.iCp0)*p.eps)*w;
+        fth = Num*pbr_rcp(Den);
+        f[R + 1] = fth;
+    }
+    if (JAC) {
+        const int NXr = PBR_NX;
+        double Jx[PBR_NX][PBR_NX];
+#pragma unroll
+        for (int a = 0; a < NXr; ++a)
+#pragma unroll
+            for (int b = 0; b < NXr; ++b) Jx[a][b] = 0.0;
+        const double cmct = p.Cmax*e.invCt;
+        const double iGH = p.iGH, iDen = pbr_rcp(Den), irho = pbr_rcp(e.rho), iCp = PBR_ISO ? 1.0 : pbr_rcp(e.Cpmix), ipr = pbr_rcp(pr);
+        const double dfp_dw = -zP*(p.E1*p.vs0 + 2.0*p.E2*e.rho*p.vs0*p.vs0*w);
+        const double dfp_drho = -zP*(p.E2*vs*vs);
+        const double rhoM = e.rho*pbr_rcp(e.M);
+        double drk[PBR_NR];
+        // ---- species derivatives, folded into the extent columns: d/dx_j = sum_k nu_jk d/dc_k
+#pragma unroll
+        for (int k = 0; k < n; ++k) {
+            pbr_dr_dc(e, p, k, 1.0, drk);
+            double col[PBR_NX];
+            const double dw = w*cmct;
+            const double drho = rhoM*cmct*(1e-3*PBR_MW[k] - e.M);
+#pragma unroll
+            for (int j = 0; j < R; ++j) col[j] = drk[j]*invGw - f[j]*cmct;
+            col[R] = dfp_dw*dw + dfp_drho*drho;
+            if (!PBR_ISO) {
+                double sH = 0.0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) sH += drk[j]*e.dH[j];
+                const double dNum = -sH*iGH;
+                const double dDen = Den*(drho*irho + cmct*(e.cpm[k] - e.Cpmix)*iCp + cmct);
+                col[R + (PBR_ISO ? 0 : 1)] = (dNum - fth*dDen)*iDen;
+            }
+#define PBR_ACC(j, i, nu) if ((i) == k) { _Pragma("unroll") for (int a = 0; a < NXr; ++a) Jx[a][j] += (nu)*col[a]; }
+            PBR_S_NNZ(PBR_ACC)
+#undef PBR_ACC
+        }
+        // ---- pressure column
+        {
+#pragma unroll
+            for (int j = 0; j < R; ++j) drk[j] = p.Pf*e.drP[j];
+            const double dw = -w*ipr, drho = e.rho*ipr;
+#pragma unroll
+            for (int j = 0; j < R; ++j) Jx[j][R] = drk[j]*invGw + f[j]*ipr;
+            Jx[R][R] = dfp_dw*dw + dfp_drho*drho;
+            if (!PBR_ISO) {
+                double sH = 0.0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) sH += drk[j]*e.dH[j];
+                Jx[R + (PBR_ISO ? 0 : 1)][R] = (-sH*iGH)*iDen;
+            }
+        }
+        // ---- temperature column
+        if (!PBR_ISO) {
+            const int ct = R + (PBR_ISO ? 0 : 1);
+#pragma unroll
+            for (int j = 0; j < R; ++j) drk[j] = p.Tf*e.drT[j];
+            const double drho = -e.rho*p.Tf*pbr_rcp(T);
+#pragma unroll
+            for (int j = 0; j < R; ++j) Jx[j][ct] = drk[j]*invGw;
+            Jx[R][ct] = dfp_drho*drho;
+            double sH = 0.0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) sH += drk[j]*e.dH[j] + p.Tf*e.r[j]*e.dHdT[j];
+            const double dQ = (p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
+            const double dNum = (-sH + dQ)*iGH;
+            const double dDen = Den*(drho*irho + p.Tf*e.dCpmixT*iCp);
+            Jx[ct][ct] = (dNum - fth*dDen)*iDen;
+        }
+#pragma unroll
+        for (int a = 0; a < NXr; ++a)
+#pragma unroll
+            for (int b = 0; b < NXr; ++b) st(a, b, Jx[a][b]);
+    }
+#endif
+}
+
 // Out-of-line copy of the plain N1 RHS for the integrator's rarely taken paths (initial-step probe, verification
 // Newton iterations): it reloads the instance constants from global memory so that nothing of the caller has to
 // live in local memory, and it keeps ~3300 instructions out of the solver kernel's instruction stream.
 PBR_NOINLINE void pbr_n1_rhs_ool(const double* par, long N, long i, const double* y, double* f) {
     InstPar q; pbr_load_par(par, N, i, q);
-    double yy[PBR_NV1], ff[PBR_NV1];
+    double yy[PBR_NX], ff[PBR_NX];
 #pragma unroll
-    for (int v = 0; v < PBR_NV1; ++v) yy[v] = y[v];
+    for (int v = 0; v < PBR_NX; ++v) yy[v] = y[v];
     NoStore ns;
-    pbr_n1_eval<false>(yy, q, ff, ns);
+    pbr_n1x_eval<false>(yy, q, ff, ns);
 #pragma unroll
-    for (int v = 0; v < PBR_NV1; ++v) f[v] = ff[v];
+    for (int v = 0; v < PBR_NX; ++v) f[v] = ff[v];
 }
 
 PBR_DEV void pbr_n1_rhs_call(const InstPar& p, const double* y, double* f) {
-    double yt[PBR_NV1], ft[PBR_NV1];           // only these temporaries are address-taken
+    double yt[PBR_NX], ft[PBR_NX];             // only these temporaries are address-taken
 #pragma unroll
-    for (int v = 0; v < PBR_NV1; ++v) yt[v] = y[v];
+    for (int v = 0; v < PBR_NX; ++v) yt[v] = y[v];
     pbr_n1_rhs_ool(p.src, p.srcN, p.srci, yt, ft);
 #pragma unroll
-    for (int v = 0; v < PBR_NV1; ++v) f[v] = ft[v];
+    for (int v = 0; v < PBR_NX; ++v) f[v] = ft[v];
 }
 
 // =====================================================================================================
@@ -551,7 +712,7 @@ PBR_DEV bool pbr_invert(const Strided& a) {
 
 struct LuStore {            // receives Jacobian entries, stores the Newton matrix I - c*J
     Strided a; double c;
-    PBR_DEV void operator()(int i, int k, double v) const { a[i*PBR_NV1 + k] = (i == k ? 1.0 : 0.0) - c*v; }
+    PBR_DEV void operator()(int i, int k, double v) const { a[i*PBR_NX + k] = (i == k ? 1.0 : 0.0) - c*v; }
 };
 
 // =====================================================================================================
@@ -679,12 +840,13 @@ struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
 template <class Sink>
 PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double atol, int n_out, int max_steps,
                          const Strided& D, const Strided& LU, Sink& out, N1Stats& stt, bool live = true) {
-    const int NV = PBR_NV1;
+    const int NV = PBR_NX;                             // integrated variables (extent coordinates when reduced)
+    const int NO = PBR_NV1;                            // variables the error norms are taken over: [c, p, theta]
     const double t_bound = 1.0;                        // DoLe = 1, pbHomoReactor.py:2856
     const double dz_out = 1.0/(double)(n_out - 1);     // np.linspace(0, 1, zNo+1), :2862
     const double newton_tol = fmax(10.0*2.220446049250313e-16/rtol, fmin(0.03, sqrt(rtol)));   // bdf.py:217
     NoStore nost;
-    double y[NV], f[NV], d[NV], iscale[NV], psi[NV];      // iscale = 1/(atol + rtol|y|): norms multiply, never divide
+    double y[NV], f[NV], d[NV], iscale[NO], psi[NV];      // iscale = 1/(atol + rtol|y|): norms multiply, never divide
     stt.nsteps = stt.nrej = stt.nfev = stt.nlu = stt.nfail = 0;
 
     // ---- initial step, scipy common.py:68-140 (order 1): f0 = f(y0), f1 = f(y0 + h0 f0); one evaluation site
@@ -692,24 +854,26 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
     {
         double h0 = 0.0, d1 = 0.0;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) { y[v] = y0[v]; iscale[v] = pbr_rcp(atol + fabs(y0[v])*rtol); }
+        for (int v = 0; v < NV; ++v) y[v] = y0[v];
+        pbr_n1x_iscale(y, p, rtol, atol, iscale);
 #pragma unroll 1
         for (int s = 0; s < 2; ++s) {
             pbr_n1_rhs_call(p, y, f); stt.nfev++;
             if (s == 0) {
-                double d0 = 0.0;
+                double d0 = 0.0, yf[NO];
+                pbr_n1x_expand(y, p, yf);
 #pragma unroll
-                for (int v = 0; v < NV; ++v) { d0 += (y[v]*iscale[v])*(y[v]*iscale[v]); d1 += (f[v]*iscale[v])*(f[v]*iscale[v]); }
-                d0 = sqrt(d0/NV); d1 = sqrt(d1/NV);
+                for (int v = 0; v < NO; ++v) d0 += (yf[v]*iscale[v])*(yf[v]*iscale[v]);
+                d0 = sqrt(d0/NO); d1 = sqrt(pbr_n1x_norm2(f, iscale)/NO);
                 h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
                 h0 = fmin(h0, t_bound);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) { D[0*NV + v] = y[v]; D[1*NV + v] = f[v]; y[v] = y[v] + h0*f[v]; }
             } else {
-                double d2 = 0.0;
+                double df[NV];
 #pragma unroll
-                for (int v = 0; v < NV; ++v) { const double df = f[v] - D[1*NV + v]; d2 += (df*iscale[v])*(df*iscale[v]); }
-                d2 = sqrt(d2/NV)/h0;
+                for (int v = 0; v < NV; ++v) df[v] = f[v] - D[1*NV + v];
+                const double d2 = sqrt(pbr_n1x_norm2(df, iscale)/NO)/h0;
                 const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0*1e-3) : sqrt(0.01/fmax(d1, d2));
                 h = fmin(fmin(100.0*h0, h1), t_bound);
             }
@@ -755,14 +919,14 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             double yp = D[v], ps = 0.0;
             for (int r = 1; r <= PBR_MAXORD; ++r) if (r <= order) { const double Dr = D[r*NV + v]; yp += Dr; ps += Dr*pbr_bdf_gamma(r); }
             y[v] = yp; psi[v] = ps*ialpha; d[v] = 0.0;
-            iscale[v] = pbr_rcp(atol + rtol*fabs(yp));
         }
+        pbr_n1x_iscale(y, p, rtol, atol, iscale);
         PBR_MID_BARRIER(2)
         // ---------------- 3. Jacobian + LU of I - cJ at the predictor (also yields f(y_pred)) ----------------
         bool lu_good = true;
         if (active) {
             LuStore st = {LU, c};
-            pbr_n1_eval<true>(y, p, f, st);
+            pbr_n1x_eval<true>(y, p, f, st);
             lu_good = pbr_lu_factor<NV>(LU, piv);
             stt.nlu++; stt.nfev++;
         }
@@ -782,14 +946,12 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             if (running) {
                 n_iter = k + 1;
                 if (k > 0) { pbr_n1_rhs_call(p, y, f); stt.nfev++; }
-                double b[NV], nrm = 0.0;
+                double b[NV];
                 bool fin = true;
 #pragma unroll
                 for (int v = 0; v < NV; ++v) { b[v] = c*f[v] - psi[v] - d[v]; fin = fin && (fabs(b[v]) < 1e300); }
                 pbr_lu_solve<NV>(LU, piv, b);
-#pragma unroll
-                for (int v = 0; v < NV; ++v) nrm += (b[v]*iscale[v])*(b[v]*iscale[v]);
-                const double dy_norm = sqrt(nrm/NV);
+                const double dy_norm = sqrt(pbr_n1x_norm2(b, iscale)/NO);
                 const double rate = (dy_norm_old >= 0.0) ? dy_norm/dy_norm_old : -1.0;
                 const bool diverge = !fin || !(dy_norm == dy_norm) ||
                     (rate >= 0.0 && (rate >= 1.0 || pbr_ipow(rate, PBR_NEWTON_MAXITER - k)/(1.0 - rate)*dy_norm > newton_tol));
@@ -810,14 +972,8 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
         const double safety = 0.9*(2*PBR_NEWTON_MAXITER + 1)/(double)(2*PBR_NEWTON_MAXITER + n_iter);
         double err_norm = 0.0;
         {
-            const double errc = pbr_bdf_errc(order);
-            double en = 0.0;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                iscale[v] = pbr_rcp(atol + rtol*fabs(y[v]));
-                const double ev = errc*d[v]*iscale[v]; en += ev*ev;
-            }
-            err_norm = sqrt(en/NV);
+            pbr_n1x_iscale(y, p, rtol, atol, iscale);
+            err_norm = pbr_bdf_errc(order)*sqrt(pbr_n1x_norm2(d, iscale)/NO);
         }
         const bool accepted = tried && converged && (err_norm <= 1.0);
         if ((tried && !converged) || (active && !lu_good)) { pend = 0.5; stt.nfail++; }   // Newton failed (or singular matrix)
@@ -829,7 +985,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
         if (accepted) {
             n_equal++; stt.nsteps++;
             t = t_new;
-            double em = 0.0, ep = 0.0;
+            double vm[NV], vp[NV];                                        // D[order] and D[order+2] after the update
 #pragma unroll
             for (int v = 0; v < NV; ++v) {                                // bdf.py:416-421
                 const double Dk1 = D[(order + 1)*NV + v];
@@ -837,8 +993,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
                 D[(order + 1)*NV + v] = d[v];
                 double acc = d[v];
                 for (int r = PBR_MAXORD; r >= 0; --r) if (r <= order) { acc += D[r*NV + v]; D[r*NV + v] = acc; }
-                if (order > 1) { const double e1 = pbr_bdf_errc(order - 1)*D[order*NV + v]*iscale[v]; em += e1*e1; }
-                if (order < PBR_MAXORD) { const double e2 = pbr_bdf_errc(order + 1)*(d[v] - Dk1)*iscale[v]; ep += e2*e2; }
+                vm[v] = D[order*NV + v]; vp[v] = d[v] - Dk1;
             }
             // dense output on (t_old, t], BdfDenseOutput bdf.py:462-484
             while (next_out < n_out && ((next_out == n_out - 1) ? 1.0 : next_out*dz_out) <= t) {
@@ -857,9 +1012,11 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             }
             // order / step selection (bdf.py:426-455) only where the change can be applied on the very next trip
             if (n_equal >= order + 1 && (trip % PBR_SEL_PERIOD) == 0) {
-                const double fm = (order > 1) ? pbr_fpow(sqrt(em/NV), -1.0/order) : 0.0;
+                const double em = (order > 1) ? pbr_bdf_errc(order - 1)*sqrt(pbr_n1x_norm2(vm, iscale)/NO) : 0.0;
+                const double ep = (order < PBR_MAXORD) ? pbr_bdf_errc(order + 1)*sqrt(pbr_n1x_norm2(vp, iscale)/NO) : 0.0;
+                const double fm = (order > 1) ? pbr_fpow(em, -1.0/order) : 0.0;
                 const double f0 = pbr_fpow(err_norm, -1.0/(order + 1));      // err_norm == 0 -> inf, as in scipy
-                const double fp = (order < PBR_MAXORD) ? pbr_fpow(sqrt(ep/NV), -1.0/(order + 2)) : 0.0;
+                const double fp = (order < PBR_MAXORD) ? pbr_fpow(ep, -1.0/(order + 2)) : 0.0;
                 double fmaxv = f0; int dord = 0;
                 if (fm > fmaxv) { fmaxv = fm; dord = -1; }
                 if (fp > fmaxv) { fmaxv = fp; dord = +1; }
@@ -1350,12 +1507,14 @@ extern "C" __global__ void __launch_bounds__(128) pbr_k_jac_n1(long N, const dou
 #ifndef PBR_N1_D_LOCAL
 #define PBR_N1_D_LOCAL 0      // 1: BDF history in per-thread local memory instead of shared memory (measured slower)
 #endif
-#define PBR_N1_SMEM_DOUBLES (PBR_NV1*PBR_NV1 + (PBR_N1_D_LOCAL ? 0 : PBR_DROWS*PBR_NV1))
+#define PBR_N1_SMEM_DOUBLES (PBR_NX*PBR_NX + (PBR_N1_D_LOCAL ? 0 : PBR_DROWS*PBR_NX))
 
-struct N1Sink {      // scaled state -> prof_y[k][v][N] (coalesced across the warp's instances)
-    double* prof; double* outlet; long N, i; int n_out; bool live;
-    __device__ __forceinline__ void operator()(int k, const double* y) const {
+struct N1Sink {      // integrated state -> scaled [c, p, theta] -> prof_y[k][v][N] (coalesced across the warp's instances)
+    double* prof; double* outlet; long N, i; int n_out; bool live; const InstPar* par;
+    __device__ __forceinline__ void operator()(int k, const double* x) const {
         if (!live) return;
+        double y[PBR_NV1];
+        pbr_n1x_expand(x, *par, y);
         if (prof) {
 #pragma unroll
             for (int v = 0; v < PBR_NV1; ++v) prof[((long)k*PBR_NV1 + v)*N + i] = y[v];
@@ -1378,19 +1537,22 @@ pbr_k2_solve_n1(long N, const double* __restrict__ par, double rtol, double atol
 #endif
     const long i = live ? i0 : N - 1;                                 // padding lanes shadow the last reactor, write nothing
     InstPar p; pbr_load_par(par, N, i, p);
-    double y0[PBR_NV1];
+    double y0[PBR_NX];                                                // IV, pbHomoReactor.py:2831-2842: c = c0, p = 1, theta = 0
 #pragma unroll
-    for (int k = 0; k < PBR_NC; ++k) y0[k] = p.c0[k];                 // IV, pbHomoReactor.py:2831-2842
-    y0[PBR_NC] = 1.0;
-    if (!PBR_ISO) y0[PBR_NC + (PBR_ISO ? 0 : 1)] = 0.0;
+    for (int k = 0; k < PBR_NX; ++k) y0[k] = 0.0;
+#if !PBR_N1_REDUCED
+#pragma unroll
+    for (int k = 0; k < PBR_NC; ++k) y0[k] = p.c0[k];
+#endif
+    y0[PBR_NX - (PBR_ISO ? 1 : 2)] = 1.0;
     const Strided LU = {pbr_smem + threadIdx.x, PBR_N1_BLOCK};
 #if PBR_N1_D_LOCAL
-    double Dloc[PBR_DROWS*PBR_NV1];
+    double Dloc[PBR_DROWS*PBR_NX];
     const Strided D = {Dloc, 1};
 #else
-    const Strided D = {pbr_smem + (long)PBR_NV1*PBR_NV1*PBR_N1_BLOCK + threadIdx.x, PBR_N1_BLOCK};
+    const Strided D = {pbr_smem + (long)PBR_NX*PBR_NX*PBR_N1_BLOCK + threadIdx.x, PBR_N1_BLOCK};
 #endif
-    N1Sink sink = {prof_y, outlet_y, N, i, n_out, live};
+    N1Sink sink = {prof_y, outlet_y, N, i, n_out, live, &p};
     N1Stats st;
     const int rc = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, D, LU, sink, st, live);
     if (!live) return;

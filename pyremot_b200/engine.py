@@ -48,6 +48,7 @@ def lib():
         "pbr_set_species": (i, [vp, i, i, dp, dp, dp, dp, dp, dp, i]),
         "pbr_load_rates": (i, [vp, C.c_char_p, i, C.c_char_p, C.POINTER(C.c_char_p)]),
         "pbr_model_dims": (i, [vp] + [C.POINTER(i)]*7),
+        "pbr_n1_layout": (i, [vp] + [C.POINTER(i)]*3),
         "pbr_model_source": (C.c_char_p, [vp]),
         "pbr_model_cubin": (i, [vp, C.POINTER(vp), C.POINTER(C.c_ulong)]),
         "pbr_kernel_attr": (i, [vp, C.c_char_p, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
@@ -71,7 +72,7 @@ def lib():
     return L
 
 
-EXPORTS = ("pbr_create pbr_destroy pbr_last_error pbr_version pbr_set_species pbr_load_rates pbr_model_dims "
+EXPORTS = ("pbr_create pbr_destroy pbr_last_error pbr_version pbr_set_species pbr_load_rates pbr_model_dims pbr_n1_layout "
            "pbr_model_source pbr_model_cubin pbr_kernel_attr pbr_prolog pbr_rhs_n1 pbr_jac_n1 pbr_rhs_n2 pbr_solve_n1 "
            "pbr_unscale_n1 pbr_solve_n1_host pbr_solve_n2 pbr_unscale_n2 pbr_solve_n2_host pbr_fp64_peak pbr_launch_count").split()
 
@@ -154,6 +155,9 @@ class Model:
         d = [C.c_int() for _ in range(7)]
         self._check(L.pbr_model_dims(self._ctx, *[C.byref(x) for x in d]))
         _, self.n_rxn, self.n_par, self.nv1, self.nv2, self.k_in, self.k_par = [x.value for x in d]
+        d = [C.c_int() for _ in range(3)]
+        self._check(L.pbr_n1_layout(self._ctx, *[C.byref(x) for x in d]))
+        self.n1_vars, self.n1_block, self.n1_smem = [x.value for x in d]      # K2: integrated variables, block, smem
 
     # -- plumbing
     def _check(self, rc):

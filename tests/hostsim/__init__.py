@@ -59,6 +59,15 @@ class HostSim:
         self.L.hs_jac_n1(C.c_long(N), self._p(par), self._p(y), self._p(f), self._p(J))
         return f, J
 
+    def n1x(self, par, x):
+        """N1 in the integrated coordinates: x [nx, N] -> (y_full [nv1, N], f_x [nx, N], J_x [nx, nx, N])."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        nx, N = x.shape
+        assert nx == self.L.hs_nx()
+        y = np.zeros((self.nv1, N)); f = np.zeros_like(x); J = np.zeros((nx, nx, N))
+        self.L.hs_n1x(C.c_long(N), self._p(par), self._p(x), self._p(y), self._p(f), self._p(J))
+        return y, f, J
+
     def rhs_n2(self, par, Y, jac=False):
         Y = np.ascontiguousarray(Y, dtype=np.float64)
         N, nv, zNo = Y.shape

@@ -63,21 +63,41 @@ void hs_rhs_n2(long N, int zNo, const double* par, const double* Y, double* dY, 
     }
 }
 
-struct Sink { double* prof; long N, i; int n_out; void operator()(int k, const double* y) const {
+struct Sink { double* prof; long N, i; int n_out; const InstPar* par; void operator()(int k, const double* x) const {
+    double y[PBR_NV1];
+    pbr_n1x_expand(x, *par, y);
     for (int v = 0; v < PBR_NV1; ++v) prof[((long)k*PBR_NV1 + v)*N + i] = y[v]; } };
+
+// N1 in the integrated (extent) coordinates: x [NX][N] -> y_full [NV1][N], f_x [NX][N], J_x [NX*NX][N]
+struct JSX { double* J; long N, i; void operator()(int r, int c, double v) const { J[(long)(r*PBR_NX + c)*N + i] = v; } };
+int hs_nx() { return PBR_NX; }
+void hs_n1x(long N, const double* par, const double* x, double* yfull, double* f, double* J) {
+    for (long i = 0; i < N; ++i) {
+        InstPar p; pbr_load_par(par, N, i, p);
+        double xx[PBR_NX], ff[PBR_NX], yy[PBR_NV1];
+        for (int v = 0; v < PBR_NX; ++v) xx[v] = x[v*N + i];
+        pbr_n1x_expand(xx, p, yy);
+        for (int v = 0; v < PBR_NV1; ++v) yfull[v*N + i] = yy[v];
+        JSX st = {J, N, i};
+        pbr_n1x_eval<true>(xx, p, ff, st);
+        for (int v = 0; v < PBR_NX; ++v) f[v*N + i] = ff[v];
+    }
+}
 
 // prof: [n_out][NV1][N] scaled; stats [5][N]
 void hs_solve_n1(long N, const double* par, double rtol, double atol, int n_out, int max_steps, double* prof, int* status, int* stats) {
     std::vector<double> work(PBR_N1_WORK_HOST);
     for (long i = 0; i < N; ++i) {
         InstPar p; pbr_load_par(par, N, i, p);
-        double y0[PBR_NV1];
+        double y0[PBR_NX];
+        for (int k = 0; k < PBR_NX; ++k) y0[k] = 0.0;
+#if !PBR_N1_REDUCED
         for (int k = 0; k < PBR_NC; ++k) y0[k] = p.c0[k];
-        y0[PBR_NC] = 1.0;
-        if (!PBR_ISO) y0[PBR_NV1 - 1] = 0.0;
+#endif
+        y0[PBR_NX - (PBR_ISO ? 1 : 2)] = 1.0;
         Strided Dw = {work.data(), 1};
         Strided LUw = {work.data() + PBR_DROWS*PBR_NV1, 1};
-        Sink sk = {prof, N, i, n_out};
+        Sink sk = {prof, N, i, n_out, &p};
         N1Stats st;
         status[i] = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, Dw, LUw, sk, st);
         stats[0*N + i] = st.nsteps; stats[1*N + i] = st.nrej; stats[2*N + i] = st.nfev; stats[3*N + i] = st.nlu; stats[4*N + i] = st.nfail;
