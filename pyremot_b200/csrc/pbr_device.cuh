@@ -741,6 +741,14 @@ PBR_TABLE double PBR_ERRC[7] = {1.0, -0.1850*PBR_G1 + 1.0/2.0, (-1.0/9.0)*PBR_G2
 PBR_DEV double pbr_bdf_gamma(int k) { return PBR_GAMMA[k]; }
 PBR_DEV double pbr_bdf_alpha(int k) { return PBR_ALPHA[k]; }
 PBR_DEV double pbr_bdf_errc(int k) { return PBR_ERRC[k]; }
+PBR_TABLE double PBR_IALPHA[7] = {0.0, 1.0/((1.0 + 0.1850)*PBR_G1), 1.0/((1.0 + 1.0/9.0)*PBR_G2), 1.0/((1.0 + 0.0823)*PBR_G3),
+                                  1.0/((1.0 + 0.0415)*PBR_G4), 1.0/PBR_G5, 0.0};
+PBR_DEV double pbr_bdf_ialpha(int k) { return PBR_IALPHA[k]; }
+// 0.9*(2*NEWTON_MAXITER + 1)/(2*NEWTON_MAXITER + n_iter) for NEWTON_MAXITER = 4, bdf.py:391
+PBR_TABLE double PBR_SAFETY[5] = {0.9*9.0/8.0, 0.9*9.0/9.0, 0.9*9.0/10.0, 0.9*9.0/11.0, 0.9*9.0/12.0};
+PBR_DEV double pbr_bdf_safety(int n_iter) { return PBR_SAFETY[n_iter]; }
+PBR_TABLE double PBR_INVR[8] = {0.0, 1.0, 0.5, 1.0/3.0, 0.25, 0.2, 1.0/6.0, 1.0/7.0};
+PBR_DEV double pbr_bdf_inv(int r) { return PBR_INVR[r]; }
 
 // D[:order+1] <- (R U)^T D[:order+1]  (bdf.py:18-33).  U is the signed Pascal matrix U[l][j] = (-1)^l C(j,l);
 // R[i][l] = prod_{m=1..i} (m-1-factor*l)/m, R[0][l] = 1, R[i>0][0] = 0.   D row r, state v at D[r*NV+v].
@@ -830,6 +838,9 @@ struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
 #ifndef PBR_KAPPA_PERIOD
 #define PBR_KAPPA_PERIOD 16
 #endif
+#ifndef PBR_RESCALE_AFTER_NEWTON
+#define PBR_RESCALE_AFTER_NEWTON 0
+#endif
 // `live` = false marks a padding lane (block tail): it runs the loop for the barrier's sake but does nothing.
 #ifndef PBR_TRIP_CONTINUE
 #define PBR_TRIP_CONTINUE(active, trip) (active)
@@ -902,7 +913,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             double hn = h*pend;
             const bool clip = (t + hn > t_bound);                     // bdf.py:351-355
             if (clip) hn = t_bound - t;
-            const double fac = hn/h;
+            const double fac = clip ? hn*pbr_rcp(h) : pend;
             if (active && fac != 1.0) {
                 pbr_change_D<NV>(D, order, fac); n_equal = 0; h = hn; pend = 1.0;
             }
@@ -912,7 +923,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
         if (active && h < pbr_ulp10(t)) { status = PBR_ERR_STEP_TOO_SMALL; active = false; }
         if (active && trip > max_steps) { status = PBR_ERR_MAX_STEPS; active = false; }
         // ---------------- 2. predictor + psi, bdf.py:360-363 ----------------
-        const double ialpha = pbr_rcp(pbr_bdf_alpha(order));
+        const double ialpha = pbr_bdf_ialpha(order);
         const double c = h*ialpha;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
@@ -951,34 +962,37 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
 #pragma unroll
                 for (int v = 0; v < NV; ++v) { b[v] = c*f[v] - psi[v] - d[v]; fin = fin && (fabs(b[v]) < 1e300); }
                 pbr_lu_solve<NV>(LU, piv, b);
-                const double dy_norm = sqrt(pbr_n1x_norm2(b, iscale)/NO);
-                const double rate = (dy_norm_old >= 0.0) ? dy_norm/dy_norm_old : -1.0;
+                const double dy_norm = sqrt(pbr_n1x_norm2(b, iscale)*(1.0/NO));
+                const double rate = (dy_norm_old >= 0.0) ? dy_norm*pbr_rcp(fmax(dy_norm_old, 1e-300)) : -1.0;
+                const double tol1 = newton_tol*(1.0 - rate);      // x/(1 - rate) > tol  <=>  x > tol*(1 - rate) for rate < 1
                 const bool diverge = !fin || !(dy_norm == dy_norm) ||
-                    (rate >= 0.0 && (rate >= 1.0 || pbr_ipow(rate, PBR_NEWTON_MAXITER - k)/(1.0 - rate)*dy_norm > newton_tol));
+                    (rate >= 0.0 && (rate >= 1.0 || pbr_ipow(rate, PBR_NEWTON_MAXITER - k)*dy_norm > tol1));
                 if (diverge) running = false;
                 else {
 #pragma unroll
                     for (int v = 0; v < NV; ++v) { y[v] += b[v]; d[v] += b[v]; }
-                    if (k == 1) kappa = rate/fmax(dy_norm_old, 1e-300);
+                    if (k == 1) kappa = rate*pbr_rcp(fmax(dy_norm_old, 1e-300));
                     const bool quad_ok = PBR_NEWTON_SKIP && k == 0 && (trip % PBR_KAPPA_PERIOD) != 0 &&
                                          kappa*dy_norm*dy_norm < PBR_NEWTON_SKIP_TOL;
-                    if (dy_norm == 0.0 || quad_ok || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; running = false; }
+                    if (dy_norm == 0.0 || quad_ok || (rate >= 0.0 && rate*dy_norm < tol1)) { converged = true; running = false; }
                     dy_norm_old = dy_norm;
                 }
             }
         }
         PBR_MID_BARRIER(4)
         // ---------------- 5. error test, bdf.py:381-404 ----------------
-        const double safety = 0.9*(2*PBR_NEWTON_MAXITER + 1)/(double)(2*PBR_NEWTON_MAXITER + n_iter);
+        const double safety = pbr_bdf_safety(n_iter);             // 0.9*(2*MAXITER + 1)/(2*MAXITER + n_iter), bdf.py:391
         double err_norm = 0.0;
         {
-            pbr_n1x_iscale(y, p, rtol, atol, iscale);
-            err_norm = pbr_bdf_errc(order)*sqrt(pbr_n1x_norm2(d, iscale)/NO);
+#if PBR_RESCALE_AFTER_NEWTON
+            pbr_n1x_iscale(y, p, rtol, atol, iscale);          // scipy: scale from y_new (bdf.py:390); differs from the
+#endif                                                         // predictor's scale by rtol*|d|/|y|, far below the heuristic's resolution
+            err_norm = pbr_bdf_errc(order)*sqrt(pbr_n1x_norm2(d, iscale)*(1.0/NO));
         }
         const bool accepted = tried && converged && (err_norm <= 1.0);
         if ((tried && !converged) || (active && !lu_good)) { pend = 0.5; stt.nfail++; }   // Newton failed (or singular matrix)
         if (tried && converged && !accepted) {                                    // also catches NaN
-            pend = (err_norm == err_norm) ? fmax(PBR_MIN_FACTOR, safety*pbr_fpow(err_norm, -1.0/(order + 1))) : 0.5;
+            pend = (err_norm == err_norm) ? fmax(PBR_MIN_FACTOR, safety*pbr_fpow(err_norm, -pbr_bdf_inv(order + 1))) : 0.5;
             stt.nrej++;
         }
         // ---------------- 6. accepted: history update, dense output, order / step selection ----------------
@@ -995,15 +1009,16 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
                 for (int r = PBR_MAXORD; r >= 0; --r) if (r <= order) { acc += D[r*NV + v]; D[r*NV + v] = acc; }
                 vm[v] = D[order*NV + v]; vp[v] = d[v] - Dk1;
             }
-            // dense output on (t_old, t], BdfDenseOutput bdf.py:462-484
+            // dense output on (t_old, t], BdfDenseOutput bdf.py:462-484 (division-free: the loop is speculated into every trip)
             while (next_out < n_out && ((next_out == n_out - 1) ? 1.0 : next_out*dz_out) <= t) {
                 const double te = (next_out == n_out - 1) ? 1.0 : next_out*dz_out;
+                const double ih = pbr_rcp(h);
                 double yo[NV];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) yo[v] = D[v];
                 double pr = 1.0;
                 for (int r = 1; r <= PBR_MAXORD; ++r) if (r <= order) {
-                    pr *= (te - (t - h*(r - 1)))/(h*r);
+                    pr *= ((te - t)*ih + (double)(r - 1))*pbr_bdf_inv(r);           // (te - (t - h (r-1)))/(h r)
 #pragma unroll
                     for (int v = 0; v < NV; ++v) yo[v] += D[r*NV + v]*pr;
                 }
@@ -1012,11 +1027,11 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             }
             // order / step selection (bdf.py:426-455) only where the change can be applied on the very next trip
             if (n_equal >= order + 1 && (trip % PBR_SEL_PERIOD) == 0) {
-                const double em = (order > 1) ? pbr_bdf_errc(order - 1)*sqrt(pbr_n1x_norm2(vm, iscale)/NO) : 0.0;
-                const double ep = (order < PBR_MAXORD) ? pbr_bdf_errc(order + 1)*sqrt(pbr_n1x_norm2(vp, iscale)/NO) : 0.0;
-                const double fm = (order > 1) ? pbr_fpow(em, -1.0/order) : 0.0;
-                const double f0 = pbr_fpow(err_norm, -1.0/(order + 1));      // err_norm == 0 -> inf, as in scipy
-                const double fp = (order < PBR_MAXORD) ? pbr_fpow(ep, -1.0/(order + 2)) : 0.0;
+                const double em = (order > 1) ? pbr_bdf_errc(order - 1)*sqrt(pbr_n1x_norm2(vm, iscale)*(1.0/NO)) : 0.0;
+                const double ep = (order < PBR_MAXORD) ? pbr_bdf_errc(order + 1)*sqrt(pbr_n1x_norm2(vp, iscale)*(1.0/NO)) : 0.0;
+                const double fm = (order > 1) ? pbr_fpow(em, -pbr_bdf_inv(order)) : 0.0;
+                const double f0 = pbr_fpow(err_norm, -pbr_bdf_inv(order + 1));      // err_norm == 0 -> inf, as in scipy
+                const double fp = (order < PBR_MAXORD) ? pbr_fpow(ep, -pbr_bdf_inv(order + 2)) : 0.0;
                 double fmaxv = f0; int dord = 0;
                 if (fm > fmaxv) { fmaxv = fm; dord = -1; }
                 if (fp > fmaxv) { fmaxv = fp; dord = +1; }
@@ -1380,7 +1395,7 @@ PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, 
             }
         }
         // ---- 5. error test
-        const double safety = 0.9*(2*PBR_NEWTON_MAXITER + 1)/(double)(2*PBR_NEWTON_MAXITER + n_iter);
+        const double safety = pbr_bdf_safety(n_iter);             // 0.9*(2*MAXITER + 1)/(2*MAXITER + n_iter), bdf.py:391
         double err_norm = 0.0;
         if (converged) {
             const double errc = pbr_bdf_errc(order);
@@ -1530,7 +1545,8 @@ extern "C" __global__ void __launch_bounds__(PBR_N1_BLOCK)
 pbr_k2_solve_n1(long N, const double* __restrict__ par, double rtol, double atol, int n_out, int max_steps,
                 double* __restrict__ prof_y, double* __restrict__ outlet_y, int* __restrict__ status, int* __restrict__ stats) {
     extern __shared__ double pbr_smem[];
-    const long i0 = (long)blockIdx.x*PBR_N1_BLOCK + threadIdx.x;
+    // launched with blockDim.x <= PBR_N1_BLOCK (the host balances the waves); PBR_N1_BLOCK is the shared-memory stride
+    const long i0 = (long)blockIdx.x*blockDim.x + threadIdx.x;
     const bool live = i0 < N;
 #if PBR_N1_BLOCK <= 32
     if (!live) return;
@@ -1988,7 +2004,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                     }
                 }
                 // ---- 5. error test
-                const double safety = 0.9*(2*PBR_NEWTON_MAXITER + 1)/(double)(2*PBR_NEWTON_MAXITER + n_iter);
+                const double safety = pbr_bdf_safety(n_iter);             // 0.9*(2*MAXITER + 1)/(2*MAXITER + n_iter), bdf.py:391
                 double err_norm = 0.0;
                 if (converged) {
                     const double errc = pbr_bdf_errc(order);

@@ -8,7 +8,10 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from pyremot_b200 import cases  # noqa: E402
+from pyremot_b200 import cases, engine  # noqa: E402
+
+if os.environ.get("PBR_AB_LIB"):           # A/B against another build of libpbr.so inside the same gpurun call
+    engine.LIB_PATH = os.path.abspath(os.environ["PBR_AB_LIB"])
 from pyremot_b200.api import get_model  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
@@ -30,6 +33,6 @@ for k in range(reps + 2):
     if k >= 2:
         ts.append(e0.elapsed_time(e1))
 st = r["stats"].cpu().numpy()
-tag = " ".join(f"{k}={os.environ[k]}" for k in ("PBR_N1_REDUCED", "PBR_N1_BLOCK", "PBR_EXTRA_DEFINES") if k in os.environ)
+tag = " ".join(f"{k}={os.environ[k]}" for k in ("PBR_AB_LIB", "PBR_N1_REDUCED", "PBR_N1_BLOCK", "PBR_N1_NO_BALANCE", "PBR_EXTRA_DEFINES") if k in os.environ)
 print(f"K2 N={N} [{tag}] ms min/med {min(ts):.3f}/{sorted(ts)[len(ts)//2]:.3f}  solves/s {N/min(ts)*1e3:.4g}  fails {int((r['status'] != 0).sum())} "
       f"steps/nfev/nlu {st[0].mean():.1f}/{st[2].mean():.1f}/{st[3].mean():.1f}  attr {m.kernel_attr('pbr_k2_solve_n1')}")

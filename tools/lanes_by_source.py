@@ -84,3 +84,7 @@ print("  top source lines by stall samples:")
 for ln, v in sorted(byline.items(), key=lambda kv: -kv[1][2])[:28]:
     if ln:
         print(f"  {100*v[2]/tots:6.2f}% samples {100*v[0]/tot:6.2f}% instr {v[1]/max(v[0],1):5.1f} lanes  L{ln}: {src[ln-1].strip()[:110]}")
+print("  top source lines by executed warp-instructions:")
+for ln, v in sorted(byline.items(), key=lambda kv: -kv[1][0])[:45]:
+    if ln:
+        print(f"  {100*v[0]/tot:6.2f}% instr {100*v[2]/tots:6.2f}% samples {v[1]/max(v[0],1):5.1f} lanes  L{ln}: {src[ln-1].strip()[:110]}")
