@@ -378,7 +378,7 @@ PBR_DEV void pbr_n1x_iscale(const double* x, const InstPar& p, double rtol, doub
     double y[PBR_NV1];
     pbr_n1x_expand(x, p, y);
 #pragma unroll
-    for (int i = 0; i < PBR_NV1; ++i) iscale[i] = pbr_rcp(atol + rtol*fabs(y[i]));
+    for (int i = 0; i < PBR_NV1; ++i) iscale[i] = pbr_rcp_20bit(atol + rtol*fabs(y[i]));
 }
 
 // N1 right-hand side and Jacobian in the integrated coordinates.  Not reduced: identical to pbr_n1_eval.
@@ -418,32 +418,37 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
 #pragma unroll
             for (int b = 0; b < NXr; ++b) Jx[a][b] = 0.0;
         const double cmct = p.Cmax*e.invCt;
-        const double iGH = p.iGH, iDen = pbr_rcp(Den), irho = pbr_rcp(e.rho), iCp = PBR_ISO ? 1.0 : pbr_rcp(e.Cpmix), ipr = pbr_rcp(pr);
+        const double iGH = p.iGH, iDen = pbr_rcp_40bit(Den), irho = pbr_rcp_40bit(e.rho), iCp = PBR_ISO ? 1.0 : pbr_rcp_40bit(e.Cpmix), ipr = pbr_rcp_40bit(pr);
         const double dfp_dw = -zP*(p.E1*p.vs0 + 2.0*p.E2*e.rho*p.vs0*p.vs0*w);
         const double dfp_drho = -zP*(p.E2*vs*vs);
         const double rhoM = e.rho*pbr_rcp(e.M);
         double drk[PBR_NR];
-        // ---- species derivatives, folded into the extent columns: d/dx_j = sum_k nu_jk d/dc_k
+        // ---- extent columns: directional derivatives along u_j = S[j][:] (d c / d x_j), taken directly --
+        //      d r/d c_k = cmct (drx[.][k] - sx) + Cmax drC[.][k]  (pbr_dr_dc)  =>  along u: cmct (sum_k u_k drx[.][k] - sx sigma) + Cmax sum_k u_k drC[.][k]
 #pragma unroll
-        for (int k = 0; k < n; ++k) {
-            pbr_dr_dc(e, p, k, 1.0, drk);
-            double col[PBR_NX];
-            const double dw = w*cmct;
-            const double drho = rhoM*cmct*(1e-3*PBR_MW[k] - e.M);
+        for (int jj = 0; jj < R; ++jj) {
+            double ax[PBR_NR], ac[PBR_NR], sig = 0.0, smw = 0.0, scp = 0.0;      // sig, smw fold to constants
 #pragma unroll
-            for (int j = 0; j < R; ++j) col[j] = drk[j]*invGw - f[j]*cmct;
-            col[R] = dfp_dw*dw + dfp_drho*drho;
+            for (int j = 0; j < R; ++j) { ax[j] = 0.0; ac[j] = 0.0; }
+#define PBR_ACC(j, i, nu) if ((j) == jj) { sig += (nu); smw += (nu)*PBR_MW[i]; if (!PBR_ISO) scp += (nu)*e.cpm[i]; \
+            _Pragma("unroll") for (int q = 0; q < R; ++q) { ax[q] += (nu)*e.drx[q][i]; ac[q] += (nu)*e.drC[q][i]; } }
+            PBR_S_NNZ(PBR_ACC)
+#undef PBR_ACC
+#pragma unroll
+            for (int j = 0; j < R; ++j) drk[j] = cmct*(ax[j] - e.sx[j]*sig) + p.Cmax*ac[j];
+            const double dw = w*cmct*sig;
+            const double drho = rhoM*cmct*(1e-3*smw - e.M*sig);
+#pragma unroll
+            for (int j = 0; j < R; ++j) Jx[j][jj] = drk[j]*invGw - f[j]*(cmct*sig);
+            Jx[R][jj] = dfp_dw*dw + dfp_drho*drho;
             if (!PBR_ISO) {
                 double sH = 0.0;
 #pragma unroll
                 for (int j = 0; j < R; ++j) sH += drk[j]*e.dH[j];
                 const double dNum = -sH*iGH;
-                const double dDen = Den*(drho*irho + cmct*(e.cpm[k] - e.Cpmix)*iCp + cmct);
-                col[R + (PBR_ISO ? 0 : 1)] = (dNum - fth*dDen)*iDen;
+                const double dDen = Den*(drho*irho + cmct*(scp - e.Cpmix*sig)*iCp + cmct*sig);
+                Jx[R + (PBR_ISO ? 0 : 1)][jj] = (dNum - fth*dDen)*iDen;
             }
-#define PBR_ACC(j, i, nu) if ((i) == k) { _Pragma("unroll") for (int a = 0; a < NXr; ++a) Jx[a][j] += (nu)*col[a]; }
-            PBR_S_NNZ(PBR_ACC)
-#undef PBR_ACC
         }
         // ---- pressure column
         {
@@ -465,7 +470,7 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
             const int ct = R + (PBR_ISO ? 0 : 1);
 #pragma unroll
             for (int j = 0; j < R; ++j) drk[j] = p.Tf*e.drT[j];
-            const double drho = -e.rho*p.Tf*pbr_rcp(T);
+            const double drho = -e.rho*p.Tf*pbr_rcp_40bit(T);
 #pragma unroll
             for (int j = 0; j < R; ++j) Jx[j][ct] = drk[j]*invGw;
             Jx[R][ct] = dfp_drho*drho;
@@ -623,7 +628,7 @@ PBR_DEV bool pbr_lu_factor(const Strided& a, unsigned long long& piv) {
             for (int j = 0; j < N; ++j) { const double t = a[k*N + j]; a[k*N + j] = a[pk*N + j]; a[pk*N + j] = t; }
         }
         if (!(amax > 0.0) || !(amax < 1e300)) ok = false;
-        const double inv = pbr_rcp(a[k*N + k]);
+        const double inv = pbr_rcp_40bit(a[k*N + k]);
         a[k*N + k] = inv;
         PBR_LU_PRAGMA
         for (int i = k + 1; i < N; ++i) {

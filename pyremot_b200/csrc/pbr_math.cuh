@@ -81,6 +81,28 @@ PBR_DEV double pbr_rcp(double x) {
 #endif
 }
 
+// Reduced-precision reciprocals for quantities that only steer the iteration, never the solution:
+//   pbr_rcp_20bit: the bare rcp.approx.ftz.f64 (relative error ~1e-6) -- error-norm weights 1/(atol + rtol|y|)
+//   pbr_rcp_40bit: one Newton step (~1e-12) -- LU pivots and Jacobian-only factors of the Newton matrix
+PBR_DEV double pbr_rcp_20bit(double x) {
+#if defined(PBR_HOST) || !PBR_FAST_RCP
+    return 1.0/x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+#endif
+}
+PBR_DEV double pbr_rcp_40bit(double x) {
+#if defined(PBR_HOST) || !PBR_FAST_RCP
+    return 1.0/x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(fma(-x, r, 1.0), r, r);
+#endif
+}
+
 // pbr_log / pbr_sqrt: branch-free replacements for libdevice's log() / sqrt() (each of those carries a range check and a
 // branch to an out-of-line slow path).  PBR_FAST_LOG=0 falls back to the library versions.
 //   log:  x = m 2^e with m in [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1), log m = 2s(1 + z/3 + z^2/5 + ... + z^10/21), z = s^2
