@@ -35,6 +35,19 @@
 #endif
 #endif
 #define PBR_NX ((PBR_N1_REDUCED ? PBR_NR : PBR_NC) + (PBR_ISO ? 1 : 2))
+// N2 (block-per-reactor kernels K4b/K4c): the same change of variables holds per node because the velocity is constant in
+// N2 (pbHomoReactor.py:3937, 4066): w_i = c_i - c0_i - sum_j nu_ji x_j obeys the homogeneous upwind advection equation
+// with w = 0 in the feed-filled bed and at the inlet, hence w == 0 and dx_j/dt = F1 (-(x_j - x_j,up)/dz + r_j/G).
+// (The reference clamps the UPSTREAM concentration at 1e-30 inside the difference, :4088-4093; the extent form uses
+// the unclamped value, which differs only for negative concentrations, i.e. below atol.)  Node state: [x_1..x_R, theta].
+#ifndef PBR_N2_REDUCED
+#if PBR_NR < PBR_NC
+#define PBR_N2_REDUCED 1
+#else
+#define PBR_N2_REDUCED 0
+#endif
+#endif
+#define PBR_NX2 ((PBR_N2_REDUCED ? PBR_NR : PBR_NC) + (PBR_ISO ? 0 : 1))
 #define PBR_NPA (PBR_NP > 0 ? PBR_NP : 1)
 
 #define PBR_R 8.314472          // core/constants.py:8
@@ -587,6 +600,121 @@ PBR_DEV double pbr_n2_node(const double* yc, const double* yb, bool first, doubl
         }
     }
     return slope;
+}
+
+// N2 node in extent coordinates (K4b/K4c): x = [x_1..x_R, theta], xb = upstream node.  Same contract as pbr_n2_node.
+PBR_DEV void pbr_n2x_expand(const double* x, const InstPar& p, double* y) {
+#if PBR_N2_REDUCED
+#pragma unroll
+    for (int i = 0; i < PBR_NC; ++i) y[i] = p.c0[i];
+#define PBR_ACC(j, i, nu) y[i] += (nu)*x[j];
+    PBR_S_NNZ(PBR_ACC)
+#undef PBR_ACC
+    if (!PBR_ISO) y[PBR_NV2 - 1] = x[PBR_NX2 - 1];
+#else
+#pragma unroll
+    for (int i = 0; i < PBR_NV2; ++i) y[i] = x[i];
+#endif
+}
+
+// sum_i ((M v)_i * isc[i*stride])^2, M = linear map from an x-increment to [dc, dtheta]
+PBR_DEV double pbr_n2x_norm2(const double* v, const double* isc, int stride) {
+    double full[PBR_NV2];
+#if PBR_N2_REDUCED
+#pragma unroll
+    for (int i = 0; i < PBR_NC; ++i) full[i] = 0.0;
+#define PBR_ACC(j, i, nu) full[i] += (nu)*v[j];
+    PBR_S_NNZ(PBR_ACC)
+#undef PBR_ACC
+    if (!PBR_ISO) full[PBR_NV2 - 1] = v[PBR_NX2 - 1];
+#else
+#pragma unroll
+    for (int i = 0; i < PBR_NV2; ++i) full[i] = v[i];
+#endif
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < PBR_NV2; ++i) { const double e = full[i]*isc[(long)i*stride]; s += e*e; }
+    return s;
+}
+
+template <bool JAC, class Store>
+PBR_DEV double pbr_n2x_node(const double* x, const double* xb, bool first, double Pz, double inv_dz,
+                            const InstPar& p, double* f, Store& st, double* sub) {
+#if !PBR_N2_REDUCED
+    return pbr_n2_node<JAC>(x, xb, first, Pz, inv_dz, p, f, st, sub);
+#else
+    const int n = PBR_NC, R = PBR_NR;
+    double yc[PBR_NV2], c[PBR_NC];
+    pbr_n2x_expand(x, p, yc);
+#pragma unroll
+    for (int i = 0; i < n; ++i) c[i] = fmax(yc[i], PBR_EPS);                    // :3899
+    const double th = PBR_ISO ? 0.0 : x[PBR_NX2 - 1];
+    const double T = th*p.Tf + p.Tf;                                            // :3914
+    PointEval e;
+    pbr_point<JAC>(c, T, Pz, p, e);
+    const double slope = -(p.E1*p.vs0 + p.E2*e.rho*p.vs0*p.vs0);                // :3970-3974
+    const double F1 = p.F1, invG = p.iG;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        f[j] = F1*(-((x[j] - (first ? 0.0 : xb[j]))*inv_dz) + e.r[j]*invG);     // :4095-4098 along the extents
+        if (JAC) sub[j] = first ? 0.0 : F1*inv_dz;
+    }
+    double D2 = 1.0, heat = 0.0;
+    if (!PBR_ISO) {
+        const double rs = e.rho*p.irho0, cps = e.Cpmix*p.iCp0;
+        D2 = rs*cps*p.eps*pbr_rcp(p.vz);                                        // 1/const_T2 :4077
+        const double thb = first ? 0.0 : xb[PBR_NX2 - 1];                       // :4106-4111
+        const double conv = -1.0*rs*(cps*p.eps)*((th - thb)*inv_dz);            // :4116
+        heat = p.iGH*(-e.Hsum) + p.iGH*e.Q;                                     // :4118-4120
+        f[R] = (conv + heat)*pbr_rcp(D2);                                       // :4125
+        if (JAC) sub[R] = first ? 0.0 : p.vz*inv_dz;
+    }
+    if (JAC) {
+        double drk[PBR_NR];
+        const double iGH = p.iGH, iD2 = pbr_rcp_40bit(D2), iM = pbr_rcp_40bit(e.M), iCp = PBR_ISO ? 1.0 : pbr_rcp_40bit(e.Cpmix);
+        const double hD2 = heat*iD2;
+        const double cmct = p.Cmax*e.invCt;
+        double mask[PBR_NC];
+#pragma unroll
+        for (int i = 0; i < n; ++i) mask[i] = (yc[i] > PBR_EPS) ? 1.0 : 0.0;    // d max(c, eps)/dc
+        // extent columns: directional derivatives along u = S[jj][:]*mask (see pbr_n1x_eval)
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+            double ax[PBR_NR], ac[PBR_NR], sig = 0.0, smw = 0.0, scp = 0.0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) { ax[j] = 0.0; ac[j] = 0.0; }
+#define PBR_ACC(j, i, nu) if ((j) == jj) { const double wq = (nu)*mask[i]; sig += wq; smw += wq*PBR_MW[i]; if (!PBR_ISO) scp += wq*e.cpm[i]; \
+            _Pragma("unroll") for (int q = 0; q < R; ++q) { ax[q] += wq*e.drx[q][i]; ac[q] += wq*e.drC[q][i]; } }
+            PBR_S_NNZ(PBR_ACC)
+#undef PBR_ACC
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                drk[j] = cmct*(ax[j] - e.sx[j]*sig) + p.Cmax*ac[j];
+                st(j, jj, F1*(drk[j]*invG - (j == jj ? inv_dz : 0.0)));
+            }
+            if (!PBR_ISO) {
+                double sH = 0.0;
+#pragma unroll
+                for (int j = 0; j < R; ++j) sH += drk[j]*e.dH[j];
+                const double dheat = -sH*iGH;
+                const double dD2 = D2*(cmct*(1e-3*smw - e.M*sig)*iM + cmct*(scp - e.Cpmix*sig)*iCp);
+                st(R, jj, (dheat - hD2*dD2)*iD2);
+            }
+        }
+        if (!PBR_ISO) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) { drk[j] = p.Tf*e.drT[j]; st(j, R, F1*drk[j]*invG); }
+            double sH = 0.0;
+#pragma unroll
+            for (int j = 0; j < R; ++j) sH += drk[j]*e.dH[j] + p.Tf*e.r[j]*e.dHdT[j];
+            const double dQ = (p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
+            const double dheat = (-sH + dQ)*iGH;
+            const double dD2 = D2*(-p.Tf*pbr_rcp_40bit(T) + p.Tf*e.dCpmixT*iCp);
+            st(R, R, -p.vz*inv_dz + (dheat - hD2*dD2)*iD2);
+        }
+    }
+    return slope;
+#endif
 }
 
 // =====================================================================================================
@@ -1762,7 +1890,7 @@ struct BlkCtx {
 
 struct SmStore {         // Jacobian entries of this thread's node -> I - c*J in its shared-memory column
     Strided a; double c;
-    __device__ __forceinline__ void operator()(int i, int k, double v) const { a[i*PBR_NV2 + k] = (i == k ? 1.0 : 0.0) - c*v; }
+    __device__ __forceinline__ void operator()(int i, int k, double v) const { a[i*PBR_NX2 + k] = (i == k ? 1.0 : 0.0) - c*v; }
 };
 
 // f(Y) at this thread's node from the iterate y[] (registers); with JAC also leaves Ainv in shared memory and sub[].
@@ -1774,18 +1902,19 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
     __syncthreads();
     if (act) {
 #pragma unroll
-        for (int v = 0; v < PBR_NV2; ++v) Ysm[v*zNo + z] = y[v];
+        for (int v = 0; v < PBR_NX2; ++v) Ysm[v*zNo + z] = y[v];
     }
     __syncthreads();
-    double yb[PBR_NV2];
+    double yb[PBR_NX2];
 #pragma unroll
-    for (int v = 0; v < PBR_NV2; ++v) yb[v] = (act && z > 0) ? Ysm[v*zNo + z - 1] : 0.0;
+    for (int v = 0; v < PBR_NX2; ++v) yb[v] = (act && z > 0) ? Ysm[v*zNo + z - 1] : 0.0;
     double a = 1.0, b = 0.0;
     if (act) {
-        double Ct = 0.0, M = 0.0;
+        double Ct = 0.0, M = 0.0, yf[PBR_NV2];
+        pbr_n2x_expand(y, p, yf);
 #pragma unroll
-        for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(y[i], PBR_EPS)*p.Cmax; Ct += C; M += C*PBR_MW[i]; }
-        const double th = PBR_ISO ? 0.0 : y[PBR_ISO ? 0 : PBR_NC];
+        for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yf[i], PBR_EPS)*p.Cmax; Ct += C; M += C*PBR_MW[i]; }
+        const double th = PBR_ISO ? 0.0 : yf[PBR_ISO ? 0 : PBR_NC];
         a = 1.0 - dz*p.E2*p.vs0*p.vs0*(M*1e-3)*pbr_rcp(Ct*(PBR_R*(th*p.Tf + p.Tf)));
         b = -dz*p.E1*p.vs0;
     }
@@ -1795,14 +1924,14 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
         if (JAC) {
             const Strided blk = {Asm + z, zNo};
             SmStore st = {blk, c};
-            pbr_n2_node<true>(y, yb, z == 0, Pz, inv_dz, p, f, st, sub);
-            if (!pbr_invert<PBR_NV2>(blk)) bad = 1.0;          // Ainv replaces I - c*J in place
+            pbr_n2x_node<true>(y, yb, z == 0, Pz, inv_dz, p, f, st, sub);
+            if (!pbr_invert<PBR_NX2>(blk)) bad = 1.0;          // Ainv replaces I - c*J in place
         } else {
             NoStore ns;
-            pbr_n2_node<false>(y, yb, z == 0, Pz, inv_dz, p, f, ns, (double*)0);
+            pbr_n2x_node<false>(y, yb, z == 0, Pz, inv_dz, p, f, ns, (double*)0);
         }
 #pragma unroll
-        for (int v = 0; v < PBR_NV2; ++v) if (!(fabs(f[v]) < 1e300)) bad = 1.0;
+        for (int v = 0; v < PBR_NX2; ++v) if (!(fabs(f[v]) < 1e300)) bad = 1.0;
     }
     return cx.sum(bad) == 0.0;
 }
@@ -1820,40 +1949,40 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
     __syncthreads();                                       // gsm (= Ysm) is no longer read as the iterate
     if (act) {
 #pragma unroll
-        for (int i = 0; i < PBR_NV2; ++i) {
+        for (int i = 0; i < PBR_NX2; ++i) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < PBR_NV2; ++k) acc += Asm[(i*PBR_NV2 + k)*zNo + z]*b[k];
+            for (int k = 0; k < PBR_NX2; ++k) acc += Asm[(i*PBR_NX2 + k)*zNo + z]*b[k];
             gsm[i*zNo + z] = acc;
         }
     }
     __syncthreads();
-    const int row = (cx.lane < PBR_NV2) ? cx.lane : 0;     // the mat-vec row this lane contributes
+    const int row = (cx.lane < PBR_NX2) ? cx.lane : 0;     // the mat-vec row this lane contributes
     for (int wv = 0; wv < nwz; ++wv) {
         if (cx.wid == wv) {
-            double xp[PBR_NV2];
+            double xp[PBR_NX2];
 #pragma unroll
-            for (int v = 0; v < PBR_NV2; ++v) xp[v] = (wv == 0) ? 0.0 : cx.red[v];
+            for (int v = 0; v < PBR_NX2; ++v) xp[v] = (wv == 0) ? 0.0 : cx.red[v];
             const int zb = wv*32;
             const int nact = (zNo - zb < 32) ? (zNo - zb) : 32;
             for (int l = 0; l < nact; ++l) {
                 const int zl = zb + l;
-                double arow[PBR_NV2];
+                double arow[PBR_NX2];
 #pragma unroll
-                for (int k = 0; k < PBR_NV2; ++k) arow[k] = Asm[(row*PBR_NV2 + k)*zNo + zl];
+                for (int k = 0; k < PBR_NX2; ++k) arow[k] = Asm[(row*PBR_NX2 + k)*zNo + zl];
                 double acc = gsm[row*zNo + zl];
 #pragma unroll
-                for (int k = 0; k < PBR_NV2; ++k) acc += arow[k]*(__shfl_sync(0xffffffffu, cs[k], l)*xp[k]);
+                for (int k = 0; k < PBR_NX2; ++k) acc += arow[k]*(__shfl_sync(0xffffffffu, cs[k], l)*xp[k]);
 #pragma unroll
-                for (int v = 0; v < PBR_NV2; ++v) xp[v] = __shfl_sync(0xffffffffu, acc, v);
+                for (int v = 0; v < PBR_NX2; ++v) xp[v] = __shfl_sync(0xffffffffu, acc, v);
                 if (cx.lane == l) {
 #pragma unroll
-                    for (int v = 0; v < PBR_NV2; ++v) b[v] = xp[v];
+                    for (int v = 0; v < PBR_NX2; ++v) b[v] = xp[v];
                 }
             }
             if (cx.lane == 0) {
 #pragma unroll
-                for (int v = 0; v < PBR_NV2; ++v) cx.red[v] = xp[v];      // x of this warp's last node
+                for (int v = 0; v < PBR_NX2; ++v) cx.red[v] = xp[v];      // x of this warp's last node
             }
         }
         __syncthreads();
@@ -1868,17 +1997,18 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                                              double rtol, double atol, int max_steps, double* __restrict__ gwork,
                                              double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
     extern __shared__ double pbr_smem[];
-    const int NV = PBR_NV2;
+    const int NV = PBR_NX2;                                // integrated variables per node (extent coordinates when reduced)
+    const int NO = PBR_NV2;                                // variables the error norms are taken over: [c, theta]
     double* Dsm = D_GLOBAL ? gwork + (long)blockIdx.x*PBR_DROWS*NV*zNo : pbr_smem;     // [PBR_DROWS*NV][zNo]
     double* Asm = D_GLOBAL ? pbr_smem : Dsm + (long)PBR_DROWS*NV*zNo;                  // [NV*NV][zNo]
     double* Ysm = Asm + (long)NV*NV*zNo;                   // [NV][zNo]
     double* Psm = Ysm + (long)NV*zNo;                      // psi
-    double* Ism = Psm + (long)NV*zNo;                      // 1/scale
-    BlkCtx cx; cx.red = Ism + (long)NV*zNo; cx.tid = threadIdx.x; cx.lane = threadIdx.x & 31; cx.wid = threadIdx.x >> 5; cx.nw = blockDim.x >> 5;
+    double* Ism = Psm + (long)NV*zNo;                      // 1/scale [NO][zNo]
+    BlkCtx cx; cx.red = Ism + (long)NO*zNo; cx.tid = threadIdx.x; cx.lane = threadIdx.x & 31; cx.wid = threadIdx.x >> 5; cx.nw = blockDim.x >> 5;
     const int z = threadIdx.x;
     const bool act = z < zNo;
     const Strided D = {Dsm + (act ? z : 0), zNo};
-    const double nTot = (double)(NV*zNo);
+    const double nTot = (double)(NO*zNo);
     const double newton_tol = fmax(10.0*2.220446049250313e-16/rtol, fmin(0.03, sqrt(rtol)));
 
     for (long inst = blockIdx.x; inst < N; inst += gridDim.x) {
@@ -1888,43 +2018,52 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
         __syncthreads();
         if (act) {
 #pragma unroll
-            for (int v = 0; v < PBR_NC; ++v) D[0*NV + v] = p.c0[v];                 // IV, :3483-3497
-            if (!PBR_ISO) D[0*NV + (PBR_ISO ? 0 : PBR_NC)] = 0.0;
+            for (int v = 0; v < NV; ++v) D[0*NV + v] = 0.0;                         // IV, :3483-3497: c = c0 (x = 0), theta = 0
+#if !PBR_N2_REDUCED
+#pragma unroll
+            for (int v = 0; v < PBR_NC; ++v) D[0*NV + v] = p.c0[v];
+#endif
         }
         for (int kint = 0; kint < tNo && rc == PBR_OK; ++kint) {
             const double t0 = (kint == 0) ? 0.0 : period*((double)kint/(double)tNo);  // np.linspace(0, opT, tNo+1)
             const double t1 = (kint == tNo - 1) ? period : period*((double)(kint + 1)/(double)tNo);
             const double span = t1 - t0;
-            double y[PBR_NV2], d[PBR_NV2], f[PBR_NV2], sub[PBR_NV2], b[PBR_NV2];
+            double y[PBR_NX2], d[PBR_NX2], f[PBR_NX2], sub[PBR_NX2], b[PBR_NX2];
             // ---- initial step (scipy common.py:68-140), restart at every interval (:3589-3685)
             double h = 0.0;
             {
-                double h0 = 0.0, d1 = 0.0, f0[PBR_NV2];
+                double h0 = 0.0, d1 = 0.0, f0[PBR_NX2];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) { y[v] = act ? D[0*NV + v] : 1.0; sub[v] = 0.0; f[v] = 0.0; f0[v] = 0.0; }
                 bool ok = pbr_k4b_eval<false>(cx, p, zNo, act, y, 0.0, Ysm, Asm, f, sub); nfev++;
                 double a0 = 0.0, a1 = 0.0;
                 if (act) {
+                    double yf[PBR_NV2];
+                    pbr_n2x_expand(y, p, yf);
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        const double sc = pbr_rcp(atol + fabs(y[v])*rtol);
+                    for (int v = 0; v < NO; ++v) {
+                        const double sc = pbr_rcp_20bit(atol + fabs(yf[v])*rtol);
                         Ism[v*zNo + z] = sc;
-                        a0 += (y[v]*sc)*(y[v]*sc); a1 += (f[v]*sc)*(f[v]*sc);
-                        f0[v] = f[v];
+                        a0 += (yf[v]*sc)*(yf[v]*sc);
                     }
+                    a1 = pbr_n2x_norm2(f, Ism + z, zNo);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) f0[v] = f[v];
                 }
                 const double d0 = sqrt(cx.sum(a0)/nTot);
                 d1 = sqrt(cx.sum(a1)/nTot);
                 h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
                 h0 = fmin(h0, span);
-                double y1[PBR_NV2];
+                double y1[PBR_NX2];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) y1[v] = y[v] + h0*f0[v];
                 ok = pbr_k4b_eval<false>(cx, p, zNo, act, y1, 0.0, Ysm, Asm, f, sub) && ok; nfev++;
                 a0 = 0.0;
                 if (act) {
+                    double df[PBR_NX2];
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) { const double df = (f[v] - f0[v])*Ism[v*zNo + z]; a0 += df*df; }
+                    for (int v = 0; v < NV; ++v) df[v] = f[v] - f0[v];
+                    a0 = pbr_n2x_norm2(df, Ism + z, zNo);
                 }
                 const double d2 = sqrt(cx.sum(a0)/nTot)/h0;
                 const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0*1e-3) : sqrt(0.01/fmax(d1, d2));
@@ -1948,7 +2087,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 if (clip) hn = t1 - t;
                 const double t_new = clip ? t1 : t + hn;
                 const double fac = hn/h;
-                if (fac != 1.0) { if (act) pbr_change_D<PBR_NV2>(D, order, fac); n_equal = 0; }
+                if (fac != 1.0) { if (act) pbr_change_D<PBR_NX2>(D, order, fac); n_equal = 0; }
                 h = hn; pend = 1.0;
                 trip++;
                 if (h < pbr_ulp10(t)) { rc = PBR_ERR_STEP_TOO_SMALL; break; }
@@ -1963,14 +2102,17 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                         for (int r = 1; r <= order; ++r) { const double Dr = D[r*NV + v]; yp += Dr; ps += Dr*pbr_bdf_gamma(r); }
                         y[v] = yp; d[v] = 0.0;
                         Psm[v*zNo + z] = ps*ialpha;
-                        Ism[v*zNo + z] = pbr_rcp(atol + rtol*fabs(yp));
                     }
+                    double yf[PBR_NV2];
+                    pbr_n2x_expand(y, p, yf);
+#pragma unroll
+                    for (int v = 0; v < NO; ++v) Ism[v*zNo + z] = pbr_rcp_20bit(atol + rtol*fabs(yf[v]));
                 }
                 // ---- 3./4. Jacobian blocks + inverses at the predictor, Newton (bdf.py:36-68)
                 bool converged = false;
                 bool running = pbr_k4b_eval<true>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub);
                 nlu++; nfev++;
-                double cs[PBR_NV2];
+                double cs[PBR_NX2];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) cs[v] = c*sub[v];
                 double dy_norm_old = -1.0;
@@ -1991,7 +2133,8 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                             double nrm = 0.0;
                             if (act) {
 #pragma unroll
-                                for (int v = 0; v < NV; ++v) { y[v] += b[v]; d[v] += b[v]; const double e = b[v]*Ism[v*zNo + z]; nrm += e*e; }
+                                for (int v = 0; v < NV; ++v) { y[v] += b[v]; d[v] += b[v]; }
+                                nrm = pbr_n2x_norm2(b, Ism + z, zNo);
                             }
                             const double dy_norm = sqrt(cx.sum(nrm)/nTot);
                             const double rate = (dy_norm_old >= 0.0) ? dy_norm/dy_norm_old : -1.0;
@@ -2012,17 +2155,9 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 const double safety = pbr_bdf_safety(n_iter);             // 0.9*(2*MAXITER + 1)/(2*MAXITER + n_iter), bdf.py:391
                 double err_norm = 0.0;
                 if (converged) {
-                    const double errc = pbr_bdf_errc(order);
-                    double en = 0.0;
-                    if (act) {
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            const double sc = pbr_rcp(atol + rtol*fabs(y[v]));
-                            Ism[v*zNo + z] = sc;
-                            const double ev = errc*d[v]*sc; en += ev*ev;
-                        }
-                    }
-                    err_norm = sqrt(cx.sum(en)/nTot);
+                    double en = 0.0;                   // the predictor's scale is reused (see pbr_n1_solve)
+                    if (act) en = pbr_n2x_norm2(d, Ism + z, zNo);
+                    err_norm = pbr_bdf_errc(order)*sqrt(cx.sum(en)/nTot);
                 }
                 const bool accepted = converged && (err_norm <= 1.0);
                 if (!converged) { pend = 0.5; nrejf++; }
@@ -2036,16 +2171,20 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                     t = t_new;
                     double em = 0.0, ep = 0.0;
                     if (act) {
+                        double vm[PBR_NX2], vp[PBR_NX2];
 #pragma unroll
                         for (int v = 0; v < NV; ++v) {
-                            const double dv = d[v], sc = Ism[v*zNo + z];
+                            const double dv = d[v];
                             const double Dk1 = D[(order + 1)*NV + v];
                             if (order < PBR_MAXORD) D[(order + 2)*NV + v] = dv - Dk1;
                             D[(order + 1)*NV + v] = dv;
                             double acc = dv;
                             for (int r = order; r >= 0; --r) { acc += D[r*NV + v]; D[r*NV + v] = acc; }
-                            if (order > 1) { const double e1 = pbr_bdf_errc(order - 1)*D[order*NV + v]*sc; em += e1*e1; }
-                            if (order < PBR_MAXORD) { const double e2 = pbr_bdf_errc(order + 1)*(dv - Dk1)*sc; ep += e2*e2; }
+                            vm[v] = D[order*NV + v]; vp[v] = dv - Dk1;
+                        }
+                        if (n_equal >= order + 1) {
+                            if (order > 1) { const double e1 = pbr_bdf_errc(order - 1); em = e1*e1*pbr_n2x_norm2(vm, Ism + z, zNo); }
+                            if (order < PBR_MAXORD) { const double e2 = pbr_bdf_errc(order + 1); ep = e2*e2*pbr_n2x_norm2(vp, Ism + z, zNo); }
                         }
                     }
                     if (n_equal >= order + 1) {
@@ -2065,8 +2204,12 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
             }
             __syncthreads();
             if (act) {
+                double xs[PBR_NX2], yf[PBR_NV2];
 #pragma unroll
-                for (int v = 0; v < NV; ++v) snaps[(inst*tNo + kint)*(long)NV*zNo + (long)v*zNo + z] = D[0*NV + v];
+                for (int v = 0; v < NV; ++v) xs[v] = D[0*NV + v];
+                pbr_n2x_expand(xs, p, yf);
+#pragma unroll
+                for (int v = 0; v < NO; ++v) snaps[(inst*tNo + kint)*(long)NO*zNo + (long)v*zNo + z] = yf[v];
             }
         }
         if (threadIdx.x == 0) {
@@ -2077,7 +2220,10 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
     }
 }
 
-extern "C" __global__ void __launch_bounds__(256) pbr_k4b_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+#ifndef PBR_K4B_MINBLOCKS
+#define PBR_K4B_MINBLOCKS 2      // caps the kernel at 128 registers/thread: 512 threads per SM (measured 258 -> 191 ms on config 3)
+#endif
+extern "C" __global__ void __launch_bounds__(256, PBR_K4B_MINBLOCKS) pbr_k4b_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                    double rtol, double atol, int max_steps,
                                                                    double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
     pbr_k4b_body<false>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats);

@@ -63,6 +63,24 @@ void hs_rhs_n2(long N, int zNo, const double* par, const double* Y, double* dY, 
     }
 }
 
+// one N2 node in the extent coordinates of K4b/K4c: x, xb [NX2]; outputs y_full, yb_full [NV2], f [NX2], J [NX2*NX2], sub [NX2]
+struct JSX2 { double* J; void operator()(int r, int c, double v) const { J[r*PBR_NX2 + c] = v; } };
+int hs_nx2() { return PBR_NX2; }
+double hs_n2x_node(const double* par, const double* x, const double* xb, int first, double Pz, double inv_dz,
+                   double* yfull, double* ybfull, double* f, double* J, double* sub) {
+    InstPar p; pbr_load_par(par, 1, 0, p);
+    pbr_n2x_expand(x, p, yfull);
+    pbr_n2x_expand(xb, p, ybfull);
+    JSX2 st = {J};
+    return pbr_n2x_node<true>(x, xb, first != 0, Pz, inv_dz, p, f, st, sub);
+}
+double hs_n2_node(const double* par, const double* y, const double* yb, int first, double Pz, double inv_dz,
+                  double* f, double* J, double* sub) {
+    InstPar p; pbr_load_par(par, 1, 0, p);
+    JS2 st = {J};
+    return pbr_n2_node<true>(y, yb, first != 0, Pz, inv_dz, p, f, st, sub);
+}
+
 struct Sink { double* prof; long N, i; int n_out; const InstPar* par; void operator()(int k, const double* x) const {
     double y[PBR_NV1];
     pbr_n1x_expand(x, *par, y);

@@ -22,3 +22,11 @@ for _ in range(2):
 torch.cuda.synchronize()
 st = r["stats"].cpu().numpy()
 print("N2", N, zNo, "failed", int((r["status"] != 0).sum()), "mean steps", st[0].mean(), "nfev", st[2].mean())
+
+if os.environ.get("PBR_SAVE_CUBIN"):      # exact cubin of this run, for tools/sass_profile.py
+    import ctypes as _C
+    from pyremot_b200 import engine as _E
+    _d, _s = _C.c_void_p(), _C.c_ulong()
+    _E.lib().pbr_model_cubin(m._ctx, _C.byref(_d), _C.byref(_s))
+    open(os.environ["PBR_SAVE_CUBIN"], "wb").write(_C.string_at(_d.value, _s.value))
+    open(os.environ["PBR_SAVE_CUBIN"] + ".cu", "w").write(m.source)
