@@ -157,15 +157,24 @@ def algorithmic_flops(model, stats):
     Per-unit figures: every +,-,*,/ and every exp/log/log10/pow/sqrt counts 1.
     rate DAG ops are counted exactly from the compiled expressions; the balance / linear-algebra terms are
     hand counts of the formulas in csrc/pbr_device.cuh."""
-    nv, n, R = model.n1_vars, model.n, model.n_rxn   # nv: integrated variables (extent coordinates: R + 2)
-    ops_r, ops_rj = model.rates.op_counts()
-    rhs = ops_r + (16*n + 14*R + 40)                 # balances: scaling, x_i, M, rho, Ergun, S^T r, Cp, dH, energy
-    jac = ops_rj + (16*n + 14*R + 40) + (n + 2)*(4*R*n//2 + 6*n + 30)    # chain rule per species / p / theta + stores
-    lu = (2*nv**3)//3 + nv*nv
-    solve = 2*nv*nv + 6*nv                           # triangular solves + Newton update / norms
-    step = 30*nv                                     # predictor, psi, error norms, D update (per accepted step)
+    nx, n, R = model.n1_vars, model.n, model.n_rxn   # nx: integrated variables (extent coordinates: R + 2)
+    reduced = nx < model.nv1
+    ops_r, ops_rj = model.rates.op_counts()          # exact: rate DAG, and rate DAG + its sparse partials
+    base = 16*n + 14*R + 40                          # balances: scaling, x_i, M, rho, Ergun, w, Cp, dH, energy
+    rhs = ops_r + base
+    # Jacobian assembly on top of the rate partials (hand counts of pbr_n1x_eval / pbr_n1_eval in csrc/pbr_device.cuh):
+    # sum_i x_i dr/dx_i (2Rn); one column per extent (directional chain rule 8R + 6n, balances 30) or per species
+    # (3R + 3n + 25); the p and theta columns and the T-derivatives of Cp / dH (9R + 9n + 32)
+    cols = R*(8*R + 6*n + 30) if reduced else n*(3*R + 3*n + 25)
+    jac = ops_rj + base + 2*R*n + cols + (9*R + 9*n + 32)
+    lu = (2*nx**3)//3 + nx*nx
+    solve = 2*nx*nx + 6*nx                           # triangular solves + Newton update
+    step = 32*nx + 14*model.nv1                      # predictor + psi, history update, three weighted norms, weights
     nsteps, nrej, nfev, nlu = [float(x) for x in stats.sum(axis=1)]
-    return nfev*(rhs + solve) + nlu*(jac + lu) + (nsteps + nrej)*step, {"rhs": rhs, "jac": jac, "lu": lu, "solve": solve, "step": step}
+    # every step attempt evaluates the Jacobian (which yields f as well: `jac` contains `rhs`); the other nfev - nlu RHS
+    # evaluations are the verification iterations and the initial-step probes; one triangular solve per Newton iteration
+    flops = (nfev - nlu)*rhs + nfev*solve + nlu*(jac + lu) + nlu*step
+    return flops, {"rhs": rhs, "jac": jac, "lu": lu, "solve": solve, "step": step}
 
 
 def run_gpu(a):

@@ -843,6 +843,61 @@ PBR_DEV bool pbr_invert(const Strided& a) {
     return ok;
 }
 
+// The same inverse on a matrix held in REGISTERS (fully unrolled, compile-time indices; row/column exchanges are taken only
+// when a pivot search asks for them).  For the small node blocks of the extent form (N <= 4): no shared-memory round trips.
+template <int N>
+PBR_DEV bool pbr_invert_reg(double* a) {
+    bool ok = true;
+    int perm[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        int pk = k;
+        double amax = fabs(a[k*N + k]);
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const double v = fabs(a[i*N + k]);
+            if (v > amax) { amax = v; pk = i; }
+        }
+        perm[k] = pk;
+        if (pk != k) {
+#pragma unroll
+            for (int i = k + 1; i < N; ++i) {
+                if (pk == i) {
+#pragma unroll
+                    for (int j = 0; j < N; ++j) { const double t = a[k*N + j]; a[k*N + j] = a[i*N + j]; a[i*N + j] = t; }
+                }
+            }
+        }
+        if (!(amax > 0.0) || !(amax < 1e300)) ok = false;
+        const double pinv = pbr_rcp_40bit(a[k*N + k]);
+        a[k*N + k] = 1.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) a[k*N + j] *= pinv;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (i != k) {
+                const double f = a[i*N + k];
+                a[i*N + k] = 0.0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) a[i*N + j] -= f*a[k*N + j];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+        if (perm[k] != k) {
+#pragma unroll
+            for (int q = k + 1; q < N; ++q) {
+                if (perm[k] == q) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) { const double t = a[i*N + k]; a[i*N + k] = a[i*N + q]; a[i*N + q] = t; }
+                }
+            }
+        }
+    }
+    return ok;
+}
+
 struct LuStore {            // receives Jacobian entries, stores the Newton matrix I - c*J
     Strided a; double c;
     PBR_DEV void operator()(int i, int k, double v) const { a[i*PBR_NX + k] = (i == k ? 1.0 : 0.0) - c*v; }
@@ -1888,12 +1943,27 @@ struct BlkCtx {
     }
 };
 
+#ifndef PBR_K4B_FLAG_REDUCTION
+#define PBR_K4B_FLAG_REDUCTION 1
+#endif
+#ifndef PBR_K4B_MARCH_ROWSPLIT
+#define PBR_K4B_MARCH_ROWSPLIT 1      // 1: row-per-lane march; 0: every lane does the whole mat-vec (A/B pending)
+#endif
+#ifndef PBR_K4B_INVERT_REG
+#define PBR_K4B_INVERT_REG 0          // 1: node blocks inverted in registers (NX2 <= 4; A/B pending)
+#endif
+struct RegStore {        // Jacobian entries of this thread's node -> I - c*J in registers (compile-time indices only)
+    double a[PBR_NX2*PBR_NX2]; double c;
+    __device__ __forceinline__ void operator()(int i, int k, double v) { a[i*PBR_NX2 + k] = (i == k ? 1.0 : 0.0) - c*v; }
+};
 struct SmStore {         // Jacobian entries of this thread's node -> I - c*J in its shared-memory column
     Strided a; double c;
     __device__ __forceinline__ void operator()(int i, int k, double v) const { a[i*PBR_NX2 + k] = (i == k ? 1.0 : 0.0) - c*v; }
 };
 
 // f(Y) at this thread's node from the iterate y[] (registers); with JAC also leaves Ainv in shared memory and sub[].
+// PBR_K4B_FLAG_REDUCTION=0: a non-finite f or a singular block poisons f[0] with NaN instead of being reduced over the block;
+// the NaN reaches the next block-wide norm through the march, so no separate reduction (2 barriers) is spent on the flag.
 template <bool JAC>
 __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p, int zNo, bool act, const double* y, double c,
                                              double* Ysm, double* Asm, double* f, double* sub) {
@@ -1923,17 +1993,34 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
     if (act) {
         if (JAC) {
             const Strided blk = {Asm + z, zNo};
+#if PBR_K4B_INVERT_REG
+            RegStore st; st.c = c;
+#pragma unroll
+            for (int q = 0; q < PBR_NX2*PBR_NX2; ++q) st.a[q] = (q % (PBR_NX2 + 1) == 0) ? 1.0 : 0.0;
+            pbr_n2x_node<true>(y, yb, z == 0, Pz, inv_dz, p, f, st, sub);
+            if (!pbr_invert_reg<PBR_NX2>(st.a)) bad = 1.0;
+#pragma unroll
+            for (int q = 0; q < PBR_NX2*PBR_NX2; ++q) blk[q] = st.a[q];      // Ainv into the node's shared-memory column
+#else
             SmStore st = {blk, c};
             pbr_n2x_node<true>(y, yb, z == 0, Pz, inv_dz, p, f, st, sub);
             if (!pbr_invert<PBR_NX2>(blk)) bad = 1.0;          // Ainv replaces I - c*J in place
+#endif
         } else {
             NoStore ns;
             pbr_n2x_node<false>(y, yb, z == 0, Pz, inv_dz, p, f, ns, (double*)0);
         }
 #pragma unroll
         for (int v = 0; v < PBR_NX2; ++v) if (!(fabs(f[v]) < 1e300)) bad = 1.0;
+#if !PBR_K4B_FLAG_REDUCTION
+        if (bad != 0.0) f[0] = __longlong_as_double(0x7ff8000000000000ll);
+#endif
     }
+#if PBR_K4B_FLAG_REDUCTION
     return cx.sum(bad) == 0.0;
+#else
+    return true;
+#endif
 }
 
 // x_z = Ainv_z (b_z + cs_z * x_{z-1}) = g_z + Ainv_z (cs_z * x_{z-1}) for all nodes; b (registers) is overwritten by x.
@@ -1942,6 +2029,89 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
 // computes row j of the 7x7 mat-vec straight out of the node's inverse block in shared memory, and NV2 shuffles gather
 // x_z for the next node.  ~60 issued instructions and ~100 cycles of latency per node, leaving the issue slots to the
 // SM's other block.  Warps hand over through shared memory + barrier.
+// PBR_K4B_MARCH_SCAN: the recurrence x_z = B_z x_{z-1} + g_z (B_z = Ainv_z diag(cs_z)) is an affine map per node, and affine
+// maps compose: (B2, g2) o (B1, g1) = (B2 B1, g2 + B2 g1).  Every warp scans its 32 maps with shuffles (5 levels), the warp
+// totals are chained through shared memory (<= nw small mat-vecs), and every thread applies its prefix map to its warp's
+// incoming x.  All warps work at once instead of one node at a time.
+#ifndef PBR_K4B_MARCH_SCAN
+#define PBR_K4B_MARCH_SCAN 0
+#endif
+#if PBR_K4B_MARCH_SCAN
+__device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool act, const double* Asm, double* gsm,
+                                              const double* cs, double* b) {
+    const int NXm = PBR_NX2;
+    const int z = cx.tid;
+    double B[PBR_NX2*PBR_NX2], g[PBR_NX2];
+#pragma unroll
+    for (int i = 0; i < NXm; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < NXm; ++k) {
+            const double aik = act ? Asm[(i*NXm + k)*zNo + z] : 0.0;
+            acc += aik*b[k];
+            B[i*NXm + k] = act ? aik*cs[k] : (i == k ? 1.0 : 0.0);       // padding lanes carry the identity map
+        }
+        g[i] = act ? acc : 0.0;
+    }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        double Bp[PBR_NX2*PBR_NX2], gp[PBR_NX2];
+#pragma unroll
+        for (int q = 0; q < NXm*NXm; ++q) Bp[q] = __shfl_up_sync(0xffffffffu, B[q], off);
+#pragma unroll
+        for (int q = 0; q < NXm; ++q) gp[q] = __shfl_up_sync(0xffffffffu, g[q], off);
+        if (cx.lane >= off) {
+#pragma unroll
+            for (int i = 0; i < NXm; ++i) {
+                double row[PBR_NX2], gi = g[i];
+#pragma unroll
+                for (int k = 0; k < NXm; ++k) { row[k] = B[i*NXm + k]; gi += row[k]*gp[k]; }
+                g[i] = gi;
+#pragma unroll
+                for (int j = 0; j < NXm; ++j) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NXm; ++k) t += row[k]*Bp[k*NXm + j];
+                    B[i*NXm + j] = t;
+                }
+            }
+        }
+    }
+    double xin[PBR_NX2];
+#pragma unroll
+    for (int v = 0; v < NXm; ++v) xin[v] = 0.0;
+    if (cx.nw > 1) {                                       // chain the warp totals (block-uniform branch)
+        const int NT = NXm*NXm + NXm;
+        __syncthreads();                                   // gsm (= Ysm) is no longer read as the iterate
+        if (cx.lane == 31) {
+#pragma unroll
+            for (int q = 0; q < NXm*NXm; ++q) gsm[cx.wid*NT + q] = B[q];
+#pragma unroll
+            for (int q = 0; q < NXm; ++q) gsm[cx.wid*NT + NXm*NXm + q] = g[q];
+        }
+        __syncthreads();
+        for (int w = 0; w < cx.wid; ++w) {
+            double xn[PBR_NX2];
+#pragma unroll
+            for (int i = 0; i < NXm; ++i) {
+                double t = gsm[w*NT + NXm*NXm + i];
+#pragma unroll
+                for (int k = 0; k < NXm; ++k) t += gsm[w*NT + i*NXm + k]*xin[k];
+                xn[i] = t;
+            }
+#pragma unroll
+            for (int i = 0; i < NXm; ++i) xin[i] = xn[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NXm; ++i) {
+        double t = g[i];
+#pragma unroll
+        for (int k = 0; k < NXm; ++k) t += B[i*NXm + k]*xin[k];
+        if (act) b[i] = t;
+    }
+}
+#else
 __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool act, const double* Asm, double* gsm,
                                               const double* cs, double* b) {
     const int z = cx.tid;
@@ -1957,6 +2127,7 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
         }
     }
     __syncthreads();
+#if PBR_K4B_MARCH_ROWSPLIT
     const int row = (cx.lane < PBR_NX2) ? cx.lane : 0;     // the mat-vec row this lane contributes
     for (int wv = 0; wv < nwz; ++wv) {
         if (cx.wid == wv) {
@@ -1987,7 +2158,47 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
         }
         __syncthreads();
     }
+#else
+    // every lane of the marching warp carries the whole x and does the full NX2 x NX2 mat-vec itself (the inverse block and
+    // g_z are broadcast loads, independent of the chain): NX2 independent FMA chains of length NX2 per node and no shuffle
+    // on the critical path (the row-per-lane version above needs NX2 shuffles per node to gather x_z)
+    for (int wv = 0; wv < nwz; ++wv) {
+        if (cx.wid == wv) {
+            double xp[PBR_NX2];
+#pragma unroll
+            for (int v = 0; v < PBR_NX2; ++v) xp[v] = (wv == 0) ? 0.0 : cx.red[v];
+            const int zb = wv*32;
+            const int nact = (zNo - zb < 32) ? (zNo - zb) : 32;
+#pragma unroll 2
+            for (int l = 0; l < nact; ++l) {
+                const int zl = zb + l;
+                double csx[PBR_NX2], acc[PBR_NX2];
+#pragma unroll
+                for (int k = 0; k < PBR_NX2; ++k) csx[k] = __shfl_sync(0xffffffffu, cs[k], l)*xp[k];
+#pragma unroll
+                for (int i = 0; i < PBR_NX2; ++i) acc[i] = gsm[i*zNo + zl];
+#pragma unroll
+                for (int k = 0; k < PBR_NX2; ++k)
+#pragma unroll
+                    for (int i = 0; i < PBR_NX2; ++i) acc[i] += Asm[(i*PBR_NX2 + k)*zNo + zl]*csx[k];
+#pragma unroll
+                for (int v = 0; v < PBR_NX2; ++v) xp[v] = acc[v];
+                if (cx.lane == l) {
+#pragma unroll
+                    for (int v = 0; v < PBR_NX2; ++v) b[v] = xp[v];
+                }
+            }
+            if (cx.lane == 0) {
+#pragma unroll
+                for (int v = 0; v < PBR_NX2; ++v) cx.red[v] = xp[v];      // x of this warp's last node
+            }
+        }
+        __syncthreads();
+    }
+#endif
 }
+
+#endif  // PBR_K4B_MARCH_SCAN
 
 // The body is shared by two kernels: pbr_k4b_solve_n2 (<= 256 threads, history in shared memory) and pbr_k4c_solve_n2
 // (<= 512 threads = up to 512 nodes, history in a global scratch slab per block that stays L2-resident; launch bounds
@@ -2068,7 +2279,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 const double d2 = sqrt(cx.sum(a0)/nTot)/h0;
                 const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0*1e-3) : sqrt(0.01/fmax(d1, d2));
                 h = fmin(fmin(100.0*h0, h1), span);
-                if (!ok) rc = PBR_ERR_NONFINITE;
+                if (!ok || !(d1 < 1e300) || !(d2 < 1e300)) rc = PBR_ERR_NONFINITE;        // also catches the NaN poison
                 if (act) {
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
@@ -2138,7 +2349,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                             }
                             const double dy_norm = sqrt(cx.sum(nrm)/nTot);
                             const double rate = (dy_norm_old >= 0.0) ? dy_norm/dy_norm_old : -1.0;
-                            const bool diverge = !(dy_norm == dy_norm) ||
+                            const bool diverge = !(dy_norm < 1e300) ||
                                 (rate >= 0.0 && (rate >= 1.0 || pbr_ipow(rate, PBR_NEWTON_MAXITER - k)/(1.0 - rate)*dy_norm > newton_tol));
                             if (diverge) running = false;
                             else {

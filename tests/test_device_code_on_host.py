@@ -103,3 +103,64 @@ def test_lu_and_history_rescale_primitives(readme):
             change_D(D1, order, factor)
             hs.L.hs_change_D(D2.ctypes.data_as(C.c_void_p), C.c_int(order), C.c_double(factor))
             assert np.max(np.abs(D1 - D2)) < 1e-12*np.max(np.abs(D1))
+
+
+def _extent_map(m, nv, nx):
+    """M = d[c, (p), theta]/dx for the extent coordinates x = [x_1..x_R, (p), theta]."""
+    R, n = m.n_rxn, m.n
+    M = np.zeros((nv, nx))
+    M[:n, :R] = np.asarray(m.S).reshape(R, n).T
+    for k in range(nv - n):
+        M[n + k, R + k] = 1.0
+    return M
+
+
+def test_n1_extent_coordinates_match_full_system(readme):
+    """K2 integrates x = [extents, p, theta] (c = c0 + S^T x): its RHS / Jacobian must be the full system's, f = M f_x and
+    M J_x = J M, and the integration must give the same profiles with the same step counts as the golden sweep test."""
+    mi, m, hs = readme
+    nx = hs.L.hs_nx()
+    assert nx == m.n_rxn + 2 < hs.nv1                      # reduced: 5 instead of 8 variables
+    rows = cases.ensemble_rows(16)
+    par = hs.prolog(m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}))
+    N, R = par.shape[1], m.n_rxn
+    rng = np.random.default_rng(0)
+    x = np.zeros((nx, N))
+    x[:R] = rng.uniform(0, 0.02, (R, N)); x[R] = rng.uniform(0.8, 1, N); x[R + 1] = rng.uniform(0, 0.1, N)
+    y, fx, Jx = hs.n1x(par, x)
+    f, J = hs.jac_n1(par, y)
+    M = _extent_map(m, hs.nv1, nx)
+    assert relerr(M @ fx, f, floor=1e-300) < 1e-12
+    for i in range(N):
+        assert np.max(np.abs(M @ Jx[:, :, i] - J[:, :, i] @ M)) < 1e-12*np.max(np.abs(J[:, :, i]))
+
+
+@pytest.mark.parametrize("mk", [lambda: cases.readme_case("N2"), cases.ch4_n2_case, lambda: cases.readme_case("N2", "iso-thermal")])
+def test_n2_extent_node_matches_full_node(mk):
+    """The per-node function of K4b/K4c in extent coordinates against the full-coordinate node (pbr_n2_node)."""
+    import ctypes as C
+    mi = mk()
+    m = engine.Model(mi, device=None)
+    hs = HostSim(m)
+    L = hs.L
+    nx, nv, R = L.hs_nx2(), hs.nv2, m.n_rxn
+    par = np.ascontiguousarray(hs.prolog(m.instance_table(mi, N=1))[:, 0])
+    M = _extent_map(m, nv, nx)
+    L.hs_n2x_node.restype = C.c_double
+    L.hs_n2_node.restype = C.c_double
+    P = HostSim._p
+    rng = np.random.default_rng(1)
+    for first in (0, 1):
+        for _ in range(10):
+            x, xb = np.zeros(nx), np.zeros(nx)
+            x[:R] = rng.uniform(-2e-6, 2e-6, R); xb[:R] = rng.uniform(-2e-6, 2e-6, R)     # concentrations stay positive
+            if nx > R:
+                x[R], xb[R] = rng.uniform(0, 0.2, 2)
+            yf, ybf, f, J, sub = np.zeros(nv), np.zeros(nv), np.zeros(nx), np.zeros((nx, nx)), np.zeros(nx)
+            s1 = L.hs_n2x_node(P(par), P(x), P(xb), first, C.c_double(4.9e6), C.c_double(19.0), P(yf), P(ybf), P(f), P(J), P(sub))
+            f2, J2, sub2 = np.zeros(nv), np.zeros((nv, nv)), np.zeros(nv)
+            s2 = L.hs_n2_node(P(par), P(yf), P(ybf), first, C.c_double(4.9e6), C.c_double(19.0), P(f2), P(J2), P(sub2))
+            assert s1 == s2
+            assert relerr(M @ f, f2, floor=1e-300) < 1e-11
+            assert np.max(np.abs(M @ J - J2 @ M)) < 1e-12*np.max(np.abs(J2))
+            assert np.max(np.abs(M @ np.diag(sub) - np.diag(sub2) @ M)) < 1e-12*max(1.0, np.max(np.abs(sub2)))
