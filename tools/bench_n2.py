@@ -30,6 +30,9 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)/reps
 st = r["stats"].cpu().numpy()
+if os.environ.get("PBR_BENCH_SAVE"):      # first 64 reactors' snapshots, for A/B comparisons between kernel variants
+    import numpy as np
+    np.save(os.environ["PBR_BENCH_SAVE"], r["snaps_y"][:64].cpu().numpy())
 print(json.dumps({"kernel": "pbr_k4_solve_n2", "N": N, "zNo": zNo, "tNo": tNo, "period": period, "rtol": rtol, "ms": ms,
                   "solves_per_s": N/(ms*1e-3), "failed": int((r["status"] != 0).sum()), "mean_steps": float(st[0].mean()),
                   "mean_nfev": float(st[2].mean()), "mean_nlu": float(st[3].mean()),
