@@ -2033,12 +2033,17 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
 // maps compose: (B2, g2) o (B1, g1) = (B2 B1, g2 + B2 g1).  Every warp scans its 32 maps with shuffles (5 levels), the warp
 // totals are chained through shared memory (<= nw small mat-vecs), and every thread applies its prefix map to its warp's
 // incoming x.  All warps work at once instead of one node at a time.
+// Measured (config-3 / config-4 grids, one B200): zNo = 100 (4 warps) serial 190 ms vs scan 209 ms per 4,096 solves;
+// zNo = 400 (13 warps) serial 412 ms vs scan 186 ms per 1,184 solves.  The launcher picks per grid size:
+// pbr_k4b_solve_n2 (serial march) up to PBR_K4B_SCAN_FROM nodes, pbr_k4bs_solve_n2 / pbr_k4c_solve_n2 (scan) above.
 #ifndef PBR_K4B_MARCH_SCAN
-#define PBR_K4B_MARCH_SCAN 0
+#define PBR_K4B_MARCH_SCAN 0          // 1: force the scan in pbr_k4b_solve_n2 as well (A/B)
 #endif
-#if PBR_K4B_MARCH_SCAN
-__device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool act, const double* Asm, double* gsm,
-                                              const double* cs, double* b) {
+#ifndef PBR_K4C_MARCH_SCAN
+#define PBR_K4C_MARCH_SCAN 1          // 0: serial march in pbr_k4c_solve_n2 (A/B)
+#endif
+__device__ __forceinline__ void pbr_k4b_march_scan(const BlkCtx& cx, int zNo, bool act, const double* Asm, double* gsm,
+                                                   const double* cs, double* b) {
     const int NXm = PBR_NX2;
     const int z = cx.tid;
     double B[PBR_NX2*PBR_NX2], g[PBR_NX2];
@@ -2111,7 +2116,7 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
         if (act) b[i] = t;
     }
 }
-#else
+
 __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool act, const double* Asm, double* gsm,
                                               const double* cs, double* b) {
     const int z = cx.tid;
@@ -2198,12 +2203,11 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
 #endif
 }
 
-#endif  // PBR_K4B_MARCH_SCAN
 
 // The body is shared by two kernels: pbr_k4b_solve_n2 (<= 256 threads, history in shared memory) and pbr_k4c_solve_n2
 // (<= 512 threads = up to 512 nodes, history in a global scratch slab per block that stays L2-resident; launch bounds
 // cap it at 128 registers, so it spills, but it keeps the block-per-reactor structure for BASELINE config 4's zNo = 400).
-template <bool D_GLOBAL>
+template <bool D_GLOBAL, bool SCAN>
 __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                              double rtol, double atol, int max_steps, double* __restrict__ gwork,
                                              double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
@@ -2340,7 +2344,8 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
 #pragma unroll
                                 for (int v = 0; v < NV; ++v) b[v] = c*f[v] - Psm[v*zNo + z] - d[v];
                             }
-                            pbr_k4b_march(cx, zNo, act, Asm, Ysm, cs, b);
+                            if (SCAN) pbr_k4b_march_scan(cx, zNo, act, Asm, Ysm, cs, b);
+                            else pbr_k4b_march(cx, zNo, act, Asm, Ysm, cs, b);
                             double nrm = 0.0;
                             if (act) {
 #pragma unroll
@@ -2437,13 +2442,20 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
 extern "C" __global__ void __launch_bounds__(256, PBR_K4B_MINBLOCKS) pbr_k4b_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                    double rtol, double atol, int max_steps,
                                                                    double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
-    pbr_k4b_body<false>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats);
+    pbr_k4b_body<false, PBR_K4B_MARCH_SCAN != 0>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats);
+}
+
+// the same kernel with the log-depth march: grids of more than PBR_K4B_SCAN_FROM nodes (chosen by the launcher)
+extern "C" __global__ void __launch_bounds__(256, PBR_K4B_MINBLOCKS) pbr_k4bs_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+                                                                    double rtol, double atol, int max_steps,
+                                                                    double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
+    pbr_k4b_body<false, true>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats);
 }
 
 extern "C" __global__ void __launch_bounds__(512) pbr_k4c_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                    double rtol, double atol, int max_steps, double* __restrict__ gwork,
                                                                    double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
-    pbr_k4b_body<true>(N, zNo, tNo, period, par, rtol, atol, max_steps, gwork, snaps, status, stats);
+    pbr_k4b_body<true, PBR_K4C_MARCH_SCAN != 0>(N, zNo, tNo, period, par, rtol, atol, max_steps, gwork, snaps, status, stats);
 }
 
 // ---- K5b epilog (N2): scaled snapshots [N][tNo][NV2][zNo] -> dataYs [N][tNo][NC+1][zNo] = [x_i ; T]

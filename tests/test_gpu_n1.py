@@ -223,7 +223,11 @@ def test_parameter_estimation_fd_jacobian(torch_cuda):
         _, refk, _ = O.solve_n1(O.Ensemble(mi, sw), method="BDF", rtol=1e-12, atol=1e-15)
         Jref = (refk[0, :, -1] - ref0[0, :, -1])/h
         scale = np.max(np.abs(Jref[:6]))
-        assert np.max(np.abs(J[i, :6, k] - Jref[:6])) < 2e-3*scale        # FD noise: 1e-11/1e-4 relative
+        # FD noise: 1e-11/1e-4 relative to the column's scale, plus the integration-noise floor of the two solves
+        # (rtol 1e-11 here, 1e-12 in the oracle) divided by the step: it dominates where the outlet sits at the chemical
+        # equilibrium of a reaction (row 17, K3: d(outlet)/dK3 ~ 6e-12, i.e. outlet differences of 5e-11)
+        floor = 5e-12*np.max(np.abs(base[i, :6]))/h
+        assert np.max(np.abs(J[i, :6, k] - Jref[:6])) < 2e-3*scale + floor
 
 
 def test_failures_are_reported_per_instance_not_hung(torch_cuda):
