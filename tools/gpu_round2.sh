@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( time timeout 1200 python -m pytest tests -m gpu -q ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc $?"; tail -4 gpurun_out/pytest_gpu.log
+for z in 160 224; do for from in 128 512; do
+  echo "zNo=$z scan_from=$from"; PBR_K4B_SCAN_FROM=$from timeout 300 python tools/bench_n2.py 1184 $z 2>&1 | tail -1 | cut -c1-260
+done; done | tee gpurun_out/ab_scan_crossover.txt
+timeout 600 python tools/bench_configs.py > gpurun_out/configs.json 2>gpurun_out/configs.err; cat gpurun_out/configs.json
