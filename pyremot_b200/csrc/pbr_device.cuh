@@ -2207,6 +2207,15 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
 // The body is shared by two kernels: pbr_k4b_solve_n2 (<= 256 threads, history in shared memory) and pbr_k4c_solve_n2
 // (<= 512 threads = up to 512 nodes, history in a global scratch slab per block that stays L2-resident; launch bounds
 // cap it at 128 registers, so it spills, but it keeps the block-per-reactor structure for BASELINE config 4's zNo = 400).
+// PBR_K4B_JAC_REUSE=1 (A/B): keep the node blocks' inverses while c = h/alpha is unchanged (SciPy's policy, bdf.py:353-388:
+// new LU only when c changes, new Jacobian only after a Newton failure).  A whole block works on one reactor, so unlike K2
+// there is no lock-step argument against it; a reused (stale) Jacobian needs the regular two-iteration convergence test.
+#ifndef PBR_K4B_JAC_REUSE
+#define PBR_K4B_JAC_REUSE 0
+#endif
+#ifndef PBR_K4B_JAC_CTOL
+#define PBR_K4B_JAC_CTOL 0.0          // reuse while |c/c_lu - 1| <= CTOL (0: only for an identical c)
+#endif
 template <bool D_GLOBAL, bool SCAN>
 __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                              double rtol, double atol, int max_steps, double* __restrict__ gwork,
@@ -2295,6 +2304,8 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
             int order = 1, n_equal = 0, trip = 0;
             double t = t0, pend = 1.0, kappa = 1e300;
             bool active = (rc == PBR_OK);
+            double c_lu = 0.0;                 // the c the inverses in Asm were built with (0: none yet)
+            bool need_jac = true;
             while (active) {
                 // ---- 1. step size, lazy history rescale
                 double hn = h*pend;
@@ -2325,11 +2336,20 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 }
                 // ---- 3./4. Jacobian blocks + inverses at the predictor, Newton (bdf.py:36-68)
                 bool converged = false;
-                bool running = pbr_k4b_eval<true>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub);
-                nlu++; nfev++;
+#if PBR_K4B_JAC_REUSE
+                const bool fresh = need_jac || !(fabs(c - c_lu) <= PBR_K4B_JAC_CTOL*c_lu);
+#else
+                const bool fresh = true;
+#endif
+                bool running = true;
+                if (fresh) {
+                    running = pbr_k4b_eval<true>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub);
+                    nlu++; nfev++;
+                    c_lu = c; need_jac = !running;
+                }
                 double cs[PBR_NX2];
 #pragma unroll
-                for (int v = 0; v < NV; ++v) cs[v] = c*sub[v];
+                for (int v = 0; v < NV; ++v) cs[v] = c_lu*sub[v];
                 double dy_norm_old = -1.0;
                 int n_iter = 0;
 #pragma unroll 1
@@ -2337,7 +2357,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                     if (running) {
                         n_iter = k + 1;
                         bool fin = true;
-                        if (k > 0) { fin = pbr_k4b_eval<false>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub); nfev++; }
+                        if (k > 0 || !fresh) { fin = pbr_k4b_eval<false>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub); nfev++; }
                         if (!fin) running = false;
                         else {
                             if (act) {
@@ -2358,8 +2378,8 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                                 (rate >= 0.0 && (rate >= 1.0 || pbr_ipow(rate, PBR_NEWTON_MAXITER - k)/(1.0 - rate)*dy_norm > newton_tol));
                             if (diverge) running = false;
                             else {
-                                if (k == 1) kappa = rate/fmax(dy_norm_old, 1e-300);
-                                const bool quad_ok = PBR_NEWTON_SKIP && k == 0 && (trip % PBR_KAPPA_PERIOD) != 0 &&
+                                if (k == 1 && fresh) kappa = rate/fmax(dy_norm_old, 1e-300);
+                                const bool quad_ok = PBR_NEWTON_SKIP && fresh && k == 0 && (trip % PBR_KAPPA_PERIOD) != 0 &&
                                                      kappa*dy_norm*dy_norm < PBR_NEWTON_SKIP_TOL;
                                 if (dy_norm == 0.0 || quad_ok || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; running = false; }
                                 dy_norm_old = dy_norm;
@@ -2376,7 +2396,11 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                     err_norm = pbr_bdf_errc(order)*sqrt(cx.sum(en)/nTot);
                 }
                 const bool accepted = converged && (err_norm <= 1.0);
-                if (!converged) { pend = 0.5; nrejf++; }
+                if (!converged) {
+                    if (fresh) pend = 0.5;             // bdf.py:375-388: with a current Jacobian halve the step,
+                    else need_jac = true;              // otherwise retry the same step with a new one
+                    nrejf++;
+                }
                 else if (!accepted) {
                     pend = (err_norm == err_norm) ? fmax(PBR_MIN_FACTOR, safety*pbr_fpow(err_norm, -1.0/(order + 1))) : 0.5;
                     nrejf++;

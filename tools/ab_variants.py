@@ -11,13 +11,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "default": "",
-    "march_fullrow": "PBR_K4B_MARCH_ROWSPLIT=0",
-    "march_scan": "PBR_K4B_MARCH_SCAN=1",
-    "invert_reg": "PBR_K4B_INVERT_REG=1",
-    "no_flag_reduction": "PBR_K4B_FLAG_REDUCTION=0",
-    "scan+invert_reg": "PBR_K4B_MARCH_SCAN=1;PBR_K4B_INVERT_REG=1",
-    "scan+invert_reg+noflag": "PBR_K4B_MARCH_SCAN=1;PBR_K4B_INVERT_REG=1;PBR_K4B_FLAG_REDUCTION=0",
+    "jac_reuse": "PBR_K4B_JAC_REUSE=1",
+    "jac_reuse_ctol0.2": "PBR_K4B_JAC_REUSE=1;PBR_K4B_JAC_CTOL=0.2",
 }
+# measured and recorded in profiles/r1l_k4*_variants_*.jsonl: PBR_K4B_MARCH_ROWSPLIT=0, PBR_K4B_MARCH_SCAN=1,
+# PBR_K4B_INVERT_REG=1, PBR_K4B_FLAG_REDUCTION=0 and their combinations
 
 
 def env_for(defs):
