@@ -137,3 +137,28 @@ def test_n2_both_kernels_agree_and_large_grid():
     ens.period = 0.05
     _, ref, _ = O.solve_n2(ens, zNo=400, tNo=1, method="BDF", rtol=1e-9, atol=1e-13, sparse=True)
     assert relerr(big["dataYs"][:1], ref) < RTOL_SOLVE
+
+
+def test_n2_scan_march_matches_serial_march_and_oracle():
+    """Grids above 128 nodes use the log-depth scan of the per-node affine maps (pbr_k4bs_solve_n2) instead of the serial
+    node march (pbr_k4b_solve_n2): both solve the same block-bidiagonal Newton systems, so the snapshots must agree to
+    integration tolerance, and with the oracle to 1e-6.  zNo = 160 is ragged (5 warps of nodes)."""
+    import os
+    from pyremot_b200.api import get_model
+    mi = cases.readme_case("N2")
+    m = get_model(mi)
+    rows = cases.ensemble_rows(5)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    tab = m.instance_table(mi, sweep)
+    scan = m.solve_n2_host(tab, 160, 2, 0.1)
+    os.environ["PBR_K4B_SCAN_FROM"] = "512"
+    try:
+        serial = m.solve_n2_host(tab, 160, 2, 0.1)
+    finally:
+        del os.environ["PBR_K4B_SCAN_FROM"]
+    assert (scan["status"] == 0).all() and (serial["status"] == 0).all()
+    assert relerr(scan["dataYs"], serial["dataYs"]) < 1e-7
+    ens = O.Ensemble(mi, {k: v[:1] for k, v in sweep.items()})
+    ens.period = 0.1
+    _, ref, _ = O.solve_n2(ens, zNo=160, tNo=2, method="BDF", rtol=1e-9, atol=1e-13, sparse=True)
+    assert relerr(scan["dataYs"][:1], ref) < RTOL_SOLVE
