@@ -1946,6 +1946,9 @@ struct BlkCtx {
 #ifndef PBR_K4B_FLAG_REDUCTION
 #define PBR_K4B_FLAG_REDUCTION 1
 #endif
+#ifndef PBR_K4B_MARCH_V2
+#define PBR_K4B_MARCH_V2 0            // 1: leaner serial chain (see pbr_k4b_march; A/B pending)
+#endif
 #ifndef PBR_K4B_MARCH_ROWSPLIT
 #define PBR_K4B_MARCH_ROWSPLIT 1      // 1: row-per-lane march; 0: every lane does the whole mat-vec (A/B pending)
 #endif
@@ -2132,7 +2135,56 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
         }
     }
     __syncthreads();
-#if PBR_K4B_MARCH_ROWSPLIT
+#if PBR_K4B_MARCH_V2
+    // Leaner serial chain (A/B): the products Ainv*cs are formed off the chain (in extent coordinates cs = c*sub is the same
+    // for every node but the reactor's first, whose incoming x is zero anyway, so it is not shuffled per node), the dot
+    // product is summed as two independent halves, and x_z goes back to shared memory in place of g_z (one predicated store)
+    // instead of being handed to the owning lane through predicated register moves; every thread picks its x up at the end.
+    const int row = (cx.lane < PBR_NX2) ? cx.lane : 0;
+    for (int wv = 0; wv < nwz; ++wv) {
+        if (cx.wid == wv) {
+            double xp[PBR_NX2];
+#pragma unroll
+            for (int v = 0; v < PBR_NX2; ++v) xp[v] = (wv == 0) ? 0.0 : cx.red[v];
+            const int zb = wv*32;
+            const int nact = (zNo - zb < 32) ? (zNo - zb) : 32;
+#if PBR_N2_REDUCED
+            double csu[PBR_NX2];
+#pragma unroll
+            for (int k = 0; k < PBR_NX2; ++k) csu[k] = __shfl_sync(0xffffffffu, cs[k], nact - 1);
+#endif
+#pragma unroll 2
+            for (int l = 0; l < nact; ++l) {
+                const int zl = zb + l;
+                double brow[PBR_NX2];
+#pragma unroll
+                for (int k = 0; k < PBR_NX2; ++k) {
+#if PBR_N2_REDUCED
+                    brow[k] = Asm[(row*PBR_NX2 + k)*zNo + zl]*csu[k];
+#else
+                    brow[k] = Asm[(row*PBR_NX2 + k)*zNo + zl]*__shfl_sync(0xffffffffu, cs[k], l);
+#endif
+                }
+                double s0 = gsm[row*zNo + zl], s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < PBR_NX2; ++k) { if (k & 1) s1 = fma(brow[k], xp[k], s1); else s0 = fma(brow[k], xp[k], s0); }
+                const double acc = s0 + s1;
+#pragma unroll
+                for (int v = 0; v < PBR_NX2; ++v) xp[v] = __shfl_sync(0xffffffffu, acc, v);
+                if (cx.lane < PBR_NX2) gsm[row*zNo + zl] = acc;
+            }
+            if (cx.lane == 0) {
+#pragma unroll
+                for (int v = 0; v < PBR_NX2; ++v) cx.red[v] = xp[v];      // x of this warp's last node
+            }
+        }
+        __syncthreads();
+    }
+    if (act) {
+#pragma unroll
+        for (int v = 0; v < PBR_NX2; ++v) b[v] = gsm[v*zNo + z];
+    }
+#elif PBR_K4B_MARCH_ROWSPLIT
     const int row = (cx.lane < PBR_NX2) ? cx.lane : 0;     // the mat-vec row this lane contributes
     for (int wv = 0; wv < nwz; ++wv) {
         if (cx.wid == wv) {
