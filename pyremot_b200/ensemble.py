@@ -84,3 +84,56 @@ def solve_n1_sharded(modelInput, sweep, params=(), rtol=None, atol=None, balance
     r = rmtExeBatch(modelInput, local_sweep, params=params, device=dev, rtol=rtol, atol=atol, return_device=True)
     full = gather_rows(r["outlet"].contiguous(), N, world, rank)
     return undeal(perm, full.cpu().numpy()), r["status"].cpu().numpy()
+
+
+def chunk_bounds(N, chunk):
+    """[(a, b), ...] covering [0, N) in pieces of at most ``chunk`` rows."""
+    chunk = max(1, int(chunk))
+    return [(a, min(a + chunk, N)) for a in range(0, N, chunk)]
+
+
+def solve_n2_sharded(modelInput, sweep, zNo=None, tNo=None, chunk=16384, rtol=None, atol=None, device=None, keep=None):
+    """Dynamic-model (N2) ensemble across all ranks of the initialised process group (BASELINE config 4: zNo = 400,
+    1,048,576 reactors = 131,072 per GPU at 8 GPUs).
+
+    Every rank solves its contiguous shard in chunks of ``chunk`` reactors: the full snapshots of a chunk
+    ([chunk, tNo, n+1, zNo] doubles; 1.8 GB at 16,384 x zNo = 400) exist on the GPU only while the chunk is processed.
+    Kept per reactor: the outlet-node rows ``[x_i ; T]`` of every snapshot ([tNo*(n+1)]), gathered with ONE all-gather at
+    the end; full profiles stay with the rank that made them -- ``keep(lo, hi, dataYs_chunk, status_chunk)`` is called
+    with each chunk's device tensors (global row range) so the caller can write them out (``io.save_shard``).
+    Returns (outlet rows [N, tNo, n+1] numpy on every rank, local status [n_local] numpy, mean BDF steps of the shard).
+    """
+    import torch
+    import torch.distributed as dist
+    from .api import DEFAULT_ATOL, DEFAULT_RTOL, get_model, solverSetting
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    s2 = solverSetting["N2"]
+    zNo = int(zNo or s2["zNo"])
+    tNo = int(tNo or s2["tNo"])
+    rtol = DEFAULT_RTOL if rtol is None else rtol
+    atol = DEFAULT_ATOL if atol is None else atol
+    N = len(next(iter(sweep.values())))
+    lo, hi = shard_bounds(N, rank, world)
+    dev = torch.cuda.current_device() if device is None else device
+    model = get_model(modelInput, device=dev)
+    tab = model.instance_table(modelInput, {k: np.asarray(v)[lo:hi] for k, v in sweep.items()})
+    tab = torch.from_numpy(tab).to(model._dev())
+    par = model.prolog(tab)
+    n = model.n
+    period = modelInput["operating-conditions"]["period"]
+    outlet = torch.empty((hi - lo, tNo*(n + 1)), dtype=torch.float64, device=tab.device)
+    status = torch.empty((hi - lo,), dtype=torch.int32, device=tab.device)
+    steps = torch.zeros((), dtype=torch.float64, device=tab.device)
+    for a, b in chunk_bounds(hi - lo, chunk):
+        pc = par[:, a:b].contiguous()
+        r = model.solve_n2(pc, zNo, tNo, period, rtol=rtol, atol=atol)
+        data = model.unscale_n2(pc, r["snaps_y"])                       # [chunk, tNo, n+1, zNo]
+        outlet[a:b] = data[:, :, :, -1].reshape(b - a, -1)
+        status[a:b] = r["status"]
+        steps += r["stats"][0].double().sum()
+        if keep is not None:
+            keep(lo + a, lo + b, data, r["status"])
+        del r, data
+    full = gather_rows(outlet, N, world, rank)
+    return full.cpu().numpy().reshape(N, tNo, n + 1), status.cpu().numpy(), float(steps)/max(1, hi - lo)

@@ -83,3 +83,13 @@ def test_result_shards_roundtrip(tmp_path):
         assert False, "a gap in the row range must be detected"
     except ValueError:
         pass
+
+
+def test_chunk_bounds_tile_the_shard():
+    for N in (0, 1, 5, 16384, 131072):
+        for chunk in (1, 7, 16384):
+            if N > 1000 and chunk < 100:
+                continue
+            b = ensemble.chunk_bounds(N, chunk)
+            assert (not b and N == 0) or (b[0][0] == 0 and b[-1][1] == N)
+            assert all(b[i][1] == b[i+1][0] for i in range(len(b) - 1)) and all(0 < hi - lo <= chunk for lo, hi in b)
