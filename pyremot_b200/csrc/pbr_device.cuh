@@ -1904,6 +1904,12 @@ extern "C" __global__ void __launch_bounds__(128) pbr_k4_solve_n2(long N, int zN
     }
 }
 
+#endif  // !PBR_HOST (kernels K2, K3, K4)
+
+// The block-per-reactor N2 solver also compiles for the host when PBR_HOST_SIMT is defined: tests/hostsim/simt.h supplies
+// threadIdx/blockDim, __syncthreads and the warp shuffles on top of one fiber per thread, so the kernel body below -- marches,
+// scans, reductions and all -- runs unmodified on the CPU-only build container (test infrastructure, never shipped).
+#if !defined(PBR_HOST) || defined(PBR_HOST_SIMT)
 // ---- K4b: fused N2 solver, ONE BLOCK PER REACTOR, ONE THREAD PER AXIAL NODE, all integrator state on chip.
 //      Used when the reactor's working set fits shared memory (119*zNo doubles: zNo <= ~230); larger grids use K4.
 //      Shared memory (element e of node z at base[e*zNo + z], conflict-free): BDF history D[7][NV2], inverse of the
@@ -2534,6 +2540,9 @@ extern "C" __global__ void __launch_bounds__(512) pbr_k4c_solve_n2(long N, int z
     pbr_k4b_body<true, PBR_K4C_MARCH_SCAN != 0>(N, zNo, tNo, period, par, rtol, atol, max_steps, gwork, snaps, status, stats);
 }
 
+#endif  // !PBR_HOST || PBR_HOST_SIMT
+
+#ifndef PBR_HOST
 // ---- K5b epilog (N2): scaled snapshots [N][tNo][NV2][zNo] -> dataYs [N][tNo][NC+1][zNo] = [x_i ; T]
 //      solvers/solResultAnalysis.py:252-301, pbHomoReactor.py:3655-3661.  One thread per (instance, snapshot, node).
 extern "C" __global__ void __launch_bounds__(256) pbr_k5_unscale_n2(long N, int tNo, int zNo, const double* __restrict__ par,

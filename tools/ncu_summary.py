@@ -19,6 +19,8 @@ for w in WANT:
     if w in hdr:
         i = hdr.index(w)
         print(f"{w} [{rows[1][i]}]: " + ", ".join(r[i] for r in rows[2:]))
-stall = [(h, [r[hdr.index(h)] for r in rows[2:]]) for h in hdr if 'issue_stalled' in h and h.endswith('_per_warp_active.pct')]
+stall = [(h, [r[hdr.index(h)] for r in rows[2:]]) for h in hdr
+         if 'issue_stalled' in h and (h.endswith('_per_warp_active.pct') or h.endswith('_per_issue_active.ratio'))]
+print("## stall cycles per issued instruction (smsp__average_warps_issue_stalled_*_per_issue_active.ratio), top 8")
 for h, v in sorted(stall, key=lambda t: -float(t[1][0] or 0))[:8]:
-    print(h.replace('smsp__average_warps_issue_stalled_', '').replace('smsp__warp_issue_stalled_', ''), v)
+    print(h.replace('smsp__average_warps_issue_stalled_', '').replace('smsp__warp_issue_stalled_', '').replace('_per_issue_active.ratio', ''), v)
