@@ -15,6 +15,45 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _BUILD = os.path.join(tempfile.gettempdir(), "pbr_hostsim")
 
 
+def _build(src, driver, extra=()):
+    """g++ build of `driver` around the model program text `src`; cached in the temp directory under a content hash."""
+    text = "".join(open(os.path.join(_HERE, f)).read() for f in (driver,) + tuple(extra))
+    key = hashlib.sha256((src + text).encode()).hexdigest()[:16]
+    os.makedirs(_BUILD, exist_ok=True)
+    so = os.path.join(_BUILD, f"{os.path.splitext(driver)[0]}_{key}.so")
+    if not os.path.exists(so):
+        cu = os.path.join(_BUILD, f"model_{key}.h")
+        with open(cu, "w") as f:
+            f.write(src)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", f"-I{_HERE}",
+                        f'-DPBR_MODEL_FILE="{cu}"', "-DPBR_N1_WORK_HOST=(PBR_DROWS*PBR_NV1+PBR_NV1*PBR_NV1)",
+                        os.path.join(_HERE, driver), "-o", so + ".tmp"], check=True)
+        os.replace(so + ".tmp", so)
+    return C.CDLL(so)
+
+
+class SimtSim:
+    """The block-per-reactor N2 solver kernels run through the fiber-based SIMT emulator (simt.h, simt_driver.cpp)."""
+    KERNELS = {"pbr_k4b_solve_n2": 0, "pbr_k4bs_solve_n2": 1, "pbr_k4c_solve_n2": 2}
+
+    def __init__(self, model):
+        self.L = _build(model.source, "simt_driver.cpp", extra=("simt.h",))
+        self.nv2 = model.nv2
+
+    def solve_n2(self, kernel, par, zNo, tNo, period, rtol=1e-9, atol=1e-13, max_steps=50000, grid=None):
+        par = np.ascontiguousarray(par, dtype=np.float64)
+        N = par.shape[1]
+        snaps = np.zeros((N, tNo, self.nv2, zNo))
+        status = np.zeros(N, dtype=np.int32)
+        stats = np.zeros((4, N), dtype=np.int32)
+        p = HostSim._p
+        rc = self.L.hs_simt_solve_n2(self.KERNELS[kernel], C.c_long(N), C.c_int(zNo), C.c_int(tNo), C.c_double(period), p(par),
+                                     C.c_double(rtol), C.c_double(atol), C.c_int(max_steps), C.c_int(grid or N), p(snaps),
+                                     p(status), p(stats))
+        assert rc == 0, rc
+        return snaps, status, stats
+
+
 class HostSim:
     def __init__(self, model):
         src = model.source

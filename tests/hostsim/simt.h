@@ -80,6 +80,7 @@ static inline SimtDim3 simt_thread_idx() { return SimtDim3{(unsigned)simt::cur, 
 #define __global__
 #define __device__
 #define __forceinline__ inline
+#define __noinline__
 #define __shared__            /* only `extern __shared__ double pbr_smem[]` is used: the driver defines the array */
 #define __launch_bounds__(...)
 

@@ -164,3 +164,56 @@ def test_n2_extent_node_matches_full_node(mk):
             assert relerr(M @ f, f2, floor=1e-300) < 1e-11
             assert np.max(np.abs(M @ J - J2 @ M)) < 1e-12*np.max(np.abs(J2))
             assert np.max(np.abs(M @ np.diag(sub) - np.diag(sub2) @ M)) < 1e-12*max(1.0, np.max(np.abs(sub2)))
+
+
+# ---- the block-per-reactor N2 solver kernels, run whole through the SIMT emulator (tests/hostsim/simt.h)
+def _simt_case(mk, extra_defines=None):
+    import os
+    from hostsim import SimtSim
+    mi = mk()
+    old = os.environ.get("PBR_EXTRA_DEFINES")
+    if extra_defines:
+        os.environ["PBR_EXTRA_DEFINES"] = extra_defines
+    try:
+        m = engine.Model(mi, device=None)
+    finally:
+        if extra_defines:
+            if old is None:
+                del os.environ["PBR_EXTRA_DEFINES"]
+            else:
+                os.environ["PBR_EXTRA_DEFINES"] = old
+    return mi, m, HostSim(m), SimtSim(m)
+
+
+def test_block_kernels_on_the_simt_emulator_vs_converged_reference(golden):
+    """pbr_k4b_solve_n2 (serial march), pbr_k4bs_solve_n2 (scan march) and pbr_k4c_solve_n2 (history in a global slab), executed
+    thread by thread with real barriers and shuffles, against the reference's converged rmtExe N2 snapshots (DME case, zNo = 20)
+    and against the scalar host build of the warp kernel (same step counts)."""
+    g = golden("n2_solve")
+    mi, m, hs, sim = _simt_case(cases.dme_n2_case)
+    ens = O.Ensemble(mi)
+    par = hs.prolog(m.instance_table(mi))
+    ref_snaps, _, ref_stats = hs.solve_n2(par, 20, 5, float(ens.period), 1e-9, 1e-13)
+    for kernel in ("pbr_k4b_solve_n2", "pbr_k4bs_solve_n2", "pbr_k4c_solve_n2"):
+        snaps, status, stats = sim.solve_n2(kernel, par, 20, 5, float(ens.period))
+        assert status[0] == 0
+        data = np.stack([ens.unscale_n2(snaps[:, k]) for k in range(5)], axis=1)[0]
+        assert relerr(data, g["dme_z20_conv_dataYs"]) < 1e-6
+        assert relerr(snaps, ref_snaps, floor=1e-12) < 1e-9 and abs(int(stats[0, 0]) - int(ref_stats[0, 0])) <= 2
+
+
+@pytest.mark.parametrize("defines", [None, "PBR_K4B_MARCH_V2=1"])
+def test_block_kernels_multi_warp_ragged_grid_and_instance_loop(defines):
+    """zNo = 40: two warps, the second one ragged (8 nodes), so the marches hand over between warps, the scan chains warp totals
+    and the block reductions span warps; 2 reactors on a grid of 1 block exercise the kernels' loop over instances.  All
+    kernels must agree with the scalar host build of the warp kernel to integration tolerance."""
+    mi, m, hs, sim = _simt_case(lambda: cases.readme_case("N2"), defines)
+    rows = cases.ensemble_rows(2)
+    par = hs.prolog(m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}))
+    zNo, tNo, period = 40, 2, 0.03
+    ref, st0, _ = hs.solve_n2(par, zNo, tNo, period, 1e-9, 1e-13)
+    assert (st0 == 0).all()
+    for kernel in ("pbr_k4b_solve_n2", "pbr_k4bs_solve_n2", "pbr_k4c_solve_n2"):
+        snaps, status, stats = sim.solve_n2(kernel, par, zNo, tNo, period, grid=1)
+        assert (status == 0).all() and (stats[0] > 20).all()
+        assert relerr(snaps, ref, floor=1e-9) < 1e-7
