@@ -1953,7 +1953,10 @@ struct BlkCtx {
 #define PBR_K4B_FLAG_REDUCTION 1
 #endif
 #ifndef PBR_K4B_MARCH_V2
-#define PBR_K4B_MARCH_V2 0            // 1: leaner serial chain (see pbr_k4b_march; A/B pending)
+#define PBR_K4B_MARCH_V2 1            // leaner serial chain (see pbr_k4b_march): 190 -> 182.6 ms per 4,096 solves at zNo = 100
+#endif
+#ifndef PBR_K4B_EVAL_OUTLINE
+#define PBR_K4B_EVAL_OUTLINE 0        // 1: the RHS-only evaluation (initial step, verification iterations) out of line (A/B)
 #endif
 #ifndef PBR_K4B_MARCH_ROWSPLIT
 #define PBR_K4B_MARCH_ROWSPLIT 1      // 1: row-per-lane march; 0: every lane does the whole mat-vec (A/B pending)
@@ -2031,6 +2034,17 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
     return true;
 #endif
 }
+
+// RHS-only evaluation: three call sites (two in the initial-step probe, one in the rare verification iterations); out of line
+// they share one copy of the node function instead of three (the kernel is ~200 KB of SASS and stalls on instruction fetch).
+#if PBR_K4B_EVAL_OUTLINE
+__device__ __noinline__ bool pbr_k4b_eval_rhs(const BlkCtx& cx, const InstPar& p, int zNo, bool act, const double* y, double c,
+                                              double* Ysm, double* Asm, double* f, double* sub) {
+    return pbr_k4b_eval<false>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub);
+}
+#else
+#define pbr_k4b_eval_rhs pbr_k4b_eval<false>
+#endif
 
 // x_z = Ainv_z (b_z + cs_z * x_{z-1}) = g_z + Ainv_z (cs_z * x_{z-1}) for all nodes; b (registers) is overwritten by x.
 // g_z = Ainv_z b_z does not depend on the march and is computed by all lanes up front (into gsm = the iterate-exchange
@@ -2142,7 +2156,7 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
     }
     __syncthreads();
 #if PBR_K4B_MARCH_V2
-    // Leaner serial chain (A/B): the products Ainv*cs are formed off the chain (in extent coordinates cs = c*sub is the same
+    // Leaner serial chain: the products Ainv*cs are formed off the chain (in extent coordinates cs = c*sub is the same
     // for every node but the reactor's first, whose incoming x is zero anyway, so it is not shuffled per node), the dot
     // product is summed as two independent halves, and x_z goes back to shared memory in place of g_z (one predicated store)
     // instead of being handed to the owning lane through predicated register moves; every thread picks its x up at the end.
@@ -2317,7 +2331,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 double h0 = 0.0, d1 = 0.0, f0[PBR_NX2];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) { y[v] = act ? D[0*NV + v] : 1.0; sub[v] = 0.0; f[v] = 0.0; f0[v] = 0.0; }
-                bool ok = pbr_k4b_eval<false>(cx, p, zNo, act, y, 0.0, Ysm, Asm, f, sub); nfev++;
+                bool ok = pbr_k4b_eval_rhs(cx, p, zNo, act, y, 0.0, Ysm, Asm, f, sub); nfev++;
                 double a0 = 0.0, a1 = 0.0;
                 if (act) {
                     double yf[PBR_NV2];
@@ -2339,7 +2353,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 double y1[PBR_NX2];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) y1[v] = y[v] + h0*f0[v];
-                ok = pbr_k4b_eval<false>(cx, p, zNo, act, y1, 0.0, Ysm, Asm, f, sub) && ok; nfev++;
+                ok = pbr_k4b_eval_rhs(cx, p, zNo, act, y1, 0.0, Ysm, Asm, f, sub) && ok; nfev++;
                 a0 = 0.0;
                 if (act) {
                     double df[PBR_NX2];
@@ -2415,7 +2429,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                     if (running) {
                         n_iter = k + 1;
                         bool fin = true;
-                        if (k > 0 || !fresh) { fin = pbr_k4b_eval<false>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub); nfev++; }
+                        if (k > 0 || !fresh) { fin = pbr_k4b_eval_rhs(cx, p, zNo, act, y, c, Ysm, Asm, f, sub); nfev++; }
                         if (!fin) running = false;
                         else {
                             if (act) {
@@ -2531,6 +2545,14 @@ extern "C" __global__ void __launch_bounds__(256, PBR_K4B_MINBLOCKS) pbr_k4b_sol
 extern "C" __global__ void __launch_bounds__(256, PBR_K4B_MINBLOCKS) pbr_k4bs_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                     double rtol, double atol, int max_steps,
                                                                     double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
+    pbr_k4b_body<false, true>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats);
+}
+
+// the whole state on chip for grids of 257..512 nodes (59*zNo doubles = 189 KB at zNo = 400), scan march; chosen by the launcher
+// only under PBR_K4C_ONCHIP=1 (A/B against pbr_k4c_solve_n2)
+extern "C" __global__ void __launch_bounds__(512) pbr_k4d_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+                                                                   double rtol, double atol, int max_steps,
+                                                                   double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
     pbr_k4b_body<false, true>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats);
 }
 
