@@ -292,8 +292,9 @@ def run_gpu(a):
             "roofline": {"kernel": "pbr_k2_solve_n1", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved/fp64_peak if fp64_peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size, ncu --set full
-                         # (profiles/r1e_k2_v6_block224_and_k3_v2.txt): 11.32 MB + 1.07 MB
-                         "traffic": 12.39e6, "traffic_unit": "B/launch (ncu, profiles/)",
+                         # (profiles/r1m_k2_final_N65536.txt): 11.10 MB read + 1.3 KB written (the 4.2 MB of outlet rows are
+                         # still in L2 when the kernel ends); algorithmic: 11.5 MB of per-reactor constants in, 4.2 MB out
+                         "traffic": 11.10e6, "traffic_unit": "B/launch (ncu, profiles/r1m_k2_final_N65536.txt)",
                          "peak_source": "DFMA probe pbr_k_dfma_peak measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                          "kernel_ms": 1e3*t_k2, "algorithmic_flops_per_launch": flops, "flops_per_unit": per_unit,
                          "mean_steps": float(stats[0].mean()), "mean_nfev": float(stats[2].mean()), "mean_nlu": float(stats[3].mean()),
