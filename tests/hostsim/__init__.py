@@ -34,7 +34,7 @@ def _build(src, driver, extra=()):
 
 class SimtSim:
     """The block-per-reactor N2 solver kernels run through the fiber-based SIMT emulator (simt.h, simt_driver.cpp)."""
-    KERNELS = {"pbr_k4b_solve_n2": 0, "pbr_k4bs_solve_n2": 1, "pbr_k4c_solve_n2": 2}
+    KERNELS = {"pbr_k4b_solve_n2": 0, "pbr_k4bs_solve_n2": 1, "pbr_k4c_solve_n2": 2, "pbr_k4d_solve_n2": 3}
 
     def __init__(self, model):
         self.L = _build(model.source, "simt_driver.cpp", extra=("simt.h",))

@@ -28,7 +28,7 @@ void hs_simt_eval(int zNo, const double* par, const double* x, double* f) {
     });
 }
 
-// kernel: 0 = pbr_k4b_solve_n2, 1 = pbr_k4bs_solve_n2, 2 = pbr_k4c_solve_n2.  par [KPAR][N]; snaps [N][tNo][NV2][zNo];
+// kernel: 0 = pbr_k4b_solve_n2, 1 = pbr_k4bs_solve_n2, 2 = pbr_k4c_solve_n2, 3 = pbr_k4d_solve_n2.  par [KPAR][N]; snaps [N][tNo][NV2][zNo];
 // stats [4][N].  grid < N exercises the kernels' loop over instances.
 int hs_simt_solve_n2(int kernel, long N, int zNo, int tNo, double period, const double* par, double rtol, double atol,
                      int max_steps, int grid, double* snaps, int* status, int* stats) {
@@ -40,6 +40,7 @@ int hs_simt_solve_n2(int kernel, long N, int zNo, int tNo, double period, const 
     simt::launch((unsigned)grid, block, [&]() {
         if (kernel == 0) pbr_k4b_solve_n2(N, zNo, tNo, period, par, rtol, atol, max_steps, snaps, status, stats);
         else if (kernel == 1) pbr_k4bs_solve_n2(N, zNo, tNo, period, par, rtol, atol, max_steps, snaps, status, stats);
+        else if (kernel == 3) pbr_k4d_solve_n2(N, zNo, tNo, period, par, rtol, atol, max_steps, snaps, status, stats);
         else pbr_k4c_solve_n2(N, zNo, tNo, period, par, rtol, atol, max_steps, gw, snaps, status, stats);
     });
     return 0;

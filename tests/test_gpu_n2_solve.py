@@ -115,7 +115,7 @@ def test_rmtExeBatch_n2_and_failure_status():
 
 def test_n2_both_kernels_agree_and_large_grid():
     """K4b (block per reactor, zNo <= 256) and K4 (warp per reactor, any zNo) integrate the same equations: they must agree
-    to integration tolerance; zNo = 400 (BASELINE config 4 grid) runs through K4 and is checked against the oracle."""
+    to integration tolerance; zNo = 400 (BASELINE config 4 grid) runs through K4d and K4c and is checked against the oracle."""
     import os
     from pyremot_b200.api import get_model
     mi = cases.readme_case("N2")
@@ -131,8 +131,14 @@ def test_n2_both_kernels_agree_and_large_grid():
         del os.environ["PBR_N2_KERNEL"]
     assert (blk["status"] == 0).all() and (wrp["status"] == 0).all()
     assert relerr(blk["dataYs"], wrp["dataYs"]) < 1e-7
-    big = m.solve_n2_host(tab[:2], 400, 1, 0.05)
+    big = m.solve_n2_host(tab[:2], 400, 1, 0.05)             # K4d: all on chip, scan march
     assert (big["status"] == 0).all()
+    os.environ["PBR_K4C_ONCHIP"] = "0"                       # K4c: history in a global slab (what a model whose state
+    try:                                                     # does not fit on chip gets at this grid size)
+        slab = m.solve_n2_host(tab[:2], 400, 1, 0.05)
+    finally:
+        del os.environ["PBR_K4C_ONCHIP"]
+    assert (slab["status"] == 0).all() and relerr(slab["dataYs"], big["dataYs"]) < 1e-7
     ens = O.Ensemble(mi, {k: v[:1] for k, v in sweep.items()})
     ens.period = 0.05
     _, ref, _ = O.solve_n2(ens, zNo=400, tNo=1, method="BDF", rtol=1e-9, atol=1e-13, sparse=True)
