@@ -1475,15 +1475,26 @@ struct N2Stats { int nsteps, nrej, nfev, nlu, nfail; };
 
 // Integrate one interval [t0, t1] from the state in ws.D(0,.) (restart: order 1, fresh initial step — the reference
 // restarts solve_ivp at every interval, pbHomoReactor.py:3589-3685).  On success ws.D(0,.) holds Y(t1).
+// The reference calls solve_ivp once per output interval (:3589-3685), i.e. the integrator restarts at order 1 with a fresh
+// initial step at every snapshot.  The converged snapshots do not depend on that; the restarts only cost ~20 steps each (10 % of
+// the steps of the BASELINE config-3 run).  PBR_N2_RESTART=0 (default): the BDF state (history, order, step size) is carried
+// across the snapshot times -- the step that reaches a snapshot time is still clipped to land on it exactly.
+// PBR_N2_RESTART=1: the reference's restarts.
+#ifndef PBR_N2_RESTART
+#define PBR_N2_RESTART 0
+#endif
+struct N2Carry { int order, n_equal, started; double h, pend, kappa; };
+
 PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, double t0, double t1,
-                            double rtol, double atol, int max_steps, N2Stats& stt) {
+                            double rtol, double atol, int max_steps, N2Stats& stt, N2Carry& cy) {
     const int zNo = ws.zNo;
     const double nTot = (double)(PBR_NV2*zNo);
     const double newton_tol = fmax(10.0*2.220446049250313e-16/rtol, fmin(0.03, sqrt(rtol)));
     const double span = t1 - t0;
+    const bool fresh_start = PBR_N2_RESTART || !cy.started;
     // ---- initial step (scipy common.py:68-140): f0 = f(Y0), f1 = f(Y0 + h0 f0)
-    double h = 0.0;
-    {
+    double h = cy.h;
+    if (fresh_start) {
         double h0 = 0.0, d1 = 0.0;
         for (int z = w.lane; z < zNo; z += WarpCtx::NL)
 #pragma unroll
@@ -1518,14 +1529,17 @@ PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, 
             }
         }
     }
-    for (int z = w.lane; z < zNo; z += WarpCtx::NL)
+    if (fresh_start) {
+        for (int z = w.lane; z < zNo; z += WarpCtx::NL)
 #pragma unroll
-        for (int v = 0; v < PBR_NV2; ++v) {
-            ws.D(1, v)[z] *= h;
-            for (int r = 2; r < PBR_DROWS; ++r) ws.D(r, v)[z] = 0.0;
-        }
-    int order = 1, n_equal = 0, trip = 0;
-    double t = t0, pend = 1.0, kappa = 1e300;
+            for (int v = 0; v < PBR_NV2; ++v) {
+                ws.D(1, v)[z] *= h;
+                for (int r = 2; r < PBR_DROWS; ++r) ws.D(r, v)[z] = 0.0;
+            }
+        cy.order = 1; cy.n_equal = 0; cy.pend = 1.0; cy.kappa = 1e300; cy.started = 1;
+    }
+    int order = cy.order, n_equal = cy.n_equal, trip = 0;
+    double t = t0, pend = cy.pend, kappa = cy.kappa;
     int status = PBR_OK;
     bool active = true;
 
@@ -1635,6 +1649,7 @@ PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, 
             if (!(t < t1)) active = false;
         }
     }
+    cy.order = order; cy.n_equal = n_equal; cy.h = h; cy.pend = pend; cy.kappa = kappa;
     return status;
 }
 
@@ -1650,10 +1665,11 @@ PBR_DEV int pbr_n2_solve(const WarpCtx& w, const InstPar& p, const N2Ws& ws, int
         if (!PBR_ISO) ws.D(0, PBR_ISO ? 0 : PBR_NC)[z] = 0.0;
     }
     int status = PBR_OK;
+    N2Carry cy; cy.order = 1; cy.n_equal = 0; cy.started = 0; cy.h = 0.0; cy.pend = 1.0; cy.kappa = 1e300;
     for (int k = 0; k < tNo && status == PBR_OK; ++k) {
         const double t0 = (k == 0) ? 0.0 : period*((double)k/(double)tNo);          // np.linspace(0, opT, tNo+1)
         const double t1 = (k == tNo - 1) ? period : period*((double)(k + 1)/(double)tNo);
-        status = pbr_n2_interval(w, p, ws, t0, t1, rtol, atol, max_steps, stt);
+        status = pbr_n2_interval(w, p, ws, t0, t1, rtol, atol, max_steps, stt, cy);
         w.sync();
         for (int z = w.lane; z < zNo; z += WarpCtx::NL)
 #pragma unroll
@@ -2320,14 +2336,20 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
             for (int v = 0; v < PBR_NC; ++v) D[0*NV + v] = p.c0[v];
 #endif
         }
+        // BDF state carried across the snapshot times unless PBR_N2_RESTART (see pbr_n2_interval)
+        int order = 1, n_equal = 0;
+        double h = 0.0, pend = 1.0, kappa = 1e300, c_lu = 0.0;
+        bool need_jac = true;
+        double sub[PBR_NX2];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) sub[v] = 0.0;
         for (int kint = 0; kint < tNo && rc == PBR_OK; ++kint) {
             const double t0 = (kint == 0) ? 0.0 : period*((double)kint/(double)tNo);  // np.linspace(0, opT, tNo+1)
             const double t1 = (kint == tNo - 1) ? period : period*((double)(kint + 1)/(double)tNo);
             const double span = t1 - t0;
-            double y[PBR_NX2], d[PBR_NX2], f[PBR_NX2], sub[PBR_NX2], b[PBR_NX2];
-            // ---- initial step (scipy common.py:68-140), restart at every interval (:3589-3685)
-            double h = 0.0;
-            {
+            double y[PBR_NX2], d[PBR_NX2], f[PBR_NX2], b[PBR_NX2];
+            // ---- initial step (scipy common.py:68-140); with PBR_N2_RESTART again at every interval (:3589-3685)
+            if (PBR_N2_RESTART || kint == 0) {
                 double h0 = 0.0, d1 = 0.0, f0[PBR_NX2];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) { y[v] = act ? D[0*NV + v] : 1.0; sub[v] = 0.0; f[v] = 0.0; f0[v] = 0.0; }
@@ -2372,12 +2394,13 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                         for (int r = 2; r < PBR_DROWS; ++r) D[r*NV + v] = 0.0;
                     }
                 }
+                order = 1; n_equal = 0; pend = 1.0; kappa = 1e300;
+                c_lu = 0.0;                    // the c the inverses in Asm were built with (0: none yet)
+                need_jac = true;
             }
-            int order = 1, n_equal = 0, trip = 0;
-            double t = t0, pend = 1.0, kappa = 1e300;
+            int trip = 0;
+            double t = t0;
             bool active = (rc == PBR_OK);
-            double c_lu = 0.0;                 // the c the inverses in Asm were built with (0: none yet)
-            bool need_jac = true;
             while (active) {
                 // ---- 1. step size, lazy history rescale
                 double hn = h*pend;

@@ -11,12 +11,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "default": "",
-    "march_v1": "PBR_K4B_MARCH_V2=0",
-    "eval_outline": "PBR_K4B_EVAL_OUTLINE=1",
+    "restart_every_interval": "PBR_N2_RESTART=1",
 }
 # measured and recorded in profiles/r1l_k4*_variants_*.jsonl: PBR_K4B_MARCH_ROWSPLIT=0, PBR_K4B_MARCH_SCAN=1,
 # PBR_K4B_INVERT_REG=1, PBR_K4B_FLAG_REDUCTION=0 and their combinations; in profiles/r1m_k4*_variants_*.jsonl:
-# PBR_K4B_MARCH_V2=1 (adopted), PBR_K4B_JAC_REUSE=1 with PBR_K4B_JAC_CTOL=0 / 0.2 (rejected: 1.5x slower)
+# PBR_K4B_MARCH_V2=1 (adopted), PBR_K4B_JAC_REUSE=1 with PBR_K4B_JAC_CTOL=0 / 0.2 (rejected: 1.5x slower);
+# in profiles/r1n_*: PBR_K4B_EVAL_OUTLINE=1 (rejected), K4d on chip (adopted)
 
 
 def env_for(defs):
