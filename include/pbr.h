@@ -105,10 +105,12 @@ int pbr_unscale_n1(pbr_ctx* ctx, long N, int K, const double* inst_par_dev, cons
 int pbr_solve_n1_host(pbr_ctx* ctx, long N, const double* inst_in_host, double rtol, double atol, int n_out,
                       int max_steps, double* prof_host, double* outlet_host, int* status_host, int* stats_host);
 
-/* K4 — the interval loop of runN2 (:3589-3685): for each of tNo intervals of length period/tNo the solve_ivp call
- * (:3609) restarted from the previous end state; variable-order BDF, block lower-bidiagonal Newton matrix (per-node 7x7
- * blocks + forward substitution along the bed).  One block per reactor / one thread per node up to 512 nodes (state in
- * shared memory), one warp per reactor above.  IV = feed-filled bed (:3483-3497).
+/* K4 — the interval loop of runN2 (:3589-3685): tNo intervals of length period/tNo, a snapshot at every interval end
+ * (the reference restarts solve_ivp (:3609) from the previous end state at each of them; here the BDF state is carried
+ * across the snapshot times, which land exactly on step ends -- same converged snapshots, ~10 % fewer steps);
+ * variable-order BDF, block lower-bidiagonal Newton matrix (per-node blocks + forward substitution / affine-map scan
+ * along the bed).  One block per reactor / one thread per node up to 512 nodes (state in shared memory), one warp per
+ * reactor above.  IV = feed-filled bed (:3483-3497).
  *   snaps_y_dev [N][tNo][nv2][zNo] scaled state at the interval ends;  status_dev [N];  stats_dev [4][N] or NULL.
  * Scratch ((13*nv2 + 2*nv2^2 + 1)*zNo doubles per resident warp) is owned by the context. */
 int pbr_solve_n2(pbr_ctx* ctx, long N, int zNo, int tNo, double period, const double* inst_par_dev, double rtol,
