@@ -843,61 +843,6 @@ PBR_DEV bool pbr_invert(const Strided& a) {
     return ok;
 }
 
-// The same inverse on a matrix held in REGISTERS (fully unrolled, compile-time indices; row/column exchanges are taken only
-// when a pivot search asks for them).  For the small node blocks of the extent form (N <= 4): no shared-memory round trips.
-template <int N>
-PBR_DEV bool pbr_invert_reg(double* a) {
-    bool ok = true;
-    int perm[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        int pk = k;
-        double amax = fabs(a[k*N + k]);
-#pragma unroll
-        for (int i = k + 1; i < N; ++i) {
-            const double v = fabs(a[i*N + k]);
-            if (v > amax) { amax = v; pk = i; }
-        }
-        perm[k] = pk;
-        if (pk != k) {
-#pragma unroll
-            for (int i = k + 1; i < N; ++i) {
-                if (pk == i) {
-#pragma unroll
-                    for (int j = 0; j < N; ++j) { const double t = a[k*N + j]; a[k*N + j] = a[i*N + j]; a[i*N + j] = t; }
-                }
-            }
-        }
-        if (!(amax > 0.0) || !(amax < 1e300)) ok = false;
-        const double pinv = pbr_rcp_40bit(a[k*N + k]);
-        a[k*N + k] = 1.0;
-#pragma unroll
-        for (int j = 0; j < N; ++j) a[k*N + j] *= pinv;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            if (i != k) {
-                const double f = a[i*N + k];
-                a[i*N + k] = 0.0;
-#pragma unroll
-                for (int j = 0; j < N; ++j) a[i*N + j] -= f*a[k*N + j];
-            }
-        }
-    }
-#pragma unroll
-    for (int k = N - 1; k >= 0; --k) {
-        if (perm[k] != k) {
-#pragma unroll
-            for (int q = k + 1; q < N; ++q) {
-                if (perm[k] == q) {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) { const double t = a[i*N + k]; a[i*N + k] = a[i*N + q]; a[i*N + q] = t; }
-                }
-            }
-        }
-    }
-    return ok;
-}
-
 struct LuStore {            // receives Jacobian entries, stores the Newton matrix I - c*J
     Strided a; double c;
     PBR_DEV void operator()(int i, int k, double v) const { a[i*PBR_NX + k] = (i == k ? 1.0 : 0.0) - c*v; }
@@ -1473,8 +1418,7 @@ PBR_DEV void pbr_n2_change_D(const WarpCtx& w, const N2Ws& ws, int order, double
 
 struct N2Stats { int nsteps, nrej, nfev, nlu, nfail; };
 
-// Integrate one interval [t0, t1] from the state in ws.D(0,.) (restart: order 1, fresh initial step — the reference
-// restarts solve_ivp at every interval, pbHomoReactor.py:3589-3685).  On success ws.D(0,.) holds Y(t1).
+// Integrate one interval [t0, t1] from the state in ws.D(0,.); on success ws.D(0,.) holds Y(t1).
 // The reference calls solve_ivp once per output interval (:3589-3685), i.e. the integrator restarts at order 1 with a fresh
 // initial step at every snapshot.  The converged snapshots do not depend on that; the restarts only cost ~20 steps each (10 % of
 // the steps of the BASELINE config-3 run).  PBR_N2_RESTART=0 (default): the BDF state (history, order, step size) is carried
@@ -1965,33 +1909,16 @@ struct BlkCtx {
     }
 };
 
-#ifndef PBR_K4B_FLAG_REDUCTION
-#define PBR_K4B_FLAG_REDUCTION 1
-#endif
-#ifndef PBR_K4B_MARCH_V2
-#define PBR_K4B_MARCH_V2 1            // leaner serial chain (see pbr_k4b_march): 190 -> 182.6 ms per 4,096 solves at zNo = 100
-#endif
-#ifndef PBR_K4B_EVAL_OUTLINE
-#define PBR_K4B_EVAL_OUTLINE 0        // 1: the RHS-only evaluation (initial step, verification iterations) out of line (A/B)
-#endif
-#ifndef PBR_K4B_MARCH_ROWSPLIT
-#define PBR_K4B_MARCH_ROWSPLIT 1      // 1: row-per-lane march; 0: every lane does the whole mat-vec (A/B pending)
-#endif
-#ifndef PBR_K4B_INVERT_REG
-#define PBR_K4B_INVERT_REG 0          // 1: node blocks inverted in registers (NX2 <= 4; A/B pending)
-#endif
-struct RegStore {        // Jacobian entries of this thread's node -> I - c*J in registers (compile-time indices only)
-    double a[PBR_NX2*PBR_NX2]; double c;
-    __device__ __forceinline__ void operator()(int i, int k, double v) { a[i*PBR_NX2 + k] = (i == k ? 1.0 : 0.0) - c*v; }
-};
+// Measured and rejected variants of this kernel (records: profiles/r1l_*, r1m_*, r1n_* and DESIGN.md section 4): a march in which every
+// lane does the whole mat-vec, the 4x4 inverse in registers, a NaN-poisoned failure flag instead of the block reduction,
+// Jacobian / inverse reuse across steps, the RHS-only evaluation out of line.  Their code is gone; the history has it.
 struct SmStore {         // Jacobian entries of this thread's node -> I - c*J in its shared-memory column
     Strided a; double c;
     __device__ __forceinline__ void operator()(int i, int k, double v) const { a[i*PBR_NX2 + k] = (i == k ? 1.0 : 0.0) - c*v; }
 };
 
 // f(Y) at this thread's node from the iterate y[] (registers); with JAC also leaves Ainv in shared memory and sub[].
-// PBR_K4B_FLAG_REDUCTION=0: a non-finite f or a singular block poisons f[0] with NaN instead of being reduced over the block;
-// the NaN reaches the next block-wide norm through the march, so no separate reduction (2 barriers) is spent on the flag.
+// Returns false (block-uniform) if any node produced a non-finite value or a singular block.
 template <bool JAC>
 __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p, int zNo, bool act, const double* y, double c,
                                              double* Ysm, double* Asm, double* f, double* sub) {
@@ -2021,46 +1948,18 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
     if (act) {
         if (JAC) {
             const Strided blk = {Asm + z, zNo};
-#if PBR_K4B_INVERT_REG
-            RegStore st; st.c = c;
-#pragma unroll
-            for (int q = 0; q < PBR_NX2*PBR_NX2; ++q) st.a[q] = (q % (PBR_NX2 + 1) == 0) ? 1.0 : 0.0;
-            pbr_n2x_node<true>(y, yb, z == 0, Pz, inv_dz, p, f, st, sub);
-            if (!pbr_invert_reg<PBR_NX2>(st.a)) bad = 1.0;
-#pragma unroll
-            for (int q = 0; q < PBR_NX2*PBR_NX2; ++q) blk[q] = st.a[q];      // Ainv into the node's shared-memory column
-#else
             SmStore st = {blk, c};
             pbr_n2x_node<true>(y, yb, z == 0, Pz, inv_dz, p, f, st, sub);
             if (!pbr_invert<PBR_NX2>(blk)) bad = 1.0;          // Ainv replaces I - c*J in place
-#endif
         } else {
             NoStore ns;
             pbr_n2x_node<false>(y, yb, z == 0, Pz, inv_dz, p, f, ns, (double*)0);
         }
 #pragma unroll
         for (int v = 0; v < PBR_NX2; ++v) if (!(fabs(f[v]) < 1e300)) bad = 1.0;
-#if !PBR_K4B_FLAG_REDUCTION
-        if (bad != 0.0) f[0] = __longlong_as_double(0x7ff8000000000000ll);
-#endif
     }
-#if PBR_K4B_FLAG_REDUCTION
     return cx.sum(bad) == 0.0;
-#else
-    return true;
-#endif
 }
-
-// RHS-only evaluation: three call sites (two in the initial-step probe, one in the rare verification iterations); out of line
-// they share one copy of the node function instead of three (the kernel is ~200 KB of SASS and stalls on instruction fetch).
-#if PBR_K4B_EVAL_OUTLINE
-__device__ __noinline__ bool pbr_k4b_eval_rhs(const BlkCtx& cx, const InstPar& p, int zNo, bool act, const double* y, double c,
-                                              double* Ysm, double* Asm, double* f, double* sub) {
-    return pbr_k4b_eval<false>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub);
-}
-#else
-#define pbr_k4b_eval_rhs pbr_k4b_eval<false>
-#endif
 
 // x_z = Ainv_z (b_z + cs_z * x_{z-1}) = g_z + Ainv_z (cs_z * x_{z-1}) for all nodes; b (registers) is overwritten by x.
 // g_z = Ainv_z b_z does not depend on the march and is computed by all lanes up front (into gsm = the iterate-exchange
@@ -2171,7 +2070,6 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
         }
     }
     __syncthreads();
-#if PBR_K4B_MARCH_V2
     // Leaner serial chain: the products Ainv*cs are formed off the chain (in extent coordinates cs = c*sub is the same
     // for every node but the reactor's first, whose incoming x is zero anyway, so it is not shuffled per node), the dot
     // product is summed as two independent halves, and x_z goes back to shared memory in place of g_z (one predicated store)
@@ -2220,90 +2118,13 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
 #pragma unroll
         for (int v = 0; v < PBR_NX2; ++v) b[v] = gsm[v*zNo + z];
     }
-#elif PBR_K4B_MARCH_ROWSPLIT
-    const int row = (cx.lane < PBR_NX2) ? cx.lane : 0;     // the mat-vec row this lane contributes
-    for (int wv = 0; wv < nwz; ++wv) {
-        if (cx.wid == wv) {
-            double xp[PBR_NX2];
-#pragma unroll
-            for (int v = 0; v < PBR_NX2; ++v) xp[v] = (wv == 0) ? 0.0 : cx.red[v];
-            const int zb = wv*32;
-            const int nact = (zNo - zb < 32) ? (zNo - zb) : 32;
-            for (int l = 0; l < nact; ++l) {
-                const int zl = zb + l;
-                double arow[PBR_NX2];
-#pragma unroll
-                for (int k = 0; k < PBR_NX2; ++k) arow[k] = Asm[(row*PBR_NX2 + k)*zNo + zl];
-                double acc = gsm[row*zNo + zl];
-#pragma unroll
-                for (int k = 0; k < PBR_NX2; ++k) acc += arow[k]*(__shfl_sync(0xffffffffu, cs[k], l)*xp[k]);
-#pragma unroll
-                for (int v = 0; v < PBR_NX2; ++v) xp[v] = __shfl_sync(0xffffffffu, acc, v);
-                if (cx.lane == l) {
-#pragma unroll
-                    for (int v = 0; v < PBR_NX2; ++v) b[v] = xp[v];
-                }
-            }
-            if (cx.lane == 0) {
-#pragma unroll
-                for (int v = 0; v < PBR_NX2; ++v) cx.red[v] = xp[v];      // x of this warp's last node
-            }
-        }
-        __syncthreads();
-    }
-#else
-    // every lane of the marching warp carries the whole x and does the full NX2 x NX2 mat-vec itself (the inverse block and
-    // g_z are broadcast loads, independent of the chain): NX2 independent FMA chains of length NX2 per node and no shuffle
-    // on the critical path (the row-per-lane version above needs NX2 shuffles per node to gather x_z)
-    for (int wv = 0; wv < nwz; ++wv) {
-        if (cx.wid == wv) {
-            double xp[PBR_NX2];
-#pragma unroll
-            for (int v = 0; v < PBR_NX2; ++v) xp[v] = (wv == 0) ? 0.0 : cx.red[v];
-            const int zb = wv*32;
-            const int nact = (zNo - zb < 32) ? (zNo - zb) : 32;
-#pragma unroll 2
-            for (int l = 0; l < nact; ++l) {
-                const int zl = zb + l;
-                double csx[PBR_NX2], acc[PBR_NX2];
-#pragma unroll
-                for (int k = 0; k < PBR_NX2; ++k) csx[k] = __shfl_sync(0xffffffffu, cs[k], l)*xp[k];
-#pragma unroll
-                for (int i = 0; i < PBR_NX2; ++i) acc[i] = gsm[i*zNo + zl];
-#pragma unroll
-                for (int k = 0; k < PBR_NX2; ++k)
-#pragma unroll
-                    for (int i = 0; i < PBR_NX2; ++i) acc[i] += Asm[(i*PBR_NX2 + k)*zNo + zl]*csx[k];
-#pragma unroll
-                for (int v = 0; v < PBR_NX2; ++v) xp[v] = acc[v];
-                if (cx.lane == l) {
-#pragma unroll
-                    for (int v = 0; v < PBR_NX2; ++v) b[v] = xp[v];
-                }
-            }
-            if (cx.lane == 0) {
-#pragma unroll
-                for (int v = 0; v < PBR_NX2; ++v) cx.red[v] = xp[v];      // x of this warp's last node
-            }
-        }
-        __syncthreads();
-    }
-#endif
 }
 
-
-// The body is shared by two kernels: pbr_k4b_solve_n2 (<= 256 threads, history in shared memory) and pbr_k4c_solve_n2
-// (<= 512 threads = up to 512 nodes, history in a global scratch slab per block that stays L2-resident; launch bounds
-// cap it at 128 registers, so it spills, but it keeps the block-per-reactor structure for BASELINE config 4's zNo = 400).
-// PBR_K4B_JAC_REUSE=1 (A/B): keep the node blocks' inverses while c = h/alpha is unchanged (SciPy's policy, bdf.py:353-388:
-// new LU only when c changes, new Jacobian only after a Newton failure).  A whole block works on one reactor, so unlike K2
-// there is no lock-step argument against it; a reused (stale) Jacobian needs the regular two-iteration convergence test.
-#ifndef PBR_K4B_JAC_REUSE
-#define PBR_K4B_JAC_REUSE 0
-#endif
-#ifndef PBR_K4B_JAC_CTOL
-#define PBR_K4B_JAC_CTOL 0.0          // reuse while |c/c_lu - 1| <= CTOL (0: only for an identical c)
-#endif
+// The body is shared by four kernels: pbr_k4b_solve_n2 / pbr_k4bs_solve_n2 (<= 256 threads, serial / scan march, state in
+// shared memory), pbr_k4d_solve_n2 (<= 512 threads, scan march, state in shared memory, one block per SM) and pbr_k4c_solve_n2
+// (<= 512 threads, scan march, BDF history in a global scratch slab per block that stays L2-resident, for states that do not fit).
+// The Jacobian blocks and their inverses are rebuilt at every step attempt: keeping them while c = h/alpha is unchanged (SciPy's
+// policy) was measured and rejected -- a stale Jacobian needs two Newton iterations, i.e. two marches per step.
 template <bool D_GLOBAL, bool SCAN>
 __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                              double rtol, double atol, int max_steps, double* __restrict__ gwork,
@@ -2338,8 +2159,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
         }
         // BDF state carried across the snapshot times unless PBR_N2_RESTART (see pbr_n2_interval)
         int order = 1, n_equal = 0;
-        double h = 0.0, pend = 1.0, kappa = 1e300, c_lu = 0.0;
-        bool need_jac = true;
+        double h = 0.0, pend = 1.0, kappa = 1e300;
         double sub[PBR_NX2];
 #pragma unroll
         for (int v = 0; v < NV; ++v) sub[v] = 0.0;
@@ -2353,7 +2173,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 double h0 = 0.0, d1 = 0.0, f0[PBR_NX2];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) { y[v] = act ? D[0*NV + v] : 1.0; sub[v] = 0.0; f[v] = 0.0; f0[v] = 0.0; }
-                bool ok = pbr_k4b_eval_rhs(cx, p, zNo, act, y, 0.0, Ysm, Asm, f, sub); nfev++;
+                bool ok = pbr_k4b_eval<false>(cx, p, zNo, act, y, 0.0, Ysm, Asm, f, sub); nfev++;
                 double a0 = 0.0, a1 = 0.0;
                 if (act) {
                     double yf[PBR_NV2];
@@ -2375,7 +2195,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 double y1[PBR_NX2];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) y1[v] = y[v] + h0*f0[v];
-                ok = pbr_k4b_eval_rhs(cx, p, zNo, act, y1, 0.0, Ysm, Asm, f, sub) && ok; nfev++;
+                ok = pbr_k4b_eval<false>(cx, p, zNo, act, y1, 0.0, Ysm, Asm, f, sub) && ok; nfev++;
                 a0 = 0.0;
                 if (act) {
                     double df[PBR_NX2];
@@ -2395,8 +2215,6 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                     }
                 }
                 order = 1; n_equal = 0; pend = 1.0; kappa = 1e300;
-                c_lu = 0.0;                    // the c the inverses in Asm were built with (0: none yet)
-                need_jac = true;
             }
             int trip = 0;
             double t = t0;
@@ -2431,20 +2249,11 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 }
                 // ---- 3./4. Jacobian blocks + inverses at the predictor, Newton (bdf.py:36-68)
                 bool converged = false;
-#if PBR_K4B_JAC_REUSE
-                const bool fresh = need_jac || !(fabs(c - c_lu) <= PBR_K4B_JAC_CTOL*c_lu);
-#else
-                const bool fresh = true;
-#endif
-                bool running = true;
-                if (fresh) {
-                    running = pbr_k4b_eval<true>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub);
-                    nlu++; nfev++;
-                    c_lu = c; need_jac = !running;
-                }
+                bool running = pbr_k4b_eval<true>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub);
+                nlu++; nfev++;
                 double cs[PBR_NX2];
 #pragma unroll
-                for (int v = 0; v < NV; ++v) cs[v] = c_lu*sub[v];
+                for (int v = 0; v < NV; ++v) cs[v] = c*sub[v];
                 double dy_norm_old = -1.0;
                 int n_iter = 0;
 #pragma unroll 1
@@ -2452,7 +2261,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                     if (running) {
                         n_iter = k + 1;
                         bool fin = true;
-                        if (k > 0 || !fresh) { fin = pbr_k4b_eval_rhs(cx, p, zNo, act, y, c, Ysm, Asm, f, sub); nfev++; }
+                        if (k > 0) { fin = pbr_k4b_eval<false>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub); nfev++; }
                         if (!fin) running = false;
                         else {
                             if (act) {
@@ -2473,8 +2282,8 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                                 (rate >= 0.0 && (rate >= 1.0 || pbr_ipow(rate, PBR_NEWTON_MAXITER - k)/(1.0 - rate)*dy_norm > newton_tol));
                             if (diverge) running = false;
                             else {
-                                if (k == 1 && fresh) kappa = rate/fmax(dy_norm_old, 1e-300);
-                                const bool quad_ok = PBR_NEWTON_SKIP && fresh && k == 0 && (trip % PBR_KAPPA_PERIOD) != 0 &&
+                                if (k == 1) kappa = rate/fmax(dy_norm_old, 1e-300);
+                                const bool quad_ok = PBR_NEWTON_SKIP && k == 0 && (trip % PBR_KAPPA_PERIOD) != 0 &&
                                                      kappa*dy_norm*dy_norm < PBR_NEWTON_SKIP_TOL;
                                 if (dy_norm == 0.0 || quad_ok || (rate >= 0.0 && rate/(1.0 - rate)*dy_norm < newton_tol)) { converged = true; running = false; }
                                 dy_norm_old = dy_norm;
@@ -2491,11 +2300,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                     err_norm = pbr_bdf_errc(order)*sqrt(cx.sum(en)/nTot);
                 }
                 const bool accepted = converged && (err_norm <= 1.0);
-                if (!converged) {
-                    if (fresh) pend = 0.5;             // bdf.py:375-388: with a current Jacobian halve the step,
-                    else need_jac = true;              // otherwise retry the same step with a new one
-                    nrejf++;
-                }
+                if (!converged) { pend = 0.5; nrejf++; }
                 else if (!accepted) {
                     pend = (err_norm == err_norm) ? fmax(PBR_MIN_FACTOR, safety*pbr_fpow(err_norm, -1.0/(order + 1))) : 0.5;
                     nrejf++;

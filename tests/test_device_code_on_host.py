@@ -202,7 +202,7 @@ def test_block_kernels_on_the_simt_emulator_vs_converged_reference(golden):
         assert relerr(snaps, ref_snaps, floor=1e-12) < 1e-9 and abs(int(stats[0, 0]) - int(ref_stats[0, 0])) <= 2
 
 
-@pytest.mark.parametrize("defines", [None, "PBR_K4B_MARCH_V2=0"])
+@pytest.mark.parametrize("defines", [None, "PBR_N2_RESTART=1"])
 def test_block_kernels_multi_warp_ragged_grid_and_instance_loop(defines):
     """zNo = 40: two warps, the second one ragged (8 nodes), so the marches hand over between warps, the scan chains warp totals
     and the block reductions span warps; 2 reactors on a grid of 1 block exercise the kernels' loop over instances.  All
@@ -213,7 +213,7 @@ def test_block_kernels_multi_warp_ragged_grid_and_instance_loop(defines):
     zNo, tNo, period = 40, 2, 0.03
     ref, st0, _ = hs.solve_n2(par, zNo, tNo, period, 1e-9, 1e-13)
     assert (st0 == 0).all()
-    # the old serial march only differs in pbr_k4b_solve_n2
+    # the reference's restart at every snapshot time (PBR_N2_RESTART=1): same body in all kernels, one is enough
     kernels = ("pbr_k4b_solve_n2",) if defines else ("pbr_k4b_solve_n2", "pbr_k4bs_solve_n2", "pbr_k4c_solve_n2", "pbr_k4d_solve_n2")
     for kernel in kernels:
         snaps, status, stats = sim.solve_n2(kernel, par, zNo, tNo, period, grid=1)

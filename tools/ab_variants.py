@@ -12,11 +12,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {
     "default": "",
     "restart_every_interval": "PBR_N2_RESTART=1",
+    "k4b_scan_march": "PBR_K4B_MARCH_SCAN=1",
+    "k4c_serial_march": "PBR_K4C_MARCH_SCAN=0",
 }
 # measured and recorded in profiles/r1l_k4*_variants_*.jsonl: PBR_K4B_MARCH_ROWSPLIT=0, PBR_K4B_MARCH_SCAN=1,
 # PBR_K4B_INVERT_REG=1, PBR_K4B_FLAG_REDUCTION=0 and their combinations; in profiles/r1m_k4*_variants_*.jsonl:
 # PBR_K4B_MARCH_V2=1 (adopted), PBR_K4B_JAC_REUSE=1 with PBR_K4B_JAC_CTOL=0 / 0.2 (rejected: 1.5x slower);
-# in profiles/r1n_*: PBR_K4B_EVAL_OUTLINE=1 (rejected), K4d on chip (adopted)
+# in profiles/r1n_*: PBR_K4B_EVAL_OUTLINE=1 (rejected), K4d on chip (adopted).  The code of the rejected variants has
+# been removed from pbr_device.cuh; the switches that remain are the ones listed above
 
 
 def env_for(defs):
