@@ -45,6 +45,9 @@ typedef enum {
 #define PBR_INST_MAX_STEPS 2
 #define PBR_INST_NONFINITE 3
 #define PBR_INST_SINGULAR 4
+#define PBR_INST_BAD_IV 5         /* N2 resume: the saved state is not of the form c0 + S^T x (cannot come from this model) */
+/* Rows of instances whose status is not 0 are filled with NaN (outlet, profile, and the N2 snapshots from the failing
+ * interval on), so a failed instance can never be mistaken for a result. */
 
 /* device >= 0: bind to that CUDA device (fails loudly if there is none). device < 0: compile-only context
  * (NVRTC needs no GPU) — used by the build check and the CPU-side tests. */
@@ -116,6 +119,15 @@ int pbr_solve_n1_host(pbr_ctx* ctx, long N, const double* inst_in_host, double r
 int pbr_solve_n2(pbr_ctx* ctx, long N, int zNo, int tNo, double period, const double* inst_par_dev, double rtol,
                  double atol, int max_steps, double* snaps_y_dev, int* status_dev, int* stats_dev, void* stream);
 
+/* The same with a saved state: integrate intervals k_first .. tNo-1 of linspace(0, period, tNo+1) starting from
+ * iv_y_dev [N][nv2][zNo] (scaled, e.g. snapshot k_first-1 of an earlier run) -- what the reference does at every interval,
+ * IV = dataYs[:, -1] (pbHomoReactor.py:3685).  iv_y_dev == NULL with k_first == 0 is pbr_solve_n2.  snaps_y_dev holds the
+ * tNo - k_first remaining interval ends: [N][tNo-k_first][nv2][zNo].  flags bit 0: restart the integrator (order 1, fresh
+ * initial step) at every interval exactly as the reference's per-interval solve_ivp calls do. */
+int pbr_solve_n2_resume(pbr_ctx* ctx, long N, int zNo, int tNo, int k_first, double period, const double* inst_par_dev,
+                        const double* iv_y_dev, int flags, double rtol, double atol, int max_steps, double* snaps_y_dev,
+                        int* status_dev, int* stats_dev, void* stream);
+
 /* K5b — sortResult5 + mole fractions (solResultAnalysis.py:252-301, pbHomoReactor.py:3655-3661):
  * scaled snapshots [N][tNo][nv2][zNo] -> dataYs [N][tNo][n_comp+1][zNo] = rows x_1..x_n, T [K] */
 int pbr_unscale_n2(pbr_ctx* ctx, long N, int tNo, int zNo, const double* inst_par_dev, const double* snaps_y_dev,
@@ -126,6 +138,10 @@ int pbr_unscale_n2(pbr_ctx* ctx, long N, int tNo, int zNo, const double* inst_pa
 int pbr_solve_n2_host(pbr_ctx* ctx, long N, int zNo, int tNo, double period, const double* inst_in_host, double rtol,
                       double atol, int max_steps, double* snaps_y_host, double* data_host, int* status_host,
                       int* stats_host);
+
+int pbr_solve_n2_host_resume(pbr_ctx* ctx, long N, int zNo, int tNo, int k_first, double period, const double* inst_in_host,
+                             const double* iv_y_host, int flags, double rtol, double atol, int max_steps, double* snaps_y_host,
+                             double* data_host, int* status_host, int* stats_host);
 
 /* FP64-pipe peak probe (DFMA streams) — roofline denominator the driver's MEASURED_PEAKS.json lacks. */
 int pbr_fp64_peak(pbr_ctx* ctx, int iters, double* tflops);

@@ -857,7 +857,12 @@ struct LuStore {            // receives Jacobian entries, stores the Newton matr
 #define PBR_MAX_FACTOR 10.0
 #define PBR_DROWS (PBR_MAXORD + 2)   // rows 0..order+2, but row MAXORD+2 would only feed an order increase past MAXORD
 
-enum { PBR_OK = 0, PBR_ERR_STEP_TOO_SMALL = 1, PBR_ERR_MAX_STEPS = 2, PBR_ERR_NONFINITE = 3, PBR_ERR_SINGULAR = 4 };
+enum { PBR_OK = 0, PBR_ERR_STEP_TOO_SMALL = 1, PBR_ERR_MAX_STEPS = 2, PBR_ERR_NONFINITE = 3, PBR_ERR_SINGULAR = 4, PBR_ERR_BAD_IV = 5 };
+#ifdef PBR_HOST
+#define PBR_NAN_VALUE ((double)NAN)
+#else
+#define PBR_NAN_VALUE (__longlong_as_double(0x7ff8000000000000ll))
+#endif
 
 // kappa = [0,-0.1850,-1/9,-0.0823,-0.0415,0]; gamma_k = sum_{j<=k} 1/j; alpha = (1-kappa)*gamma;
 // error_const = kappa*gamma + 1/(k+1)      (bdf.py:244-247).  Tables (constant bank), index = order 0..6.
@@ -1430,12 +1435,12 @@ struct N2Stats { int nsteps, nrej, nfev, nlu, nfail; };
 struct N2Carry { int order, n_equal, started; double h, pend, kappa; };
 
 PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, double t0, double t1,
-                            double rtol, double atol, int max_steps, N2Stats& stt, N2Carry& cy) {
+                            double rtol, double atol, int max_steps, N2Stats& stt, N2Carry& cy, bool restart = false) {
     const int zNo = ws.zNo;
     const double nTot = (double)(PBR_NV2*zNo);
     const double newton_tol = fmax(10.0*2.220446049250313e-16/rtol, fmin(0.03, sqrt(rtol)));
     const double span = t1 - t0;
-    const bool fresh_start = PBR_N2_RESTART || !cy.started;
+    const bool fresh_start = PBR_N2_RESTART || restart || !cy.started;
     // ---- initial step (scipy common.py:68-140): f0 = f(Y0), f1 = f(Y0 + h0 f0)
     double h = cy.h;
     if (fresh_start) {
@@ -1599,25 +1604,28 @@ PBR_DEV int pbr_n2_interval(const WarpCtx& w, const InstPar& p, const N2Ws& ws, 
 
 // Whole N2 run of one instance: IV (c0 everywhere, theta = 0, :3483-3497), tNo intervals of length period/tNo
 // (:3557-3558), snapshot of the scaled state at every interval end -> snaps[tNo][NV2][zNo].
+// `iv` != NULL: start from the saved scaled state iv[NV2][zNo] at interval k_first (the reference restarts from IV = dataYs[:, -1],
+// :3685); snaps then holds the tNo - k_first remaining interval ends.  flags bit 0: restart the integrator at every interval
+// as the reference does.  After a failure the remaining snapshots are NaN.
 PBR_DEV int pbr_n2_solve(const WarpCtx& w, const InstPar& p, const N2Ws& ws, int tNo, double period, double rtol, double atol,
-                         int max_steps, double* snaps, N2Stats& stt) {
+                         int max_steps, double* snaps, N2Stats& stt, const double* iv = 0, int k_first = 0, int flags = 0) {
     const int zNo = ws.zNo;
     stt.nsteps = stt.nrej = stt.nfev = stt.nlu = stt.nfail = 0;
     for (int z = w.lane; z < zNo; z += WarpCtx::NL) {
 #pragma unroll
-        for (int v = 0; v < PBR_NC; ++v) ws.D(0, v)[z] = p.c0[v];
-        if (!PBR_ISO) ws.D(0, PBR_ISO ? 0 : PBR_NC)[z] = 0.0;
+        for (int v = 0; v < PBR_NC; ++v) ws.D(0, v)[z] = iv ? iv[(long)v*zNo + z] : p.c0[v];
+        if (!PBR_ISO) ws.D(0, PBR_ISO ? 0 : PBR_NC)[z] = iv ? iv[(long)(PBR_ISO ? 0 : PBR_NC)*zNo + z] : 0.0;
     }
     int status = PBR_OK;
     N2Carry cy; cy.order = 1; cy.n_equal = 0; cy.started = 0; cy.h = 0.0; cy.pend = 1.0; cy.kappa = 1e300;
-    for (int k = 0; k < tNo && status == PBR_OK; ++k) {
+    for (int k = k_first; k < tNo; ++k) {
         const double t0 = (k == 0) ? 0.0 : period*((double)k/(double)tNo);          // np.linspace(0, opT, tNo+1)
         const double t1 = (k == tNo - 1) ? period : period*((double)(k + 1)/(double)tNo);
-        status = pbr_n2_interval(w, p, ws, t0, t1, rtol, atol, max_steps, stt, cy);
+        if (status == PBR_OK) status = pbr_n2_interval(w, p, ws, t0, t1, rtol, atol, max_steps, stt, cy, (flags & 1) != 0);
         w.sync();
         for (int z = w.lane; z < zNo; z += WarpCtx::NL)
 #pragma unroll
-            for (int v = 0; v < PBR_NV2; ++v) snaps[((long)k*PBR_NV2 + v)*zNo + z] = ws.D(0, v)[z];
+            for (int v = 0; v < PBR_NV2; ++v) snaps[((long)(k - k_first)*PBR_NV2 + v)*zNo + z] = (status == PBR_OK) ? ws.D(0, v)[z] : PBR_NAN_VALUE;
     }
     return status;
 }
@@ -1721,6 +1729,14 @@ pbr_k2_solve_n1(long N, const double* __restrict__ par, double rtol, double atol
     const int rc = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, D, LU, sink, st, live);
     if (!live) return;
     status[i] = rc;
+    if (rc != PBR_OK) {                                               // a failed instance must not look like a result: NaN rows
+        const double nan = PBR_NAN_VALUE;
+#pragma unroll
+        for (int v = 0; v < PBR_NV1; ++v) outlet_y[(long)v*N + i] = nan;
+        if (prof_y) for (int k = 0; k < n_out; ++k)
+#pragma unroll
+            for (int v = 0; v < PBR_NV1; ++v) prof_y[((long)k*PBR_NV1 + v)*N + i] = nan;
+    }
     if (stats) { stats[0*N + i] = st.nsteps; stats[1*N + i] = st.nrej + st.nfail; stats[2*N + i] = st.nfev; stats[3*N + i] = st.nlu; }
 }
 
@@ -1845,7 +1861,8 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
 // ---- K4: fused N2 solver. Persistent warps: warp g handles instances g, g+G, ... with its own scratch slab.
 extern "C" __global__ void __launch_bounds__(128) pbr_k4_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                   double rtol, double atol, int max_steps, double* __restrict__ work,
-                                                                  double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
+                                                                  double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
+                                                                  const double* __restrict__ iv, int k_first, int flags) {
     extern __shared__ double pbr_smem[];
     const long gw = ((long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     const long G = ((long)gridDim.x*blockDim.x) >> 5;
@@ -1855,7 +1872,8 @@ extern "C" __global__ void __launch_bounds__(128) pbr_k4_solve_n2(long N, int zN
     for (long inst = gw; inst < N; inst += G) {
         InstPar p; pbr_load_par(par, N, inst, p);
         N2Stats st;
-        const int rc = pbr_n2_solve(w, p, ws, tNo, period, rtol, atol, max_steps, snaps + inst*(long)tNo*PBR_NV2*zNo, st);
+        const int rc = pbr_n2_solve(w, p, ws, tNo, period, rtol, atol, max_steps, snaps + inst*(long)(tNo - k_first)*PBR_NV2*zNo, st,
+                                    iv ? iv + inst*(long)PBR_NV2*zNo : (const double*)0, k_first, flags);
         if (w.lane == 0) {
             status[inst] = rc;
             if (stats) { stats[0*N + inst] = st.nsteps; stats[1*N + inst] = st.nrej + st.nfail; stats[2*N + inst] = st.nfev; stats[3*N + inst] = st.nlu; }
@@ -2128,7 +2146,8 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
 template <bool D_GLOBAL, bool SCAN>
 __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                              double rtol, double atol, int max_steps, double* __restrict__ gwork,
-                                             double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
+                                             double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
+                                             const double* __restrict__ iv, int k_first, int flags) {
     extern __shared__ double pbr_smem[];
     const int NV = PBR_NX2;                                // integrated variables per node (extent coordinates when reduced)
     const int NO = PBR_NV2;                                // variables the error norms are taken over: [c, theta]
@@ -2149,6 +2168,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
         int nsteps = 0, nrejf = 0, nfev = 0, nlu = 0;
         int rc = PBR_OK;
         __syncthreads();
+        double iv_res = 0.0;
         if (act) {
 #pragma unroll
             for (int v = 0; v < NV; ++v) D[0*NV + v] = 0.0;                         // IV, :3483-3497: c = c0 (x = 0), theta = 0
@@ -2156,20 +2176,48 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
 #pragma unroll
             for (int v = 0; v < PBR_NC; ++v) D[0*NV + v] = p.c0[v];
 #endif
+            if (iv) {                                                               // resume from a saved state (:3685, IV = dataYs[:, -1])
+                const double* yi = iv + inst*(long)NO*zNo + z;
+                double yf[PBR_NV2], xs[PBR_NX2];
+#pragma unroll
+                for (int v = 0; v < NO; ++v) yf[v] = yi[(long)v*zNo];
+#if PBR_N2_REDUCED
+                // extents from the saved concentrations: x = (S S^T)^-1 S (c - c0); a state that is not of the form c0 + S^T x
+                // (it cannot come from this model started at the feed-filled bed) is refused with PBR_ERR_BAD_IV
+#pragma unroll
+                for (int j = 0; j < PBR_NR; ++j) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int i = 0; i < PBR_NC; ++i) a += PBR_SPINV[j][i]*(yf[i] - p.c0[i]);
+                    xs[j] = a;
+                }
+                if (!PBR_ISO) xs[NV - 1] = yf[NO - 1];
+                double back[PBR_NV2];
+                pbr_n2x_expand(xs, p, back);
+#pragma unroll
+                for (int i = 0; i < PBR_NC; ++i) { const double e = (back[i] - yf[i])*pbr_rcp(atol + rtol*fabs(yf[i])); iv_res += e*e; }
+#else
+#pragma unroll
+                for (int v = 0; v < NV; ++v) xs[v] = yf[v];
+#endif
+#pragma unroll
+                for (int v = 0; v < NV; ++v) D[0*NV + v] = xs[v];
+            }
         }
+        if (iv && PBR_N2_REDUCED) { if (!(cx.sum(iv_res) <= nTot)) rc = PBR_ERR_BAD_IV; }   // weighted RMS residual above one tolerance unit
         // BDF state carried across the snapshot times unless PBR_N2_RESTART (see pbr_n2_interval)
         int order = 1, n_equal = 0;
         double h = 0.0, pend = 1.0, kappa = 1e300;
         double sub[PBR_NX2];
 #pragma unroll
         for (int v = 0; v < NV; ++v) sub[v] = 0.0;
-        for (int kint = 0; kint < tNo && rc == PBR_OK; ++kint) {
+        for (int kint = k_first; kint < tNo; ++kint) {
             const double t0 = (kint == 0) ? 0.0 : period*((double)kint/(double)tNo);  // np.linspace(0, opT, tNo+1)
             const double t1 = (kint == tNo - 1) ? period : period*((double)(kint + 1)/(double)tNo);
             const double span = t1 - t0;
             double y[PBR_NX2], d[PBR_NX2], f[PBR_NX2], b[PBR_NX2];
-            // ---- initial step (scipy common.py:68-140); with PBR_N2_RESTART again at every interval (:3589-3685)
-            if (PBR_N2_RESTART || kint == 0) {
+            // ---- initial step (scipy common.py:68-140); with PBR_N2_RESTART / flags bit 0 again at every interval (:3589-3685)
+            if (rc == PBR_OK && (PBR_N2_RESTART || (flags & 1) || kint == k_first)) {
                 double h0 = 0.0, d1 = 0.0, f0[PBR_NX2];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) { y[v] = act ? D[0*NV + v] : 1.0; sub[v] = 0.0; f[v] = 0.0; f0[v] = 0.0; }
@@ -2343,13 +2391,14 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 }
             }
             __syncthreads();
-            if (act) {
+            if (act) {                                     // snapshot of this interval's end; NaN once the instance has failed
                 double xs[PBR_NX2], yf[PBR_NV2];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) xs[v] = D[0*NV + v];
                 pbr_n2x_expand(xs, p, yf);
 #pragma unroll
-                for (int v = 0; v < NO; ++v) snaps[(inst*tNo + kint)*(long)NO*zNo + (long)v*zNo + z] = yf[v];
+                for (int v = 0; v < NO; ++v)
+                    snaps[(inst*(tNo - k_first) + (kint - k_first))*(long)NO*zNo + (long)v*zNo + z] = (rc == PBR_OK) ? yf[v] : PBR_NAN_VALUE;
             }
         }
         if (threadIdx.x == 0) {
@@ -2365,29 +2414,33 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
 #endif
 extern "C" __global__ void __launch_bounds__(256, PBR_K4B_MINBLOCKS) pbr_k4b_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                    double rtol, double atol, int max_steps,
-                                                                   double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
-    pbr_k4b_body<false, PBR_K4B_MARCH_SCAN != 0>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats);
+                                                                   double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
+                                                            const double* __restrict__ iv, int k_first, int flags) {
+    pbr_k4b_body<false, PBR_K4B_MARCH_SCAN != 0>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats, iv, k_first, flags);
 }
 
 // the same kernel with the log-depth march: grids of more than PBR_K4B_SCAN_FROM nodes (chosen by the launcher)
 extern "C" __global__ void __launch_bounds__(256, PBR_K4B_MINBLOCKS) pbr_k4bs_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                     double rtol, double atol, int max_steps,
-                                                                    double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
-    pbr_k4b_body<false, true>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats);
+                                                                    double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
+                                                            const double* __restrict__ iv, int k_first, int flags) {
+    pbr_k4b_body<false, true>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats, iv, k_first, flags);
 }
 
 // K4d: the whole state on chip for grids of 257..512 nodes (59*zNo doubles = 189 KB at zNo = 400), scan march, one block per SM.
 // The launcher prefers it to pbr_k4c_solve_n2 whenever the state fits (170 vs 190 ms per 1,184 solves at zNo = 400).
 extern "C" __global__ void __launch_bounds__(512) pbr_k4d_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                    double rtol, double atol, int max_steps,
-                                                                   double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
-    pbr_k4b_body<false, true>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats);
+                                                                   double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
+                                                            const double* __restrict__ iv, int k_first, int flags) {
+    pbr_k4b_body<false, true>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats, iv, k_first, flags);
 }
 
 extern "C" __global__ void __launch_bounds__(512) pbr_k4c_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                    double rtol, double atol, int max_steps, double* __restrict__ gwork,
-                                                                   double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats) {
-    pbr_k4b_body<true, PBR_K4C_MARCH_SCAN != 0>(N, zNo, tNo, period, par, rtol, atol, max_steps, gwork, snaps, status, stats);
+                                                                   double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
+                                                                   const double* __restrict__ iv, int k_first, int flags) {
+    pbr_k4b_body<true, PBR_K4C_MARCH_SCAN != 0>(N, zNo, tNo, period, par, rtol, atol, max_steps, gwork, snaps, status, stats, iv, k_first, flags);
 }
 
 #endif  // !PBR_HOST || PBR_HOST_SIMT

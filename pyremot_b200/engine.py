@@ -60,6 +60,8 @@ def lib():
         "pbr_unscale_n1": (i, [vp, l, i, dp, dp, dp, vp]),
         "pbr_solve_n1_host": (i, [vp, l, dp, d, d, i, i, dp, dp, ip, ip]),
         "pbr_solve_n2": (i, [vp, l, i, i, d, dp, d, d, i, dp, ip, ip, vp]),
+        "pbr_solve_n2_resume": (i, [vp, l, i, i, i, d, dp, dp, i, d, d, i, dp, ip, ip, vp]),
+        "pbr_solve_n2_host_resume": (i, [vp, l, i, i, i, d, dp, dp, i, d, d, i, dp, dp, ip, ip]),
         "pbr_unscale_n2": (i, [vp, l, i, i, dp, dp, dp, vp]),
         "pbr_solve_n2_host": (i, [vp, l, i, i, d, dp, d, d, i, dp, dp, ip, ip]),
         "pbr_fp64_peak": (i, [vp, i, C.POINTER(d)]),
@@ -74,7 +76,8 @@ def lib():
 
 EXPORTS = ("pbr_create pbr_destroy pbr_last_error pbr_version pbr_set_species pbr_load_rates pbr_model_dims pbr_n1_layout "
            "pbr_model_source pbr_model_cubin pbr_kernel_attr pbr_prolog pbr_rhs_n1 pbr_jac_n1 pbr_rhs_n2 pbr_solve_n1 "
-           "pbr_unscale_n1 pbr_solve_n1_host pbr_solve_n2 pbr_unscale_n2 pbr_solve_n2_host pbr_fp64_peak pbr_launch_count").split()
+           "pbr_unscale_n1 pbr_solve_n1_host pbr_solve_n2 pbr_solve_n2_resume pbr_unscale_n2 pbr_solve_n2_host pbr_solve_n2_host_resume "
+           "pbr_fp64_peak pbr_launch_count").split()
 
 
 # ----------------------------------------------------------------------------- reaction parsing
@@ -188,10 +191,9 @@ class Model:
         self._check(lib().pbr_kernel_attr(self._ctx, name.encode(), C.byref(r), C.byref(s), C.byref(l)))
         return {"regs": r.value, "static_smem": s.value, "local_bytes": l.value}
 
-    @staticmethod
-    def _stream():
+    def _stream(self):
         import torch
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _dev(self):
         import torch
@@ -295,16 +297,26 @@ class Model:
             status.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p)))
         return {"dataYs": prof, "outlet": outlet, "status": status, "stats": stats}
 
-    def solve_n2(self, par, zNo, tNo, period, rtol=1e-9, atol=1e-13, max_steps=0, stats=True):
-        """K4 on device tensors. Returns dict(snaps_y [N,tNo,nv2,zNo] scaled, status [N], stats [4,N])."""
+    def solve_n2(self, par, zNo, tNo, period, rtol=1e-9, atol=1e-13, max_steps=0, stats=True, iv=None, k_first=0,
+                 restart_every_interval=False):
+        """K4 on device tensors. Returns dict(snaps_y [N,tNo-k_first,nv2,zNo] scaled, status [N], stats [4,N]).
+
+        ``iv`` [N,nv2,zNo] (scaled state, e.g. ``snaps_y[:, k_first-1]`` of an earlier run) resumes at interval ``k_first``
+        — the reference's own restart, ``IV = dataYs[:, -1]`` (`pbHomoReactor.py:3685`).  ``restart_every_interval``
+        reproduces the reference's per-interval ``solve_ivp`` restarts (order 1, fresh initial step)."""
         import torch
         N = par.shape[1]
         dev = par.device
-        snaps = torch.empty((N, tNo, self.nv2, zNo), dtype=torch.float64, device=dev)
+        assert par.device.index == self.device, "tensor lives on another GPU than this model"
+        if iv is not None:
+            assert iv.shape == (N, self.nv2, zNo) and iv.is_contiguous() and iv.dtype == torch.float64 and iv.device == dev
+        snaps = torch.empty((N, tNo - k_first, self.nv2, zNo), dtype=torch.float64, device=dev)
         status = torch.empty((N,), dtype=torch.int32, device=dev)
         st = torch.empty((4, N), dtype=torch.int32, device=dev) if stats else None
-        self._check(lib().pbr_solve_n2(self._ctx, N, zNo, tNo, float(period), par.data_ptr(), rtol, atol, max_steps,
-                                       snaps.data_ptr(), status.data_ptr(), st.data_ptr() if stats else None, self._stream()))
+        self._check(lib().pbr_solve_n2_resume(self._ctx, N, zNo, tNo, int(k_first), float(period), par.data_ptr(),
+                                              iv.data_ptr() if iv is not None else None, 1 if restart_every_interval else 0,
+                                              rtol, atol, max_steps, snaps.data_ptr(), status.data_ptr(),
+                                              st.data_ptr() if stats else None, self._stream()))
         return {"snaps_y": snaps, "status": status, "stats": st}
 
     def unscale_n2(self, par, snaps_y):
@@ -315,16 +327,23 @@ class Model:
         self._check(lib().pbr_unscale_n2(self._ctx, N, tNo, zNo, par.data_ptr(), snaps_y.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
-    def solve_n2_host(self, inst_in, zNo, tNo, period, rtol=1e-9, atol=1e-13, max_steps=0, scaled=True):
-        """Whole N2 path through the host-buffer C-ABI call. Returns dict(dataYs [N,tNo,n+1,zNo], snaps_y, status, stats)."""
+    def solve_n2_host(self, inst_in, zNo, tNo, period, rtol=1e-9, atol=1e-13, max_steps=0, scaled=True, iv=None, k_first=0,
+                      restart_every_interval=False):
+        """Whole N2 path through the host-buffer C-ABI call. Returns dict(dataYs [N,tNo-k_first,n+1,zNo], snaps_y, status, stats).
+        ``iv`` / ``k_first``: resume from a saved scaled state (see ``solve_n2``)."""
         inst_in = np.ascontiguousarray(inst_in, dtype=np.float64)
         N = inst_in.shape[0]
-        data = np.empty((N, tNo, self.n + 1, zNo), dtype=np.float64)
-        snaps = np.empty((N, tNo, self.nv2, zNo), dtype=np.float64) if scaled else None
+        nt = tNo - int(k_first)
+        data = np.empty((N, nt, self.n + 1, zNo), dtype=np.float64)
+        snaps = np.empty((N, nt, self.nv2, zNo), dtype=np.float64) if scaled else None
         status = np.empty((N,), dtype=np.int32)
         stats = np.empty((4, N), dtype=np.int32)
-        self._check(lib().pbr_solve_n2_host(
-            self._ctx, N, zNo, tNo, float(period), inst_in.ctypes.data_as(C.c_void_p), rtol, atol, max_steps,
+        if iv is not None:
+            iv = np.ascontiguousarray(iv, dtype=np.float64)
+            assert iv.shape == (N, self.nv2, zNo)
+        self._check(lib().pbr_solve_n2_host_resume(
+            self._ctx, N, zNo, tNo, int(k_first), float(period), inst_in.ctypes.data_as(C.c_void_p),
+            iv.ctypes.data_as(C.c_void_p) if iv is not None else None, 1 if restart_every_interval else 0, rtol, atol, max_steps,
             snaps.ctypes.data_as(C.c_void_p) if scaled else None, data.ctypes.data_as(C.c_void_p),
             status.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p)))
         return {"dataYs": data, "snaps_y": snaps, "status": status, "stats": stats}

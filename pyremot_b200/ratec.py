@@ -380,6 +380,12 @@ def _eval_nodes(g, inputs):
 
 
 # ----------------------------------------------------------------------------- symbolic forward-mode derivatives
+def _union(da, db):
+    """Keys of both partial maps in a fixed order.  (A set of tuples that contain strings iterates in an order that depends
+    on PYTHONHASHSEED; node ids, the emitted text and therefore the cubin-cache key would differ between processes.)"""
+    return sorted(set(da) | set(db))
+
+
 def _derivatives(g, outs, n_comp):
     """For every output, partials w.r.t. T, P, X_i, C_i as node ids in ``g`` (sparse: missing = 0)."""
     LN10 = math.log(10.0)
@@ -396,13 +402,13 @@ def _derivatives(g, outs, n_comp):
                 d[(n[1], n[2])] = g.const(1.0)
         elif op in ("add", "sub"):
             da, db = dmap[n[1]], dmap[n[2]]
-            for k in set(da) | set(db):
+            for k in _union(da, db):
                 a = da.get(k, g.const(0.0))
                 b = db.get(k, g.const(0.0))
                 d[k] = g.add(a, b) if op == "add" else g.sub(a, b)
         elif op == "mul":
             da, db = dmap[n[1]], dmap[n[2]]
-            for k in set(da) | set(db):
+            for k in _union(da, db):
                 t = g.const(0.0)
                 if k in da:
                     t = g.add(t, g.mul(da[k], n[2]))
@@ -436,7 +442,7 @@ def _derivatives(g, outs, n_comp):
                 d = {k: g.mul(g.mul(g.const(float(e)), pm1), v) for k, v in dmap[n[1]].items()}
         elif op == "pow":
             da, db = dmap[n[1]], dmap[n[2]]
-            for k in set(da) | set(db):
+            for k in _union(da, db):
                 t = g.const(0.0)
                 if k in da:   # v * u^(v-1) * u'
                     t = g.add(t, g.mul(g.mul(n[2], g.pow(n[1], g.sub(n[2], g.const(1.0)))), da[k]))

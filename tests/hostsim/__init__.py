@@ -40,16 +40,20 @@ class SimtSim:
         self.L = _build(model.source, "simt_driver.cpp", extra=("simt.h",))
         self.nv2 = model.nv2
 
-    def solve_n2(self, kernel, par, zNo, tNo, period, rtol=1e-9, atol=1e-13, max_steps=50000, grid=None):
+    def solve_n2(self, kernel, par, zNo, tNo, period, rtol=1e-9, atol=1e-13, max_steps=50000, grid=None, iv=None, k_first=0,
+                 flags=0):
         par = np.ascontiguousarray(par, dtype=np.float64)
         N = par.shape[1]
-        snaps = np.zeros((N, tNo, self.nv2, zNo))
+        snaps = np.zeros((N, tNo - k_first, self.nv2, zNo))
+        if iv is not None:
+            iv = np.ascontiguousarray(iv, dtype=np.float64)
+            assert iv.shape == (N, self.nv2, zNo)
         status = np.zeros(N, dtype=np.int32)
         stats = np.zeros((4, N), dtype=np.int32)
         p = HostSim._p
         rc = self.L.hs_simt_solve_n2(self.KERNELS[kernel], C.c_long(N), C.c_int(zNo), C.c_int(tNo), C.c_double(period), p(par),
                                      C.c_double(rtol), C.c_double(atol), C.c_int(max_steps), C.c_int(grid or N), p(snaps),
-                                     p(status), p(stats))
+                                     p(status), p(stats), p(iv) if iv is not None else None, C.c_int(k_first), C.c_int(flags))
         assert rc == 0, rc
         return snaps, status, stats
 

@@ -29,19 +29,20 @@ void hs_simt_eval(int zNo, const double* par, const double* x, double* f) {
 }
 
 // kernel: 0 = pbr_k4b_solve_n2, 1 = pbr_k4bs_solve_n2, 2 = pbr_k4c_solve_n2, 3 = pbr_k4d_solve_n2.  par [KPAR][N]; snaps [N][tNo][NV2][zNo];
-// stats [4][N].  grid < N exercises the kernels' loop over instances.
+// stats [4][N].  grid < N exercises the kernels' loop over instances.  iv (or NULL) [N][NV2][zNo], k_first, flags: resume arguments
+// (snaps then holds tNo - k_first interval ends per instance).
 int hs_simt_solve_n2(int kernel, long N, int zNo, int tNo, double period, const double* par, double rtol, double atol,
-                     int max_steps, int grid, double* snaps, int* status, int* stats) {
+                     int max_steps, int grid, double* snaps, int* status, int* stats, const double* iv, int k_first, int flags) {
     const unsigned block = (unsigned)((zNo + 31)/32*32);
     if ((size_t)(7*PBR_NX2 + PBR_NX2*PBR_NX2 + 2*PBR_NX2 + PBR_NV2)*zNo + 400 > sizeof(pbr_smem)/sizeof(double)) return -1;
     if (grid < 1) grid = 1;
     std::vector<double> gwork((size_t)grid*PBR_DROWS*PBR_NX2*zNo);
     double* gw = gwork.data();
     simt::launch((unsigned)grid, block, [&]() {
-        if (kernel == 0) pbr_k4b_solve_n2(N, zNo, tNo, period, par, rtol, atol, max_steps, snaps, status, stats);
-        else if (kernel == 1) pbr_k4bs_solve_n2(N, zNo, tNo, period, par, rtol, atol, max_steps, snaps, status, stats);
-        else if (kernel == 3) pbr_k4d_solve_n2(N, zNo, tNo, period, par, rtol, atol, max_steps, snaps, status, stats);
-        else pbr_k4c_solve_n2(N, zNo, tNo, period, par, rtol, atol, max_steps, gw, snaps, status, stats);
+        if (kernel == 0) pbr_k4b_solve_n2(N, zNo, tNo, period, par, rtol, atol, max_steps, snaps, status, stats, iv, k_first, flags);
+        else if (kernel == 1) pbr_k4bs_solve_n2(N, zNo, tNo, period, par, rtol, atol, max_steps, snaps, status, stats, iv, k_first, flags);
+        else if (kernel == 3) pbr_k4d_solve_n2(N, zNo, tNo, period, par, rtol, atol, max_steps, snaps, status, stats, iv, k_first, flags);
+        else pbr_k4c_solve_n2(N, zNo, tNo, period, par, rtol, atol, max_steps, gw, snaps, status, stats, iv, k_first, flags);
     });
     return 0;
 }

@@ -219,3 +219,24 @@ def test_block_kernels_multi_warp_ragged_grid_and_instance_loop(defines):
         snaps, status, stats = sim.solve_n2(kernel, par, zNo, tNo, period, grid=1)
         assert (status == 0).all() and (stats[0] > 20).all()
         assert relerr(snaps, ref, floor=1e-9) < 1e-7
+
+
+def test_n2_resume_from_a_saved_snapshot_on_the_simt_emulator():
+    """pbr_solve_n2_resume semantics (reference restart `pbHomoReactor.py:3685`, IV = dataYs[:, -1]) on the block
+    kernel, CPU-side: intervals 0..1 then a resume at interval 2 from the saved snapshot must reproduce the uninterrupted 5-interval
+    run -- to rounding when the integrator restarts at every interval (flags bit 0, the reference's behaviour), to integration
+    tolerance otherwise; an off-manifold state is refused with PBR_INST_BAD_IV and NaN snapshots."""
+    mi, m, hs, sim = _simt_case(lambda: cases.readme_case("N2"))
+    rows = cases.ensemble_rows(2)
+    par = hs.prolog(m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}))
+    zNo, tNo, period, k = 40, 5, 0.05, 2
+    for flags, tol in ((1, 1e-11), (0, 1e-6)):
+        full, st, _ = sim.solve_n2("pbr_k4b_solve_n2", par, zNo, tNo, period, flags=flags)
+        assert (st == 0).all()
+        tail, st2, _ = sim.solve_n2("pbr_k4b_solve_n2", par, zNo, tNo, period, iv=full[:, k - 1], k_first=k, flags=flags)
+        assert (st2 == 0).all() and tail.shape == (2, tNo - k, m.nv2, zNo)
+        assert relerr(tail, full[:, k:], floor=1e-9) < tol, (flags, relerr(tail, full[:, k:], floor=1e-9))
+    bad = full[:, k - 1].copy()
+    bad[1, 0] *= 1.001                                   # H2 alone moved: not reachable through the three reactions
+    tail, st3, _ = sim.solve_n2("pbr_k4b_solve_n2", par, zNo, tNo, period, iv=bad, k_first=k)
+    assert st3[0] == 0 and st3[1] == 5 and np.isnan(tail[1]).all() and np.isfinite(tail[0]).all()

@@ -87,3 +87,17 @@ def test_reference_executor_semantics():
     # general pow, log with base, math constants
     cr = ratec.compile_rates({"VARS": {"n": 1.7}, "RATES": {"r": lambda x: math.pow(x["T"], x["n"]) + math.pi*x["P"]**-0.5 + 2**x["MoFri"][0]}}, 2)
     assert np.isclose(cr.evaluate(500.0, 2e5, [0.3, 0.7], [1, 1])[0], 500.0**1.7 + math.pi*(2e5)**-0.5 + 2**0.3, rtol=1e-14)
+
+
+def test_emitted_program_does_not_depend_on_the_hash_seed():
+    """The cubin cache is keyed by the program text: it must be the same in every process (PYTHONHASHSEED)."""
+    import subprocess
+    import sys
+    code = ("from pyremot_b200 import ratec, cases\n"
+            "cr = ratec.compile_rates(cases.readme_case('N1', theta_as_vars=True)['reaction-rates'], 6, params=tuple(cases.MEOH_DME_THETA))\n"
+            "print(cr.key)")
+    keys = set()
+    for seed in ("1", "2", "77"):
+        env = dict(os.environ, PYTHONHASHSEED=seed, PYTHONPATH=ROOT)
+        keys.add(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip())
+    assert len(keys) == 1, keys
