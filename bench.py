@@ -8,8 +8,12 @@ One "step" = one pass of the hot path over one batch: K0 prolog -> K2 fused BDF 
 outlet rows, for every reactor of the rank's shard (weak scaling: 65,536 reactors per GPU; N>1 adds the single
 NCCL all-gather of outlet rows).  `value` times the step with inputs resident in HBM; `e2e` times the
 host-buffer C-ABI call (pinned host input table -> H2D -> kernels -> D2H of outlet/status).  `cpu_baseline` /
-`--impl reference` time the CPU path (oracle port of the reference: SciPy LSODA at the reference's default
-tolerances on the NumPy restatement of its RHS, one process per host core) on a bounded sample of the same rows.
+`--impl reference` time the reference's own CPU path on a bounded sample of the same rows: the UNMODIFIED
+`PyREMOT.rmtExe` (oracle/_ref, placed there by oracle/build_ref.py; kind "reference"), one call per ensemble member,
+one process per host core (fork) -- BASELINE.md section 3.  If the copy is absent the oracle port is timed instead
+(SciPy LSODA at the reference's default tolerances on the NumPy restatement of its RHS; kind "port").
+Also emitted by default: the dynamic model (N2) at BASELINE configs[2] (4,096 x 100 nodes) and a configs[3] slice
+(1,184 x 400 nodes) with their own roofline and CPU figures, and the end-to-end rate with full 101-point profiles.
 """
 from __future__ import annotations
 
@@ -44,19 +48,111 @@ def _cpu_worker(args):
     return hi - lo, int(nfev.sum())
 
 
-def cpu_path(n_inst, cores=None, tol=None):
-    """Solve rows [0, n_inst) with the oracle port on `cores` processes; returns (solves/s, seconds, total nfev)."""
+def _ref_worker(args):
+    """The UNMODIFIED reference: one `PyREMOT.rmtExe(modelInput)` call per ensemble member (`PyREMOT/rmt.py:21-80`);
+    the worker rebuilds modelInput (incl. the rate lambdas, which cannot be pickled) from the numeric row."""
+    lo, hi, _ = args
+    from oracle import ref_driver as ref
+    from pyremot_b200 import cases
+    rows = cases.ensemble_rows(hi - lo, offset=lo)
+    for k in range(hi - lo):
+        mi = cases.readme_case("N1", T=float(rows["T"][k]), P=float(rows["P"][k]), conc=[float(c) for c in rows["conc"][k]],
+                               Tm=float(rows["T"][k]))
+        res, _ = ref.run(mi)
+        assert res["resModel"][0]["successStatus"]
+    return hi - lo, 0
+
+
+def reference_available():
+    from oracle import ref_driver as ref
+    return ref.available()
+
+
+def cpu_path(n_inst, cores=None, tol=None, kind="port"):
+    """Solve rows [0, n_inst) on `cores` processes with the reference itself (kind "reference") or the oracle port;
+    returns (solves/s, seconds, total nfev)."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
+    worker = _ref_worker if kind == "reference" else _cpu_worker
     per = max(1, n_inst // (cores*2))
     chunks = [(lo, min(lo + per, n_inst), tol) for lo in range(0, n_inst, per)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(0, 1, tol)]*cores)      # warm the workers (imports) outside the timed region
+        pool.map(worker, [(0, 1, tol)]*cores)           # warm the workers (imports) outside the timed region
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, chunks, chunksize=1)
+        res = pool.map(worker, chunks, chunksize=1)
         dt = time.perf_counter() - t0
     return n_inst/dt, dt, sum(r[1] for r in res)
+
+
+def _n2_port_worker(i):
+    from oracle import pbr_oracle as O
+    from pyremot_b200 import cases
+    rows = cases.ensemble_rows(1, offset=i)
+    ens = O.Ensemble(cases.readme_case("N2"), {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]})
+    _, _, nfev = O.solve_n2(ens, zNo=20, tNo=5, method="LSODA")
+    return int(nfev[0])
+
+
+def cpu_n2(cores):
+    """CPU figures for the dynamic model: RHS evaluations per second of the reference's own
+    `modelEquationN2` (one core, zNo = 20 / 100 / 400; a full reference solve at zNo = 100 is ~17 min per instance), and
+    whole solves per second of the oracle port at zNo = 20 (SciPy LSODA, the reference's defaults), one instance per core."""
+    import multiprocessing as mp
+    out = {"cores": cores}
+    if reference_available():
+        from oracle import ref_driver as ref
+        out["rhs_kind"] = "reference"
+        out["rhs_evals_per_s_per_core"] = {f"zNo{z}": ref_rhs_n2_rate(ref, z, n) for z, n in ((20, 20), (100, 8), (400, 3))}
+    else:
+        out["rhs_kind"] = "port"
+        out["rhs_evals_per_s_per_core"] = {"zNo100": cpu_rhs_rates()["n2_z100"]}
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        nfev = pool.map(_n2_port_worker, range(cores), chunksize=1)
+        dt = time.perf_counter() - t0
+    out["solve_zNo20"] = {"kind": "port", "value": cores/dt, "unit": "solves/s", "seconds": dt, "mean_nfev": float(np.mean(nfev)),
+                          "sample": f"{cores} instances (rows 0..{cores-1}), zNo=20, tNo=5, period 0.5 s, SciPy LSODA rtol 1e-3/atol 1e-6"}
+    r20 = out["rhs_evals_per_s_per_core"].get("zNo20")
+    if r20:
+        out["solve_zNo20_reference_derived"] = {
+            "value": cores*r20/float(np.mean(nfev)), "unit": "solves/s",
+            "note": "derived, not timed: cores x reference RHS evals/s at zNo=20 / RHS evals per solve counted on the port"}
+    return out
+
+
+def ref_rhs_n2_rate(ref, zNo, n):
+    """Evaluations per second of the reference's modelEquationN2 at the README N2 case's initial state (one core)."""
+    from pyremot_b200 import cases
+    PyREMOT, H, setting = ref.load()
+    cap = {}
+
+    class _Stop(Exception):
+        pass
+
+    orig = H.PackedBedHomoReactorClass.modelEquationN2
+
+    def spy(t, y, p):
+        cap["y"], cap["p"] = np.array(y), p
+        raise _Stop
+
+    old = setting["N2"]["zNo"]
+    H.PackedBedHomoReactorClass.modelEquationN2 = spy
+    setting["N2"]["zNo"] = zNo
+    try:
+        with ref.quiet():
+            PyREMOT.rmtExe(cases.readme_case("N2"))
+    except BaseException:
+        pass
+    finally:
+        H.PackedBedHomoReactorClass.modelEquationN2 = orig
+        setting["N2"]["zNo"] = old
+    ref.rhs("N2", cap["y"], cap["p"])
+    t0 = time.perf_counter()
+    for _ in range(n):
+        ref.rhs("N2", cap["y"], cap["p"])
+    return n/(time.perf_counter() - t0)
 
 
 def cpu_rhs_rates():
@@ -83,22 +179,25 @@ def run_reference(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = max(8*cores, 64)
-    # bounded sample per step: ~0.35 s per solve per core
+    kind = "reference" if reference_available() else "port"
+    # bounded sample per step: ~0.5-0.8 s per solve per core with the reference (0.35 s with the port)
+    n = max(4*cores, 32) if kind == "reference" else max(8*cores, 64)
     times = []
     for s in range(a.warmup + a.steps):
-        v, dt, nfev = cpu_path(n, cores)
+        v, dt, nfev = cpu_path(n, cores, kind=kind)
         if s >= a.warmup:
             times.append(dt)
     total = sum(times)
     value = n*len(times)/total
-    sample = f"rows 0..{n-1} of the seeded config-2 table per step, SciPy LSODA rtol 1e-3/atol 1e-6 (the reference's defaults), {cores} processes"
+    what = ("the unmodified PyREMOT.rmtExe (copy of the reference package under oracle/_ref), one call per member, ivp='default' (LSODA rtol 1e-3/atol 1e-6)" if kind == "reference"
+            else "oracle port: SciPy LSODA rtol 1e-3/atol 1e-6 (the reference's defaults) on the NumPy RHS restatement")
+    sample = f"rows 0..{n-1} of the seeded config-2 table per step, {what}, {cores} processes"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3*total/len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample_per_step": n},
-        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -175,6 +274,28 @@ def algorithmic_flops(model, stats):
     # evaluations are the verification iterations and the initial-step probes; one triangular solve per Newton iteration
     flops = (nfev - nlu)*rhs + nfev*solve + nlu*(jac + lu) + nlu*step
     return flops, {"rhs": rhs, "jac": jac, "lu": lu, "solve": solve, "step": step}
+
+
+def algorithmic_flops_n2(model, stats, zNo):
+    """Algorithmic FP64 operation count of one N2 solver launch (block kernels, extent coordinates) from the per-instance
+    counters: per node and step attempt one analytic node Jacobian (which yields f as well), one nx x nx inverse
+    (Gauss-Jordan, 2 nx^3), one Newton solve (g = Ainv b and the march, 4 nx^2 + 2 nx) and the step algebra (predictor, psi,
+    history update, weights, norms, the affine pressure scan); the other nfev - nlu evaluations are plain RHS evaluations
+    followed by a solve.  Hand counts of pbr_n2x_node / pbr_k4b_body in csrc/pbr_device.cuh; same conventions as N1."""
+    n, R = model.n, model.n_rxn
+    reduced = R < n
+    nx = (R if reduced else n) + (0 if model.iso else 1)
+    ops_r, ops_rj = model.rates.op_counts()
+    base = 16*n + 14*R + 30
+    rhs = ops_r + base
+    cols = R*(8*R + 6*n + 24) if reduced else n*(3*R + 3*n + 20)
+    jac = ops_rj + base + 2*R*n + cols + (9*R + 9*n + 24)
+    inv = 2*nx**3
+    solve = 4*nx*nx + 2*nx
+    step = 32*nx + 14*model.nv2 + 20
+    nsteps, nrej, nfev, nlu = [float(x) for x in stats.sum(axis=1)]
+    per_node = (nfev - nlu)*(rhs + solve) + nlu*(jac + inv + solve + step)
+    return per_node*zNo, {"rhs": rhs, "jac": jac, "inverse": inv, "solve": solve, "step": step}
 
 
 def run_gpu(a):
@@ -273,13 +394,26 @@ def run_gpu(a):
             pass
         fp64_peak = model.fp64_peak()
         flops, per_unit = algorithmic_flops(model, stats)
+        # second convention: without the per-attempt analytic Jacobian (RHS + LU + solves + step algebra only)
+        flops_nojac = flops - float(stats[3].sum())*(per_unit["jac"] - per_unit["rhs"])
         achieved = flops/t_k2/1e12
+        k2_traffic, k2_traffic_src = traffic_record("pbr_k2_solve_n1")
         # secondary: standalone N2 RHS kernel (HBM-bound side of the path), zNo=100, inputs larger than L2
         rhs = bench_rhs_n2(model, mi, peaks)
         cores = os.cpu_count() or 1
-        n_cpu = max(32*cores, 256)                      # ~0.35 s per solve per core -> 10-20 s of CPU work
+        # dynamic model under the same clock: BASELINE configs[2] whole, and one GPU's worth of 8 waves of the configs[3] grid
+        n2c3 = bench_n2(model, 4096, 100, "N2 dynamic model, 100 nodes, 4096 instances, start-up transient (BASELINE configs[2])",
+                        "pbr_k4b_solve_n2", fp64_peak)
+        n2c4 = bench_n2(model, 1184, 400, "N2 dynamic model, 400 nodes, 1184-instance slice (8 per SM) of BASELINE configs[3]",
+                        "pbr_k4d_solve_n2", fp64_peak)
+        if world == 1:
+            n2c3["cpu_baseline"] = cpu_n2(cores)
+        e2e_prof = bench_e2e_profile(model, tab_h, a.steps)
+        kind = "reference" if reference_available() else "port"
+        n_cpu = max(16*cores, 128)                      # ~0.3-0.8 s per solve per core -> 5-15 s of CPU work per leg
         # the CPU path is timed at N = 1 only (at N > 1 the other ranks would sit in the final barrier for its duration)
-        cpu_v, cpu_dt = (cpu_path(n_cpu, cores)[:2] if world == 1 else (None, None))
+        cpu_v, cpu_dt = (cpu_path(n_cpu, cores, kind=kind)[:2] if world == 1 else (None, None))
+        port_v = cpu_path(n_cpu, cores, kind="port")[0] if (world == 1 and kind == "reference") else None
         line = {
             "metric": METRIC, "value": world*N*a.steps/t_dev, "unit": "solves/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": 1e3*t_dev/a.steps, "higher_is_better": True, "scaling": "weak",
@@ -292,20 +426,23 @@ def run_gpu(a):
             "clocks": clk.summary(),
             "roofline": {"kernel": "pbr_k2_solve_n1", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved/fp64_peak if fp64_peak else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size, ncu --set full
-                         # (profiles/r1m_k2_final_N65536.txt): 11.10 MB read + 1.3 KB written (the 4.2 MB of outlet rows are
-                         # still in L2 when the kernel ends); algorithmic: 11.5 MB of per-reactor constants in, 4.2 MB out
-                         "traffic": 11.10e6, "traffic_unit": "B/launch (ncu, profiles/r1m_k2_final_N65536.txt)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size from the committed
+                         # `ncu --set full` record (algorithmic: 11.5 MB of per-reactor constants in, 4.2 MB of outlet rows out)
+                         "traffic": k2_traffic, "traffic_unit": f"B/launch (ncu, {k2_traffic_src})" if k2_traffic else None,
+                         "frac_without_jacobian": (flops_nojac/t_k2/1e12)/fp64_peak if fp64_peak else None,
                          "peak_source": "DFMA probe pbr_k_dfma_peak measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                          "kernel_ms": 1e3*t_k2, "algorithmic_flops_per_launch": flops, "flops_per_unit": per_unit,
                          "mean_steps": float(stats[0].mean()), "mean_nfev": float(stats[2].mean()), "mean_nlu": float(stats[3].mean()),
                          "max_over_mean_nfev": float(stats[2].max()/stats[2].mean())},
             "rhs_n2_roofline": rhs,
-            **({"n2_config3": bench_n2_config3(model)} if a.extras else {}),
+            "n2_config3": n2c3, "n2_config4_slice": n2c4, "e2e_profile": e2e_prof,
             "cpu_baseline": None if cpu_v is None else {
-                "value": cpu_v, "unit": "solves/s", "cores": cores, "kind": "port", "rhs_evals_per_s_per_core": cpu_rhs_rates(),
-                "sample": f"rows 0..{n_cpu-1} of the same table, SciPy LSODA at the reference's default rtol 1e-3/atol 1e-6 "
-                          f"on the NumPy RHS restatement, {cores} processes, {cpu_dt:.1f} s"},
+                "value": cpu_v, "unit": "solves/s", "cores": cores, "kind": kind, "port_value": port_v,
+                "rhs_evals_per_s_per_core_port": cpu_rhs_rates(),
+                "sample": f"rows 0..{n_cpu-1} of the same table, " +
+                          ("the unmodified PyREMOT.rmtExe (oracle/_ref) per member at its defaults (LSODA rtol 1e-3/atol 1e-6)" if kind == "reference"
+                           else "SciPy LSODA at the reference's default rtol 1e-3/atol 1e-6 on the NumPy RHS restatement") +
+                          f", {cores} processes, {cpu_dt:.1f} s"},
         }
         print(json.dumps(line))
     if world > 1:
@@ -313,29 +450,77 @@ def run_gpu(a):
         dist.destroy_process_group()
 
 
-def bench_n2_config3(model):
-    """BASELINE configs[2]: dynamic model, 100 axial nodes, 4,096 instances, start-up transient (tNo = 5, period 0.5 s).
-    Secondary figure (the headline metric is configs[1]); one warm-up pass, one timed pass with CUDA events."""
+def bench_n2(model, N, zNo, label, kernel, fp64_peak, reps=3):
+    """Dynamic model (N2) ensemble on one GPU: N instances x zNo nodes, tNo = 5, period 0.5 s, start-up from the feed-filled
+    bed, same seeded T/P/composition rows as config 2.  Device-timed (CUDA events on the launching stream, one warm-up pass,
+    `reps` timed passes, L2 flushed in between); roofline of the solver kernel from its per-instance counters."""
     import torch
     from pyremot_b200 import cases
     from pyremot_b200.api import get_model
     mi2 = cases.readme_case("N2")
     m2 = get_model(mi2, device=model.device)
-    N, zNo, tNo, period = 4096, 100, 5, 0.5
+    tNo, period = 5, 0.5
     rows = cases.ensemble_rows(N)
     tab = torch.from_numpy(m2.instance_table(mi2, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]})).cuda()
     par = m2.prolog(tab)
+    flush = torch.empty(256*1024*1024, dtype=torch.uint8, device="cuda")
     r = m2.solve_n2(par, zNo, tNo, period, rtol=RTOL, atol=ATOL)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    r = m2.solve_n2(par, zNo, tNo, period, rtol=RTOL, atol=ATOL)
-    e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    l0 = m2.launch_count
+    ms = []
+    for k in range(reps):
+        flush.fill_(k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = m2.solve_n2(par, zNo, tNo, period, rtol=RTOL, atol=ATOL)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    launches = m2.launch_count - l0
+    t = float(np.mean(ms))*1e-3
     st = r["stats"].cpu().numpy()
-    return {"kernel": "pbr_k4b_solve_n2", "workload": "N2 dynamic model, zNo=100, tNo=5, period 0.5 s, 4096 instances (BASELINE configs[2])",
-            "ms": ms, "solves_per_s": N/(ms*1e-3), "failed": int((r["status"] != 0).sum().item()), "mean_steps": float(st[0].mean()),
-            "node_steps_per_s": float(st[0].sum())*zNo/(ms*1e-3), "rtol": RTOL}
+    flops, per_unit = algorithmic_flops_n2(m2, st, zNo)
+    ach = flops/t/1e12
+    return {"workload": label, "kernel": kernel, "instances": N, "zNo": zNo, "tNo": tNo, "period_s": period, "rtol": RTOL, "atol": ATOL,
+            "ms": 1e3*t, "ms_each": ms, "value": N/t, "unit": "solves/s", "failed": int((r["status"] != 0).sum().item()),
+            "mean_steps": float(st[0].mean()), "mean_nfev": float(st[2].mean()), "node_steps_per_s": float(st[0].sum())*zNo/t,
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": kernel, "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": ach/fp64_peak if fp64_peak else None, "algorithmic_flops_per_launch": flops,
+                         "flops_per_node_unit": per_unit, "traffic": None,
+                         "peak_source": "DFMA probe pbr_k_dfma_peak measured in this run"}}
+
+
+def traffic_record(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, read at run time from the committed ncu summary
+    (profiles/traffic.json, written from an `ncu --set full` capture by tools/ncu_traffic.py); None when there is no record."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), rec.get("source")
+    except Exception:
+        return None, None
+
+
+def bench_e2e_profile(model, tab_h, steps):
+    """The rmtExe contract end to end: 101-point profiles of every reactor through the host-buffer C-ABI call with pinned
+    buffers (7.9 MB H2D, 424 MB + 5.5 MB D2H per 65,536 reactors); chunked over two streams inside libpbr."""
+    import torch
+    N = tab_h.shape[0]
+    K = 101
+    out = {"dataYs": torch.empty((N, model.nv1, K), dtype=torch.float64).pin_memory().numpy(),
+           "outlet": torch.empty((N, model.nv1), dtype=torch.float64).pin_memory().numpy(),
+           "status": torch.empty((N,), dtype=torch.int32).pin_memory().numpy(),
+           "stats": torch.empty((4, N), dtype=torch.int32).pin_memory().numpy()}
+    model.solve_n1_host(tab_h.numpy(), rtol=RTOL, atol=ATOL, n_out=K, profile=True, out=out)
+    reps = max(2, min(3, steps))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = model.solve_n1_host(tab_h.numpy(), rtol=RTOL, atol=ATOL, n_out=K, profile=True, out=out)
+    dt = (time.perf_counter() - t0)/reps
+    assert (r["status"] == 0).all()
+    d2h = int(sum(v.nbytes for v in out.values()))
+    return {"value": N/dt, "unit": "solves/s", "ms_per_step": 1e3*dt, "points_per_profile": K, "h2d_bytes_per_step": int(tab_h.numel()*8),
+            "d2h_bytes_per_step": d2h, "d2h_GBps": d2h/dt/1e9, "outputs": "dataYs [N][n+2][101] + outlet rows, pinned host buffers"}
 
 
 def bench_rhs_n2(model, mi, peaks):
@@ -381,16 +566,18 @@ def bench_rhs_n2(model, mi, peaks):
     e1.record()
     torch.cuda.synchronize()
     ms1 = e0.elapsed_time(e1)/reps
-    b1 = (16.0*m2.nv1 + 8.0*m2.k_par)*N1
+    # bytes the kernel actually moves (SASS: 23 LDG.E.64 + 8 STG.E.64): state in + derivative out + the table rows the
+    # plain RHS uses (the n rows of c0 and the mu row are dead in pbr_n1_eval<false> and never loaded)
+    bpe = 8.0*(2*m2.nv1 + m2.k_par - m2.n - 1)
+    b1 = bpe*N1
     src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     return {"kernel": "pbr_k3_rhs_n2", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs/peak,
             "peak_source": src, "zNo": zNo, "instances": N, "ms": ms, "rhs_evals_per_s": N/(ms*1e-3),
-            # ncu at 16,384 instances: 94.7 MB read + 51.5 MB written to DRAM by kernel end (algorithmic 91.8 + 91.8 MB)
-            "traffic": None,
+            "traffic": traffic_record("pbr_k3_rhs_n2")[0],
             "node_evals_per_s": N*zNo/(ms*1e-3),
             "note": "16*(n+1)*zNo B per instance-eval; at ~650 executed FP64 ops per node this kernel sits on the FP64 side of the ridge",
             "rhs_n1": {"kernel": "pbr_k_rhs_n1", "bound": "hbm", "achieved": b1/(ms1*1e-3)/1e9, "peak": peak, "unit": "GB/s",
-                       "frac": b1/(ms1*1e-3)/1e9/peak, "bytes_per_eval": 16*m2.nv1 + 8*m2.k_par, "instances": N1, "ms": ms1,
+                       "frac": b1/(ms1*1e-3)/1e9/peak, "bytes_per_eval": bpe, "instances": N1, "ms": ms1,
                        "rhs_evals_per_s": N1/(ms1*1e-3), "state_only_GBs": 16.0*m2.nv1*N1/(ms1*1e-3)/1e9}}
 
 
@@ -400,7 +587,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--extras", action="store_true", help="also time BASELINE configs[2] (N2, 4096 x zNo=100) after the timed region")
+    ap.add_argument("--extras", action="store_true", help="accepted for compatibility: the N2 lines are emitted by default")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

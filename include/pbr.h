@@ -143,6 +143,10 @@ int pbr_solve_n2_host_resume(pbr_ctx* ctx, long N, int zNo, int tNo, int k_first
                              const double* iv_y_host, int flags, double rtol, double atol, int max_steps, double* snaps_y_host,
                              double* data_host, int* status_host, int* stats_host);
 
+/* Device math primitives on x_dev[n] -> out_dev[7][n]: 1/x at full, ~40-bit and ~20-bit precision, log, sqrt, exp(-x),
+ * x^(-1/3) through single-precision exp2/log2 (the reduced ones only steer the integrators; test hook). */
+int pbr_math_probe(pbr_ctx* ctx, long n, const double* x_dev, double* out_dev, void* stream);
+
 /* FP64-pipe peak probe (DFMA streams) — roofline denominator the driver's MEASURED_PEAKS.json lacks. */
 int pbr_fp64_peak(pbr_ctx* ctx, int iters, double* tflops);
 

@@ -1,7 +1,8 @@
-"""Drive the UNMODIFIED reference (``/root/reference``) — build container only.
+"""Drive the UNMODIFIED reference (``/root/reference``, or its copy ``oracle/_ref`` made by ``oracle/build_ref.py``).
 
-Used by ``oracle/make_golden.py`` to produce the committed fixtures under ``tests/golden/``.
-``/root/reference`` does not exist on the GPU box, so nothing at test/bench time imports this.
+Used by ``oracle/make_golden.py`` to produce the committed fixtures under ``tests/golden/`` (build container) and by the CPU arm
+of ``bench.py`` (``--impl reference`` / ``cpu_baseline``), the only run-time user.  The ``-m gpu`` tests and ``smoke()`` never
+import it.
 
 Recipe: matplotlib is absent from the image and ``import PyREMOT`` pulls it
 in, so a no-op stub package (``oracle/_mplstub``) goes first on ``sys.path``; tolerances are injected
@@ -18,8 +19,10 @@ import os
 import sys
 import warnings
 
-REFERENCE_ROOT = "/root/reference"
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference in the build container; elsewhere (the GPU box) the byte-for-byte copy made by oracle/build_ref.py
+REFERENCE_ROOT = os.environ.get("PBR_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/PyREMOT") else os.path.join(_HERE, "_ref"))
 
 
 def available():
@@ -30,7 +33,7 @@ def load():
     """Import the reference package; returns (PyREMOT, pbHomoReactor module, solverSetting dict)."""
     if not available():
         raise RuntimeError("reference tree not present (expected only in the build container)")
-    for p in (REFERENCE_ROOT, os.path.join(_HERE, "_mplstub")):
+    for p in (REFERENCE_ROOT, os.path.join(_HERE, "_mplstub")):      # oracle/_ref carries its own stub; the extra one is harmless
         if p not in sys.path:
             sys.path.insert(0, p)
     warnings.filterwarnings("ignore")

@@ -2465,6 +2465,21 @@ extern "C" __global__ void __launch_bounds__(256) pbr_k5_unscale_n2(long N, int 
     o[(long)PBR_NC*zNo] = th*Tf + Tf;
 }
 
+// ---- probe of the device math primitives the integrators steer with (tests): out[k][i] for x[i], k = rcp, rcp_40bit,
+//      rcp_20bit, log, sqrt, exp, fpow(x, -1/3)
+extern "C" __global__ void __launch_bounds__(128) pbr_k_math_probe(long n, const double* __restrict__ x, double* __restrict__ out) {
+    const long i = (long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    out[0*n + i] = pbr_rcp(v);
+    out[1*n + i] = pbr_rcp_40bit(v);
+    out[2*n + i] = pbr_rcp_20bit(v);
+    out[3*n + i] = pbr_log(v);
+    out[4*n + i] = pbr_sqrt(v);
+    out[5*n + i] = pbr_exp(-v);
+    out[6*n + i] = pbr_fpow(v, -1.0/3.0);
+}
+
 // ---- FP64 pipe peak probe: dependent-free DFMA streams (roofline denominator; no FP64 number in MEASURED_PEAKS.json)
 extern "C" __global__ void __launch_bounds__(256) pbr_k_dfma_peak(int iters, double* out) {
     double a0 = threadIdx.x*1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

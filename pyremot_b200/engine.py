@@ -64,6 +64,7 @@ def lib():
         "pbr_solve_n2_host_resume": (i, [vp, l, i, i, i, d, dp, dp, i, d, d, i, dp, dp, ip, ip]),
         "pbr_unscale_n2": (i, [vp, l, i, i, dp, dp, dp, vp]),
         "pbr_solve_n2_host": (i, [vp, l, i, i, d, dp, d, d, i, dp, dp, ip, ip]),
+        "pbr_math_probe": (i, [vp, l, dp, dp, vp]),
         "pbr_fp64_peak": (i, [vp, i, C.POINTER(d)]),
         "pbr_launch_count": (l, [vp]),
     }
@@ -77,7 +78,7 @@ def lib():
 EXPORTS = ("pbr_create pbr_destroy pbr_last_error pbr_version pbr_set_species pbr_load_rates pbr_model_dims pbr_n1_layout "
            "pbr_model_source pbr_model_cubin pbr_kernel_attr pbr_prolog pbr_rhs_n1 pbr_jac_n1 pbr_rhs_n2 pbr_solve_n1 "
            "pbr_unscale_n1 pbr_solve_n1_host pbr_solve_n2 pbr_solve_n2_resume pbr_unscale_n2 pbr_solve_n2_host pbr_solve_n2_host_resume "
-           "pbr_fp64_peak pbr_launch_count").split()
+           "pbr_math_probe pbr_fp64_peak pbr_launch_count").split()
 
 
 # ----------------------------------------------------------------------------- reaction parsing
@@ -347,6 +348,14 @@ class Model:
             snaps.ctypes.data_as(C.c_void_p) if scaled else None, data.ctypes.data_as(C.c_void_p),
             status.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p)))
         return {"dataYs": data, "snaps_y": snaps, "status": status, "stats": stats}
+
+    def math_probe(self, x):
+        """Device math primitives on a CUDA float64 vector -> [7, n] (rcp, rcp_40bit, rcp_20bit, log, sqrt, exp(-x), x^(-1/3))."""
+        import torch
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()
+        out = torch.empty((7, x.numel()), dtype=torch.float64, device=x.device)
+        self._check(lib().pbr_math_probe(self._ctx, x.numel(), x.data_ptr(), out.data_ptr(), self._stream()))
+        return out
 
     def fp64_peak(self, iters=8192):
         t = C.c_double()

@@ -168,3 +168,96 @@ def test_n2_scan_march_matches_serial_march_and_oracle():
     ens.period = 0.1
     _, ref, _ = O.solve_n2(ens, zNo=160, tNo=2, method="BDF", rtol=1e-9, atol=1e-13, sparse=True)
     assert relerr(scan["dataYs"][:1], ref) < RTOL_SOLVE
+
+
+def test_config3_full_size_hardest_instances_vs_oracle():
+    """BASELINE configs[2] at full size: 4,096 reactors x 100 nodes, tNo = 5, period 0.5 s.  Every instance integrates; all five
+    snapshots (full axial profiles) of the 8 reactors that needed the most RHS evaluations and of 8 seeded ones are compared with
+    the oracle (SciPy BDF rtol 1e-9 on the NumPy RHS, `pbHomoReactor.py:3589-3685` interval loop)."""
+    import torch
+    import parity_helpers as H
+    from pyremot_b200.api import get_model
+    N, zNo, tNo, period = 4096, 100, 5, 0.5
+    rows = cases.ensemble_rows(N)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    mi = cases.readme_case("N2")
+    m = get_model(mi)
+    par = m.prolog(torch.from_numpy(m.instance_table(mi, sweep)).cuda())
+    r = m.solve_n2(par, zNo, tNo, period)
+    assert int((r["status"] != 0).sum()) == 0
+    nfev = r["stats"][2].cpu().numpy()
+    idx = sorted(set(np.argsort(nfev)[-8:].tolist() + np.random.default_rng(11).choice(N, 8, replace=False).tolist()))
+    sel = torch.tensor(idx, device="cuda")
+    data = m.unscale_n2(par[:, sel].contiguous(), r["snaps_y"][sel].contiguous()).cpu().numpy()
+    ref = H.oracle_n2(sweep, idx, zNo, tNo, period)
+    err = H.relerr_rows(data, ref)
+    print(f"\nconfig 3 (N = 4096): {len(idx)} reactors x 5 snapshots x 100 nodes vs oracle: worst rel. error {err.max():.2e} "
+          f"(max nfev {nfev.max()}, mean {nfev.mean():.0f})")
+    assert err.max() < RTOL_SOLVE/3, err
+
+
+def test_config4_grid_full_period_vs_oracle():
+    """BASELINE configs[3] grid (400 nodes) over the FULL transient (tNo = 5, period 0.5 s) through K4d: 4 reactors, all snapshots
+    against the oracle."""
+    import parity_helpers as H
+    from pyremot_b200.api import get_model
+    N, zNo, tNo, period = 4, 400, 5, 0.5
+    rows = cases.ensemble_rows(N, offset=4242)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    mi = cases.readme_case("N2")
+    m = get_model(mi)
+    r = m.solve_n2_host(m.instance_table(mi, sweep), zNo, tNo, period)
+    assert (r["status"] == 0).all()
+    ref = H.oracle_n2(sweep, range(N), zNo, tNo, period)
+    err = H.relerr_rows(r["dataYs"], ref)
+    print(f"\nconfig-4 grid (zNo = 400, full period): worst rel. error {err.max():.2e}, steps {r['stats'][0].tolist()}")
+    assert err.max() < RTOL_SOLVE/3, err
+
+
+def test_warp_kernel_on_a_grid_that_needs_it_vs_oracle():
+    """Grids above 512 nodes run through K4 (one warp per reactor, scratch in global memory): zNo = 640 against the oracle."""
+    import parity_helpers as H
+    from pyremot_b200.api import get_model
+    N, zNo, tNo, period = 3, 640, 2, 0.06
+    rows = cases.ensemble_rows(N, offset=99)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    mi = cases.readme_case("N2")
+    m = get_model(mi)
+    r = m.solve_n2_host(m.instance_table(mi, sweep), zNo, tNo, period)
+    assert (r["status"] == 0).all()
+    ref = H.oracle_n2(sweep, range(N), zNo, tNo, period)
+    err = H.relerr_rows(r["dataYs"], ref)
+    print(f"\nwarp kernel (zNo = 640): worst rel. error {err.max():.2e}")
+    assert err.max() < RTOL_SOLVE/3, err
+
+
+@pytest.mark.parametrize("zNo", [100, 400, 640])
+def test_resume_from_saved_snapshot(zNo):
+    """intervals 0..1 then a resume at interval 2 from the saved snapshot (the reference's restart,
+    IV = dataYs[:, -1], `pbHomoReactor.py:3685`) reproduce the uninterrupted run -- to 1e-9 when the integrator restarts at every
+    interval as the reference does, within the parity bar otherwise.  All three kernel families (K4b, K4d, K4 warp)."""
+    import torch
+    from pyremot_b200.api import get_model
+    N, tNo, period, k = 3, 5, 0.1, 2
+    rows = cases.ensemble_rows(N, offset=7)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    mi = cases.readme_case("N2")
+    m = get_model(mi)
+    tab = m.instance_table(mi, sweep)
+    par = m.prolog(torch.from_numpy(tab).cuda())
+    for restart, tol in ((True, 1e-9), (False, RTOL_SOLVE)):
+        full = m.solve_n2(par, zNo, tNo, period, restart_every_interval=restart)
+        assert int((full["status"] != 0).sum()) == 0
+        tail = m.solve_n2(par, zNo, tNo, period, iv=full["snaps_y"][:, k - 1].contiguous(), k_first=k, restart_every_interval=restart)
+        assert int((tail["status"] != 0).sum()) == 0 and tuple(tail["snaps_y"].shape) == (N, tNo - k, m.nv2, zNo)
+        a, b = tail["snaps_y"].cpu().numpy(), full["snaps_y"][:, k:].cpu().numpy()
+        assert relerr(a, b, floor=1e-9) < tol, (zNo, restart, relerr(a, b, floor=1e-9))
+    # host-buffer entry point, and a state that cannot come from this model
+    fh = m.solve_n2_host(tab, zNo, tNo, period)
+    th = m.solve_n2_host(tab, zNo, tNo, period, iv=fh["snaps_y"][:, k - 1], k_first=k)
+    assert (th["status"] == 0).all() and relerr(th["dataYs"], fh["dataYs"][:, k:]) < RTOL_SOLVE
+    if zNo <= 512:                                       # the block kernels integrate in extent coordinates and refuse it
+        bad = fh["snaps_y"][:, k - 1].copy()
+        bad[1, 0] *= 1.001
+        tb = m.solve_n2_host(tab, zNo, tNo, period, iv=bad, k_first=k)
+        assert tb["status"][1] == 5 and np.isnan(tb["dataYs"][1]).all() and (tb["status"][[0, 2]] == 0).all()
