@@ -369,6 +369,10 @@ def run_gpu(a):
     launches = model.launch_count - l0
     t_dev = sum(e0.elapsed_time(e1) for e0, e1 in ev)*1e-3
     t_k2 = sum(e0.elapsed_time(e1) for e0, e1 in kev)*1e-3/a.steps
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    phase_ms = {"prolog": float(np.mean([ev[k][0].elapsed_time(kev[k][0]) for k in range(a.steps)])),
+                "k2": 1e3*t_k2,
+                "epilog_and_gather": float(np.mean([kev[k][1].elapsed_time(ev[k][1]) for k in range(a.steps)]))}
     # ---- timed: end-to-end through the host-buffer C-ABI call
     for _ in range(2):
         step_host()
@@ -423,6 +427,7 @@ def run_gpu(a):
             "e2e": {"value": world*N*a.steps/t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(tab_h.numel()*8),
                     "d2h_bytes_per_step": int(sum(v.nbytes for v in out_h.values()))},
             "gpu_launches": int(launches),
+            "ms_each_step": step_ms, "phase_ms": phase_ms,
             "clocks": clk.summary(),
             "roofline": {"kernel": "pbr_k2_solve_n1", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved/fp64_peak if fp64_peak else None,

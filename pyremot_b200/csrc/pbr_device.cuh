@@ -50,9 +50,10 @@
 #define PBR_NX2 ((PBR_N2_REDUCED ? PBR_NR : PBR_NC) + (PBR_ISO ? 0 : 1))
 #define PBR_NPA (PBR_NP > 0 ? PBR_NP : 1)
 
-#define PBR_R 8.314472          // core/constants.py:8
-#define PBR_TREF 298.15         // core/constants.py:23
-#define PBR_EPS 1e-30           // core/constants.py:11
+#define PBR_R PBR_CONSTS[0]      // 8.314472  core/constants.py:8   (constant-bank operands, see pbr_api.cu assemble())
+#define PBR_TREF PBR_CONSTS[1]   // 298.15    core/constants.py:23
+#define PBR_EPS PBR_CONSTS[2]    // 1e-30     core/constants.py:11
+#define PBR_MILLI PBR_CONSTS[3]  // 1e-3
 #define PBR_PI 3.141592653589793
 
 // ---- rows of the derived per-instance parameter table inst_par[KPAR][N] (written by K0, SoA: row-major, instance-minor)
@@ -115,6 +116,7 @@ PBR_DEV double pbr_fpow(double x, double e) { return (double)exp2f((float)e*log2
 // ---- property polynomials
 PBR_DEV double pbr_poly(const double* c, double T) { return c[0] + T*(c[1] + T*(c[2] + T*c[3])); }
 PBR_DEV double pbr_dpoly(const double* c, double T) { return c[1] + T*(2.0*c[2] + T*3.0*c[3]); }
+PBR_DEV double pbr_dpolyh(const double* c, double T) { return c[0] + T*(c[1] + T*c[2]); }      // tables *DH: {b, 2c, 3d}/2
 
 // =====================================================================================================
 // K0 prolog: raw inputs -> derived constants (one thread per instance)
@@ -203,7 +205,7 @@ PBR_DEV void pbr_point(const double* c, double T, double P, const InstPar& p, Po
     double M = 0.0;
 #pragma unroll
     for (int i = 0; i < PBR_NC; ++i) { e.x[i] = e.C[i]*e.invCt; M += e.x[i]*PBR_MW[i]; }   // :3176, :3202
-    e.M = M*1e-3;
+    e.M = M*PBR_MILLI;
     e.rho = P*e.M*pbr_rcp(PBR_R*T);                                               // rmtThermo.py:353-369
     if (JAC) pbr_rates_jac(T, P, e.x, e.C, p.rp, e.r, e.drT, e.drP, e.drx, e.drC);
     else     pbr_rates(T, P, e.x, e.C, p.rp, e.r);                                // rmtReaction.py:11-61
@@ -216,17 +218,17 @@ PBR_DEV void pbr_point(const double* c, double T, double P, const InstPar& p, Po
         double Cpmix = 0.0, dCp = 0.0;
 #pragma unroll
         for (int i = 0; i < PBR_NC; ++i) {
-            e.cpm[i] = 0.5*(PBR_CPREF[i] + pbr_poly(PBR_CP[i], T));               // rmtThermo.py:52-75
+            e.cpm[i] = PBR_CPREFH[i] + pbr_poly(PBR_CPH[i], T);                   // 0.5*(Cp(298.15) + Cp(T)), rmtThermo.py:52-75
             Cpmix += e.x[i]*e.cpm[i];
-            if (JAC) dCp += e.x[i]*0.5*pbr_dpoly(PBR_CP[i], T);
+            if (JAC) dCp += e.x[i]*pbr_dpolyh(PBR_CPDH[i], T);
         }
         e.Cpmix = Cpmix; e.dCpmixT = dCp;
         double Hsum = 0.0;
 #pragma unroll
         for (int j = 0; j < PBR_NR; ++j) {
-            const double m = 0.5*(PBR_DCPREF[j] + pbr_poly(PBR_DCP[j], T));       // rmtThermo.py:258-312
+            const double m = PBR_DCPREFH[j] + pbr_poly(PBR_DCPH[j], T);           // rmtThermo.py:258-312
             e.dH[j] = PBR_DH25[j] + m*(T - PBR_TREF);
-            if (JAC) e.dHdT[j] = m + 0.5*pbr_dpoly(PBR_DCP[j], T)*(T - PBR_TREF);
+            if (JAC) e.dHdT[j] = m + pbr_dpolyh(PBR_DCPDH[j], T)*(T - PBR_TREF);
             Hsum += e.r[j]*e.dH[j];
         }
         e.Hsum = Hsum;
@@ -301,7 +303,7 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
             pbr_dr_dc(e, p, k, 1.0, drk);
             pbr_dri(drk, dri);
             const double dw = w*cmct;
-            const double drho = rhoM*cmct*(1e-3*PBR_MW[k] - e.M);
+            const double drho = rhoM*cmct*(PBR_MWK[k] - e.M);
 #pragma unroll
             for (int i = 0; i < n; ++i) st(i, k, dri[i]*invGw - f[i]*cmct);
             st(n, k, dfp_dw*dw + dfp_drho*drho);
@@ -443,7 +445,7 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
             double ax[PBR_NR], ac[PBR_NR], sig = 0.0, smw = 0.0, scp = 0.0;      // sig, smw fold to constants
 #pragma unroll
             for (int j = 0; j < R; ++j) { ax[j] = 0.0; ac[j] = 0.0; }
-#define PBR_ACC(j, i, nu) if ((j) == jj) { sig += (nu); smw += (nu)*PBR_MW[i]; if (!PBR_ISO) scp += (nu)*e.cpm[i]; \
+#define PBR_ACC(j, i, nu) if ((j) == jj) { sig += (nu); smw += (nu)*PBR_MWC[i]; if (!PBR_ISO) scp += (nu)*e.cpm[i]; \
             _Pragma("unroll") for (int q = 0; q < R; ++q) { ax[q] += (nu)*e.drx[q][i]; ac[q] += (nu)*e.drC[q][i]; } }
             PBR_S_NNZ(PBR_ACC)
 #undef PBR_ACC
@@ -579,7 +581,7 @@ PBR_DEV double pbr_n2_node(const double* yc, const double* yb, bool first, doubl
 #pragma unroll
                 for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j];
                 const double dheat = -s*iGH;
-                const double dD2 = D2*(cmct*(1e-3*PBR_MW[k] - e.M)*iM + cmct*(e.cpm[k] - e.Cpmix)*iCp);
+                const double dD2 = D2*(cmct*(PBR_MWK[k] - e.M)*iM + cmct*(e.cpm[k] - e.Cpmix)*iCp);
                 // d(conv/D2)/dc = 0: conv/D2 = -(vs0/zf)(th-thb)/dz exactly
                 st(n, k, (dheat - hD2*dD2)*iD2);
             }
@@ -697,7 +699,7 @@ PBR_DEV double pbr_n2x_node(const double* x, const double* xb, bool first, doubl
 #pragma unroll
                 for (int j = 0; j < R; ++j) sH += drk[j]*e.dH[j];
                 const double dheat = -sH*iGH;
-                const double dD2 = D2*(cmct*(1e-3*smw - e.M*sig)*iM + cmct*(scp - e.Cpmix*sig)*iCp);
+                const double dD2 = D2*(cmct*(PBR_MILLI*smw - e.M*sig)*iM + cmct*(scp - e.Cpmix*sig)*iCp);
                 st(R, jj, (dheat - hD2*dD2)*iD2);
             }
         }
@@ -1277,7 +1279,7 @@ PBR_DEV bool pbr_n2_sweep_eval(const WarpCtx& w, const InstPar& p, const N2Ws& w
 #pragma unroll
             for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yc[i], PBR_EPS)*p.Cmax; Ct += C; M += C*PBR_MW[i]; }
             const double th = PBR_ISO ? 0.0 : yc[PBR_ISO ? 0 : PBR_NC];
-            a = 1.0 - dz*p.E2*p.vs0*p.vs0*(M*1e-3)*pbr_rcp(Ct*(PBR_R*(th*p.Tf + p.Tf)));
+            a = 1.0 - dz*p.E2*p.vs0*p.vs0*(M*PBR_MILLI)*pbr_rcp(Ct*(PBR_R*(th*p.Tf + p.Tf)));
             b = -dz*p.E1*p.vs0;
         }
         const double Pz = w.scan_affine(a, b, Pcarry);
@@ -1775,12 +1777,11 @@ extern "C" __global__ void __launch_bounds__(256) pbr_k5_unscale_n1(long N, int 
 extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n2(long N, int zNo, int G, const double* __restrict__ par,
                                                                                   const double* __restrict__ Y, double* __restrict__ dY) {
     __shared__ double s_par[PBR_K3_MAXG*PBR_K3_SPAR];
-    __shared__ double s_wa[4], s_wb[4], s_carry;
+    __shared__ double s_wa[2][4], s_wb[2][4];             // warp totals of the scan, double-buffered by round parity
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long g0 = (long)blockIdx.x*G;
     const int Gb = (int)((N - g0 < G) ? (N - g0) : G);                // reactors in this block
     for (int k = tid; k < Gb*PBR_KPAR; k += 128) { const int g = k / PBR_KPAR, r = k % PBR_KPAR; s_par[g*PBR_K3_SPAR + r] = par[(long)r*N + g0 + g]; }
-    if (tid == 0) s_carry = 0.0;
     __syncthreads();
     if (tid < Gb) {                                                    // derived reciprocals once per reactor
         double* sp = s_par + tid*PBR_K3_SPAR;
@@ -1796,6 +1797,7 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
     const int total = Gb*zNo;
     NoStore ns;
     int gq = tid / zNo, zq = tid - gq*zNo;                            // (reactor, node) of flattened index q, advanced without divisions
+    double carry = 0.0;
     for (int q0 = 0; q0 < total; q0 += 128) {
         const int q = q0 + tid;
         const bool act = q < total;
@@ -1803,16 +1805,9 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
         zq += 128;
         while (zq >= zNo) { zq -= zNo; ++gq; }
         const double* sp = s_par + g*PBR_K3_SPAR;
-        InstPar pp;
-        pp.Tf = sp[PAR_TF]; pp.Pf = sp[PAR_PF]; pp.Cmax = sp[PAR_CMAX]; pp.Ct0 = sp[PAR_CT0]; pp.vs0 = sp[PAR_VS0]; pp.eps = sp[PAR_EPS];
-        pp.zf = sp[PAR_ZF]; pp.E1 = sp[PAR_E1]; pp.E2 = sp[PAR_E2]; pp.rho0 = sp[PAR_RHO0]; pp.Cpmix0 = sp[PAR_CPMIX0]; pp.G = sp[PAR_G];
-        pp.GH = sp[PAR_GH]; pp.Ua = sp[PAR_UA]; pp.Tm = sp[PAR_TM];
-#pragma unroll
-        for (int k = 0; k < PBR_NC; ++k) pp.c0[k] = sp[PAR_C0 + k];
-#pragma unroll
-        for (int k = 0; k < PBR_NP; ++k) pp.rp[k] = sp[PAR_RP + k];
-        pp.iG = sp[PBR_KPAR + 0]; pp.iGH = sp[PBR_KPAR + 1]; pp.irho0 = sp[PBR_KPAR + 2]; pp.iCp0 = sp[PBR_KPAR + 3];
-        pp.F1 = sp[PBR_KPAR + 4]; pp.zP = sp[PBR_KPAR + 5]; pp.vz = sp[PBR_KPAR + 6];
+        // Only what the pressure map needs is read before the scan; everything else is read from shared memory AFTER the scan's
+        // last barrier (loads cannot move across a barrier, so values read up here would sit in registers through the scan:
+        // round 1 held all 35 staged constants = 70 registers and spilled at the 128-register cap).
         const double* Yi = Y + (g0 + g)*(long)PBR_NV2*zNo;
         double yc[PBR_NV2], yb[PBR_NV2];
 #pragma unroll
@@ -1823,13 +1818,14 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
         // affine map of this node (identity for idle lanes, constant map for a reactor's first node)
         double a = 1.0, b = 0.0;
         if (act) {
+            const double Cmax = sp[PAR_CMAX], vs0 = sp[PAR_VS0], Tf = sp[PAR_TF];
             double Ct = 0.0, M = 0.0;
 #pragma unroll
-            for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yc[i], PBR_EPS)*pp.Cmax; Ct += C; M += C*PBR_MW[i]; }
+            for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yc[i], PBR_EPS)*Cmax; Ct += C; M += C*PBR_MW[i]; }
             const double th = PBR_ISO ? 0.0 : yc[PBR_ISO ? 0 : PBR_NC];
-            a = 1.0 - dz*pp.E2*pp.vs0*pp.vs0*(M*1e-3)*pbr_rcp(Ct*(PBR_R*(th*pp.Tf + pp.Tf)));
-            b = -dz*pp.E1*pp.vs0;
-            if (z == 0) { b = a*pp.Pf + b; a = 0.0; }                 // P_z[0] = P0 (:3848): the map forgets what came before
+            a = 1.0 - dz*sp[PAR_E2]*vs0*vs0*(M*PBR_MILLI)*pbr_rcp(Ct*(PBR_R*(th*Tf + Tf)));
+            b = -dz*sp[PAR_E1]*vs0;
+            if (z == 0) { b = a*sp[PAR_PF] + b; a = 0.0; }            // P_z[0] = P0 (:3848): the map forgets what came before
         }
         // inclusive warp scan under composition (a2,b2)o(a1,b1) = (a2 a1, a2 b1 + b2)
 #pragma unroll
@@ -1838,17 +1834,32 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
             const double b1 = __shfl_up_sync(0xffffffffu, b, off);
             if (lane >= off) { b = a*b1 + b; a = a*a1; }
         }
-        if (lane == 31) { s_wa[wid] = a; s_wb[wid] = b; }
+        const int par_ = (q0 >> 7) & 1;
+        if (lane == 31) { s_wa[par_][wid] = a; s_wb[par_][wid] = b; }
         double ae = __shfl_up_sync(0xffffffffu, a, 1), be = __shfl_up_sync(0xffffffffu, b, 1);
         if (lane == 0) { ae = 1.0; be = 0.0; }
-        __syncthreads();
-        // pressure entering this warp = maps of the earlier warps of the round applied to the round's carry
-        double Pin = s_carry;
-        for (int w2 = 0; w2 < wid; ++w2) Pin = s_wa[w2]*Pin + s_wb[w2];
-        const double Pz = (z == 0) ? pp.Pf : ae*Pin + be;
-        __syncthreads();
-        if (tid == 127) s_carry = a*Pin + b;                         // pressure after the round's last node
+        __syncthreads();                                              // the only barrier of the round (totals are double-buffered)
+        // pressure entering this warp = maps of the earlier warps of the round applied to the round's carry; the carry (pressure
+        // after the round's last node) is tracked redundantly by every thread, so it needs no shared variable and no second barrier
+        double Pin = carry, Pall = carry;
+#pragma unroll
+        for (int w2 = 0; w2 < 4; ++w2) {
+            Pall = s_wa[par_][w2]*Pall + s_wb[par_][w2];
+            if (w2 + 1 == wid) Pin = Pall;
+        }
+        carry = Pall;
+        const double Pz = (z == 0) ? sp[PAR_PF] : ae*Pin + be;
         if (act) {
+            InstPar pp;
+            pp.Tf = sp[PAR_TF]; pp.Pf = sp[PAR_PF]; pp.Cmax = sp[PAR_CMAX]; pp.Ct0 = sp[PAR_CT0]; pp.vs0 = sp[PAR_VS0]; pp.eps = sp[PAR_EPS];
+            pp.zf = sp[PAR_ZF]; pp.E1 = sp[PAR_E1]; pp.E2 = sp[PAR_E2]; pp.rho0 = sp[PAR_RHO0]; pp.Cpmix0 = sp[PAR_CPMIX0]; pp.G = sp[PAR_G];
+            pp.GH = sp[PAR_GH]; pp.Ua = sp[PAR_UA]; pp.Tm = sp[PAR_TM];
+#pragma unroll
+            for (int k = 0; k < PBR_NC; ++k) pp.c0[k] = sp[PAR_C0 + k];
+#pragma unroll
+            for (int k = 0; k < PBR_NP; ++k) pp.rp[k] = sp[PAR_RP + k];
+            pp.iG = sp[PBR_KPAR + 0]; pp.iGH = sp[PBR_KPAR + 1]; pp.irho0 = sp[PBR_KPAR + 2]; pp.iCp0 = sp[PBR_KPAR + 3];
+            pp.F1 = sp[PBR_KPAR + 4]; pp.zP = sp[PBR_KPAR + 5]; pp.vz = sp[PBR_KPAR + 6];
             double f[PBR_NV2];
             pbr_n2_node<false>(yc, yb, z == 0, Pz, inv_dz, pp, f, ns, (double*)0);
             double* dYi = dY + (g0 + g)*(long)PBR_NV2*zNo;
@@ -1958,7 +1969,7 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
 #pragma unroll
         for (int i = 0; i < PBR_NC; ++i) { const double C = fmax(yf[i], PBR_EPS)*p.Cmax; Ct += C; M += C*PBR_MW[i]; }
         const double th = PBR_ISO ? 0.0 : yf[PBR_ISO ? 0 : PBR_NC];
-        a = 1.0 - dz*p.E2*p.vs0*p.vs0*(M*1e-3)*pbr_rcp(Ct*(PBR_R*(th*p.Tf + p.Tf)));
+        a = 1.0 - dz*p.E2*p.vs0*p.vs0*(M*PBR_MILLI)*pbr_rcp(Ct*(PBR_R*(th*p.Tf + p.Tf)));
         b = -dz*p.E1*p.vs0;
     }
     const double Pz = cx.scan_affine(a, b, p.Pf);

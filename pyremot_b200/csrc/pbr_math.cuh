@@ -22,14 +22,74 @@ PBR_CTABLE double PBR_EXPC[20] = {
     2.302585092994046,             // [18] ln(10)
     0.0};
 
-// A/B on B200 (round 1): the table-driven exp below is +2 % on the N1 solver kernel but -7 % on the N2 RHS kernel
-// (higher register pressure); libdevice's exp stays the default, this one is kept behind the switch.
-#ifndef PBR_CUSTOM_EXP
-#define PBR_CUSTOM_EXP 0
+// PBR_EXP_MODE selects the exponential:
+//   0  libdevice exp()/exp10()                      (default)
+//   1  Taylor-13 on |r| <= ln2/2 with constant-bank coefficients (round 1: +2 % on K2, -7 % on K3: register pressure)
+//   2  table-driven (round 2; measured in one gpurun call against 0 / 1: K2 8.62 vs 8.40 / 8.33 ms, K3 0.364 vs 0.358 / 0.358 ms,
+//      K4b 156.5 vs 158.6 / 167.6 ms -- the kernels are latency-bound, not instruction-bound, so it does not pay): x = (32k + j) ln2/32 + r, |r| <= ln2/64, exp(x) = 2^k * T[j] * (1 + q(r)) with a 32-entry table
+//      of 2^(j/32) in global memory (L1-resident; the index differs per lane, so the constant bank would serialise) and a
+//      degree-6 polynomial: 12 FP64 instructions instead of ~21, no 64-bit immediates.  |x| >= 708, inf and NaN take the
+//      library function in an out-of-line slow path (one predicated branch on the fast path).  Max error 1 ulp against libm
+//      (host replica of the algorithm over [-700, 700], tests/test_gpu_math.py checks the device version).
+#ifndef PBR_EXP_MODE
+#ifdef PBR_CUSTOM_EXP
+#define PBR_EXP_MODE (PBR_CUSTOM_EXP ? 1 : 0)
+#else
+#define PBR_EXP_MODE 0
 #endif
-#if !PBR_CUSTOM_EXP
+#endif
+#if defined(PBR_HOST) || PBR_EXP_MODE == 0
 PBR_DEV double pbr_exp(double x) { return exp(x); }
+#ifdef PBR_HOST
+PBR_DEV double pbr_exp10(double x) { return pow(10.0, x); }
+#else
 PBR_DEV double pbr_exp10(double x) { return exp10(x); }
+#endif
+#elif PBR_EXP_MODE == 2
+__device__ double PBR_EXPT[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
+    0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
+    0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
+    0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
+    0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+PBR_CTABLE double PBR_EXPC2[12] = {
+    46.166241308446828,             // [0] 32/ln2
+    6755399441055744.0,             // [1] 1.5 * 2^52: adding it rounds to the nearest integer
+    -6.93147180369123816490e-01/32, // [2] -(ln2 high part)/32 (trailing bits zero: n*this is exact for |n| < 2^20)
+    -1.90821492927058770002e-10/32, // [3] -(ln2 low part)/32
+    1.0/6.0, 1.0/24.0, 1.0/120.0, 1.0/720.0,    // [4..7]
+    2.302585092994046,          // [8] ln(10) high
+    -2.1707562233822494e-16,       // [9] ln(10) low
+    0.0, 0.0};
+__device__ __noinline__ double pbr_exp_slow(double x) { return exp(x); }
+PBR_DEV double pbr_exp(double x) {
+    const double t = fma(x, PBR_EXPC2[0], PBR_EXPC2[1]);
+    const double nf = t - PBR_EXPC2[1];
+    double r = fma(nf, PBR_EXPC2[2], x);
+    r = fma(nf, PBR_EXPC2[3], r);
+    const int n = __double2loint(t);                              // 32k + j in the low mantissa bits (two's complement)
+    const double Tj = __ldg(&PBR_EXPT[n & 31]);
+    double q = fma(r, PBR_EXPC2[7], PBR_EXPC2[6]);
+    q = fma(q, r, PBR_EXPC2[5]);
+    q = fma(q, r, PBR_EXPC2[4]);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = q*r;                                                      // exp(r) - 1
+    double y = fma(Tj, q, Tj);                                    // in [1, 2): scaling by 2^k is an add on the exponent field
+    y = __hiloint2double(__double2hiint(y) + ((n << 15) & 0xfff00000), __double2loint(y));      // normal result for |x| < 708
+    if ((__double2hiint(x) & 0x7fffffff) >= 0x40862000) y = pbr_exp_slow(x);     // |x| >= 708, inf, NaN
+    return y;
+}
+// 10^x = exp(x ln10): the product is formed in two parts so that the argument's rounding error (|x ln10| ulps) does not reach the result
+PBR_DEV double pbr_exp10(double x) {
+    const double p = x*PBR_EXPC2[8];
+    const double e = fma(x, PBR_EXPC2[8], -p) + x*PBR_EXPC2[9];
+    const double y = pbr_exp(p);
+    return fma(y, e, y);
+}
 #else
 PBR_DEV double pbr_exp(double x) {
     const double xc = fmin(fmax(x, -746.0), 710.0);              // keeps k in range; NaN passes through fmin/fmax below

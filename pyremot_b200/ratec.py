@@ -24,6 +24,7 @@ from __future__ import annotations
 import ast
 import hashlib
 import math
+import os
 import types
 
 R_CONST = 8.314472  # PyREMOT/core/constants.py:8
@@ -313,7 +314,7 @@ class CompiledRates:
         return hashlib.sha256(self.cuda_source.encode()).hexdigest()[:16]
 
 
-def compile_rates(rate_expr, n_comp, params=()):
+def compile_rates(rate_expr, n_comp, params=(), optimize=None):
     """Trace ``{"VARS": {...}, "RATES": {...}}`` (lambdas, numbers, or dashboard text) into a CompiledRates."""
     VARS, RATES = rate_expr["VARS"], rate_expr["RATES"]
     if isinstance(VARS, str):
@@ -349,7 +350,79 @@ def compile_rates(rate_expr, n_comp, params=()):
     for k, f in RATES.items():
         v = _rebind(f, tm)(d) if isinstance(f, types.FunctionType) else f
         outs.append(v.i if isinstance(v, Expr) else g.const(float(v)))
+    if optimize is None:
+        optimize = os.environ.get("PBR_RATEC_OPT", "1") != "0"      # A/B switch for measurements
+    if optimize:
+        g, outs, var_nodes = _optimize(g, outs, var_nodes)
     return CompiledRates(g, outs, n_comp, params, defaults, var_nodes)
+
+
+def _optimize(g, outs, var_nodes):
+    """Strength-reducing rewrites on the traced DAG (values change by <= a few ulp, the op count drops):
+
+    * ``log10(u) -> log(u) * (1/ln 10)``: shares the logarithm with ``log(u)`` when both occur (KP2 / KP1, KP3 of the README kinetics);
+    * ``1/exp(u) -> exp(-u)`` and ``1/10**u -> 10**(-u)`` when the exponential is used in no other way (equilibrium constants
+      that only ever divide): one reciprocal less per site, and its partials lose the ``-(1/u)^2`` factor;
+    * ``1/(c*u) -> (1/c) * (1/u)`` and ``1/u**k -> (1/u)**k``: reciprocals of ``R*T``, ``T**3`` ... collapse onto the one of ``T``.
+    Returns (new graph, new outs, new var_nodes)."""
+    live, stack = set(), list(outs)
+    while stack:
+        i = stack.pop()
+        if i not in live:
+            live.add(i)
+            stack.extend(_children(g.nodes[i]))
+    uses = {}
+    for i in sorted(live):
+        for c in _children(g.nodes[i]):
+            uses.setdefault(c, []).append(i)
+    for o in outs:
+        uses.setdefault(o, []).append(-1)
+
+    def only_divides(i):
+        return all(u >= 0 and g.nodes[u][0] == "rcp" for u in uses.get(i, [-1]))
+
+    ng = Graph()
+    m = {}
+    inv_ln10 = 1.0/math.log(10.0)
+    for i, n in enumerate(g.nodes):
+        if i not in live and i not in var_nodes.values():
+            continue
+        op = n[0]
+        if op == "const":
+            m[i] = ng.const(n[1])
+        elif op == "in":
+            m[i] = ng.inp(n[1], n[2])
+        elif op == "add":
+            m[i] = ng.add(m[n[1]], m[n[2]])
+        elif op == "sub":
+            m[i] = ng.sub(m[n[1]], m[n[2]])
+        elif op == "mul":
+            m[i] = ng.mul(m[n[1]], m[n[2]])
+        elif op == "neg":
+            m[i] = ng.neg(m[n[1]])
+        elif op == "powi":
+            m[i] = ng.pow(m[n[1]], ng.const(float(n[2])))
+        elif op == "pow":
+            m[i] = ng.pow(m[n[1]], m[n[2]])
+        elif op == "log10":
+            m[i] = ng.mul(ng.fn("log", m[n[1]]), ng.const(inv_ln10))
+        elif op == "rcp":
+            a = n[1]
+            an = g.nodes[a]
+            if an[0] == "exp" and only_divides(a):
+                m[i] = ng.fn("exp", ng.neg(m[an[1]]))
+            elif an[0] == "pow" and g.is_const(an[1], 10.0) and only_divides(a):
+                m[i] = ng.pow(ng.const(10.0), ng.neg(m[an[2]]))
+            elif an[0] == "mul" and (g.is_const(an[1]) or g.is_const(an[2])):
+                cst, u = (an[1], an[2]) if g.is_const(an[1]) else (an[2], an[1])
+                m[i] = ng.mul(ng.const(1.0/g.cval(cst)), ng.div(ng.const(1.0), m[u]))
+            elif an[0] == "powi" and an[2] > 0:
+                m[i] = ng.pow(ng.div(ng.const(1.0), m[an[1]]), ng.const(float(an[2])))
+            else:
+                m[i] = ng.div(ng.const(1.0), m[a])
+        else:
+            m[i] = ng.fn(op, m[n[1]])
+    return ng, [m[o] for o in outs], {k: m[v] for k, v in var_nodes.items() if v in m}
 
 
 def _eval_nodes(g, inputs):

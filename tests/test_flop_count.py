@@ -17,9 +17,14 @@ def test_reference_formula_op_counts_are_pinned(capsys):
 
 def test_compiled_rate_dag_is_smaller_than_the_formulas_as_written():
     """The device evaluates the same function after common-subexpression elimination: bench.py's roofline counts THAT
-    (conservative), 294 ops per N1 RHS evaluation instead of the 491 the reference spells out."""
+    (conservative), 295 ops per N1 RHS evaluation instead of the 491 the reference spells out.  (Round 2: the DAG rewrites
+    log10 -> log * const, 1/exp(u) -> exp(-u), 1/(c u) -> (1/c)(1/u) trade reciprocals for multiplications: 117 / 384 ops, of which 5
+    reciprocals instead of 11; without them (PBR_RATEC_OPT=0) 116 / 393.)"""
     from pyremot_b200 import cases, engine
     m = engine.Model(cases.readme_case("N1"), device=None)
     ops_r, ops_rj = m.rates.op_counts()
-    assert (ops_r, ops_rj) == (116, 393)
-    assert ops_r + 16*m.n + 14*m.n_rxn + 40 == 294 < 491
+    assert (ops_r, ops_rj) == (117, 384)
+    assert ops_r + 16*m.n + 14*m.n_rxn + 40 == 295 < 491
+    from pyremot_b200 import ratec
+    raw = ratec.compile_rates(cases.readme_case("N1")["reaction-rates"], 6, optimize=False)
+    assert raw.op_counts() == (116, 393)

@@ -1,12 +1,15 @@
 """Rate-expression compiler (pyremot_b200/ratec.py) against the reference executor's semantics
 (`PyREMOT/docs/rmtReaction.py:11-61`, restated in oracle.rates with the untouched lambdas)."""
 import math
+import os
 
 import numpy as np
 import pytest
 
 from oracle import pbr_oracle as O
 from pyremot_b200 import cases, ratec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _state(seed=0, n=6):
