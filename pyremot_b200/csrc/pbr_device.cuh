@@ -50,6 +50,23 @@
 #define PBR_NX2 ((PBR_N2_REDUCED ? PBR_NR : PBR_NC) + (PBR_ISO ? 0 : 1))
 #define PBR_NPA (PBR_NP > 0 ? PBR_NP : 1)
 
+// Precision of the Jacobian partials.  PBR_JAC_F32=1: the rate partials (pbr_rates_jacf) and the assembly of the Jacobian in the
+// extent-coordinate evaluators run in single precision; the Newton matrix I - cJ, its LU / inverse, the residual and everything
+// that enters the solution stay FP64.  The partials only steer the Newton iteration: a relative error eps_J in J perturbs the
+// contraction of the (already inexact) iteration by ~cond(I - cJ)*eps_J.
+#ifndef PBR_JAC_F32
+#define PBR_JAC_F32 0
+#endif
+#if PBR_JAC_F32
+typedef float jreal;
+#define PBR_RATES_JAC pbr_rates_jacf
+#define PBR_JRCP(x) pbr_rcpf(x)
+#else
+typedef double jreal;
+#define PBR_RATES_JAC pbr_rates_jac
+#define PBR_JRCP(x) pbr_rcp_40bit(x)
+#endif
+
 #define PBR_R PBR_CONSTS[0]      // 8.314472  core/constants.py:8   (constant-bank operands, see pbr_api.cu assemble())
 #define PBR_TREF PBR_CONSTS[1]   // 298.15    core/constants.py:23
 #define PBR_EPS PBR_CONSTS[2]    // 1e-30     core/constants.py:11
@@ -192,7 +209,7 @@ struct PointEval {
     double r[PBR_NR], ri[PBR_NC];
     double cpm[PBR_NC], Cpmix, dH[PBR_NR], Hsum, Q;
     // partials (JAC only)
-    double drT[PBR_NR], drP[PBR_NR], drx[PBR_NR][PBR_NC], drC[PBR_NR][PBR_NC], sx[PBR_NR];
+    jreal drT[PBR_NR], drP[PBR_NR], drx[PBR_NR][PBR_NC], drC[PBR_NR][PBR_NC], sx[PBR_NR];
     double dCpmixT, dHdT[PBR_NR];
 };
 
@@ -207,7 +224,7 @@ PBR_DEV void pbr_point(const double* c, double T, double P, const InstPar& p, Po
     for (int i = 0; i < PBR_NC; ++i) { e.x[i] = e.C[i]*e.invCt; M += e.x[i]*PBR_MW[i]; }   // :3176, :3202
     e.M = M*PBR_MILLI;
     e.rho = P*e.M*pbr_rcp(PBR_R*T);                                               // rmtThermo.py:353-369
-    if (JAC) pbr_rates_jac(T, P, e.x, e.C, p.rp, e.r, e.drT, e.drP, e.drx, e.drC);
+    if (JAC) PBR_RATES_JAC(T, P, e.x, e.C, p.rp, e.r, e.drT, e.drP, e.drx, e.drC);
     else     pbr_rates(T, P, e.x, e.C, p.rp, e.r);                                // rmtReaction.py:11-61
 #pragma unroll
     for (int i = 0; i < PBR_NC; ++i) e.ri[i] = 0.0;
@@ -237,9 +254,9 @@ PBR_DEV void pbr_point(const double* c, double T, double P, const InstPar& p, Po
     if (JAC) {
 #pragma unroll
         for (int j = 0; j < PBR_NR; ++j) {
-            double s = 0.0;
+            jreal s = 0;
 #pragma unroll
-            for (int i = 0; i < PBR_NC; ++i) s += e.x[i]*e.drx[j][i];
+            for (int i = 0; i < PBR_NC; ++i) s += (jreal)e.x[i]*e.drx[j][i];
             e.sx[j] = s;
         }
     }
@@ -427,56 +444,63 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
     }
     if (JAC) {
         const int NXr = PBR_NX;
-        double Jx[PBR_NX][PBR_NX];
+        jreal Jx[PBR_NX][PBR_NX];
 #pragma unroll
         for (int a = 0; a < NXr; ++a)
 #pragma unroll
-            for (int b = 0; b < NXr; ++b) Jx[a][b] = 0.0;
-        const double cmct = p.Cmax*e.invCt;
-        const double iGH = p.iGH, iDen = pbr_rcp_40bit(Den), irho = pbr_rcp_40bit(e.rho), iCp = PBR_ISO ? 1.0 : pbr_rcp_40bit(e.Cpmix), ipr = pbr_rcp_40bit(pr);
-        const double dfp_dw = -zP*(p.E1*p.vs0 + 2.0*p.E2*e.rho*p.vs0*p.vs0*w);
-        const double dfp_drho = -zP*(p.E2*vs*vs);
-        const double rhoM = e.rho*pbr_rcp(e.M);
-        double drk[PBR_NR];
+            for (int b = 0; b < NXr; ++b) Jx[a][b] = 0;
+        const jreal Cmaxj = (jreal)p.Cmax, wj = (jreal)w, rhoj = (jreal)e.rho, Mj = (jreal)e.M, Denj = (jreal)Den, fthj = (jreal)fth;
+        const jreal invGwj = (jreal)invGw, Cpmixj = (jreal)e.Cpmix, Tfj = (jreal)p.Tf;
+        const jreal cmct = Cmaxj*(jreal)e.invCt;
+        const jreal iGH = (jreal)p.iGH, iDen = PBR_JRCP(Denj), irho = PBR_JRCP(rhoj), iCp = PBR_ISO ? (jreal)1 : PBR_JRCP(Cpmixj), ipr = PBR_JRCP((jreal)pr);
+        const jreal dfp_dw = (jreal)(-zP*(p.E1*p.vs0 + 2.0*p.E2*e.rho*p.vs0*p.vs0*w));
+        const jreal dfp_drho = (jreal)(-zP*(p.E2*vs*vs));
+        const jreal rhoM = rhoj*PBR_JRCP(Mj);
+        jreal fj[PBR_NR], dHj[PBR_NR], drk[PBR_NR];
+#pragma unroll
+        for (int j = 0; j < R; ++j) { fj[j] = (jreal)f[j]; dHj[j] = PBR_ISO ? (jreal)0 : (jreal)e.dH[j]; }
         // ---- extent columns: directional derivatives along u_j = S[j][:] (d c / d x_j), taken directly --
         //      d r/d c_k = cmct (drx[.][k] - sx) + Cmax drC[.][k]  (pbr_dr_dc)  =>  along u: cmct (sum_k u_k drx[.][k] - sx sigma) + Cmax sum_k u_k drC[.][k]
 #pragma unroll
         for (int jj = 0; jj < R; ++jj) {
-            double ax[PBR_NR], ac[PBR_NR], sig = 0.0, smw = 0.0, scp = 0.0;      // sig, smw fold to constants
+            jreal ax[PBR_NR], ac[PBR_NR], scp = 0;
+            double sig = 0.0, smw = 0.0;                                      // sig, smw fold to constants
 #pragma unroll
-            for (int j = 0; j < R; ++j) { ax[j] = 0.0; ac[j] = 0.0; }
-#define PBR_ACC(j, i, nu) if ((j) == jj) { sig += (nu); smw += (nu)*PBR_MWC[i]; if (!PBR_ISO) scp += (nu)*e.cpm[i]; \
-            _Pragma("unroll") for (int q = 0; q < R; ++q) { ax[q] += (nu)*e.drx[q][i]; ac[q] += (nu)*e.drC[q][i]; } }
+            for (int j = 0; j < R; ++j) { ax[j] = 0; ac[j] = 0; }
+#define PBR_ACC(j, i, nu) if ((j) == jj) { sig += (nu); smw += (nu)*PBR_MWC[i]; if (!PBR_ISO) scp += (jreal)(nu)*(jreal)e.cpm[i]; \
+            _Pragma("unroll") for (int q = 0; q < R; ++q) { ax[q] += (jreal)(nu)*e.drx[q][i]; ac[q] += (jreal)(nu)*e.drC[q][i]; } }
             PBR_S_NNZ(PBR_ACC)
 #undef PBR_ACC
+            const jreal sigj = (jreal)sig, smwj = (jreal)(1e-3*smw);
 #pragma unroll
-            for (int j = 0; j < R; ++j) drk[j] = cmct*(ax[j] - e.sx[j]*sig) + p.Cmax*ac[j];
-            const double dw = w*cmct*sig;
-            const double drho = rhoM*cmct*(1e-3*smw - e.M*sig);
+            for (int j = 0; j < R; ++j) drk[j] = cmct*(ax[j] - e.sx[j]*sigj) + Cmaxj*ac[j];
+            const jreal dw = wj*cmct*sigj;
+            const jreal drho = rhoM*cmct*(smwj - Mj*sigj);
 #pragma unroll
-            for (int j = 0; j < R; ++j) Jx[j][jj] = drk[j]*invGw - f[j]*(cmct*sig);
+            for (int j = 0; j < R; ++j) Jx[j][jj] = drk[j]*invGwj - fj[j]*(cmct*sigj);
             Jx[R][jj] = dfp_dw*dw + dfp_drho*drho;
             if (!PBR_ISO) {
-                double sH = 0.0;
+                jreal sH = 0;
 #pragma unroll
-                for (int j = 0; j < R; ++j) sH += drk[j]*e.dH[j];
-                const double dNum = -sH*iGH;
-                const double dDen = Den*(drho*irho + cmct*(scp - e.Cpmix*sig)*iCp + cmct*sig);
-                Jx[R + (PBR_ISO ? 0 : 1)][jj] = (dNum - fth*dDen)*iDen;
+                for (int j = 0; j < R; ++j) sH += drk[j]*dHj[j];
+                const jreal dNum = -sH*iGH;
+                const jreal dDen = Denj*(drho*irho + cmct*(scp - Cpmixj*sigj)*iCp + cmct*sigj);
+                Jx[R + (PBR_ISO ? 0 : 1)][jj] = (dNum - fthj*dDen)*iDen;
             }
         }
         // ---- pressure column
         {
+            const jreal Pfj = (jreal)p.Pf;
 #pragma unroll
-            for (int j = 0; j < R; ++j) drk[j] = p.Pf*e.drP[j];
-            const double dw = -w*ipr, drho = e.rho*ipr;
+            for (int j = 0; j < R; ++j) drk[j] = Pfj*e.drP[j];
+            const jreal dw = -wj*ipr, drho = rhoj*ipr;
 #pragma unroll
-            for (int j = 0; j < R; ++j) Jx[j][R] = drk[j]*invGw + f[j]*ipr;
+            for (int j = 0; j < R; ++j) Jx[j][R] = drk[j]*invGwj + fj[j]*ipr;
             Jx[R][R] = dfp_dw*dw + dfp_drho*drho;
             if (!PBR_ISO) {
-                double sH = 0.0;
+                jreal sH = 0;
 #pragma unroll
-                for (int j = 0; j < R; ++j) sH += drk[j]*e.dH[j];
+                for (int j = 0; j < R; ++j) sH += drk[j]*dHj[j];
                 Jx[R + (PBR_ISO ? 0 : 1)][R] = (-sH*iGH)*iDen;
             }
         }
@@ -484,18 +508,18 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
         if (!PBR_ISO) {
             const int ct = R + (PBR_ISO ? 0 : 1);
 #pragma unroll
-            for (int j = 0; j < R; ++j) drk[j] = p.Tf*e.drT[j];
-            const double drho = -e.rho*p.Tf*pbr_rcp_40bit(T);
+            for (int j = 0; j < R; ++j) drk[j] = Tfj*e.drT[j];
+            const jreal drho = -rhoj*Tfj*PBR_JRCP((jreal)T);
 #pragma unroll
-            for (int j = 0; j < R; ++j) Jx[j][ct] = drk[j]*invGw;
+            for (int j = 0; j < R; ++j) Jx[j][ct] = drk[j]*invGwj;
             Jx[R][ct] = dfp_drho*drho;
-            double sH = 0.0;
+            jreal sH = 0;
 #pragma unroll
-            for (int j = 0; j < R; ++j) sH += drk[j]*e.dH[j] + p.Tf*e.r[j]*e.dHdT[j];
-            const double dQ = (p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
-            const double dNum = (-sH + dQ)*iGH;
-            const double dDen = Den*(drho*irho + p.Tf*e.dCpmixT*iCp);
-            Jx[ct][ct] = (dNum - fth*dDen)*iDen;
+            for (int j = 0; j < R; ++j) sH += drk[j]*dHj[j] + Tfj*(jreal)e.r[j]*(jreal)e.dHdT[j];
+            const jreal dQ = (p.Tm == 0.0) ? (jreal)0 : (jreal)(-p.Ua*p.Tf);
+            const jreal dNum = (-sH + dQ)*iGH;
+            const jreal dDen = Denj*(drho*irho + Tfj*(jreal)e.dCpmixT*iCp);
+            Jx[ct][ct] = (dNum - fthj*dDen)*iDen;
         }
 #pragma unroll
         for (int a = 0; a < NXr; ++a)
@@ -672,47 +696,51 @@ PBR_DEV double pbr_n2x_node(const double* x, const double* xb, bool first, doubl
         if (JAC) sub[R] = first ? 0.0 : p.vz*inv_dz;
     }
     if (JAC) {
-        double drk[PBR_NR];
-        const double iGH = p.iGH, iD2 = pbr_rcp_40bit(D2), iM = pbr_rcp_40bit(e.M), iCp = PBR_ISO ? 1.0 : pbr_rcp_40bit(e.Cpmix);
-        const double hD2 = heat*iD2;
-        const double cmct = p.Cmax*e.invCt;
-        double mask[PBR_NC];
+        jreal drk[PBR_NR];
+        const jreal D2j = (jreal)D2, Mj = (jreal)e.M, Cpmixj = (jreal)e.Cpmix, Cmaxj = (jreal)p.Cmax, Tfj = (jreal)p.Tf;
+        const jreal iGH = (jreal)p.iGH, iD2 = PBR_JRCP(D2j), iM = PBR_JRCP(Mj), iCp = PBR_ISO ? (jreal)1 : PBR_JRCP(Cpmixj);
+        const jreal hD2 = (jreal)heat*iD2;
+        const jreal cmct = Cmaxj*(jreal)e.invCt;
+        const jreal F1j = (jreal)F1, invGj = (jreal)invG, idzj = (jreal)inv_dz, vzdz = (jreal)(p.vz*inv_dz);
+        jreal mask[PBR_NC], dHj[PBR_NR];
 #pragma unroll
-        for (int i = 0; i < n; ++i) mask[i] = (yc[i] > PBR_EPS) ? 1.0 : 0.0;    // d max(c, eps)/dc
+        for (int i = 0; i < n; ++i) mask[i] = (yc[i] > PBR_EPS) ? (jreal)1 : (jreal)0;    // d max(c, eps)/dc
+#pragma unroll
+        for (int j = 0; j < R; ++j) dHj[j] = PBR_ISO ? (jreal)0 : (jreal)e.dH[j];
         // extent columns: directional derivatives along u = S[jj][:]*mask (see pbr_n1x_eval)
 #pragma unroll
         for (int jj = 0; jj < R; ++jj) {
-            double ax[PBR_NR], ac[PBR_NR], sig = 0.0, smw = 0.0, scp = 0.0;
+            jreal ax[PBR_NR], ac[PBR_NR], sig = 0, smw = 0, scp = 0;
 #pragma unroll
-            for (int j = 0; j < R; ++j) { ax[j] = 0.0; ac[j] = 0.0; }
-#define PBR_ACC(j, i, nu) if ((j) == jj) { const double wq = (nu)*mask[i]; sig += wq; smw += wq*PBR_MW[i]; if (!PBR_ISO) scp += wq*e.cpm[i]; \
+            for (int j = 0; j < R; ++j) { ax[j] = 0; ac[j] = 0; }
+#define PBR_ACC(j, i, nu) if ((j) == jj) { const jreal wq = (jreal)(nu)*mask[i]; sig += wq; smw += wq*(jreal)PBR_MWK[i]; if (!PBR_ISO) scp += wq*(jreal)e.cpm[i]; \
             _Pragma("unroll") for (int q = 0; q < R; ++q) { ax[q] += wq*e.drx[q][i]; ac[q] += wq*e.drC[q][i]; } }
             PBR_S_NNZ(PBR_ACC)
 #undef PBR_ACC
 #pragma unroll
             for (int j = 0; j < R; ++j) {
-                drk[j] = cmct*(ax[j] - e.sx[j]*sig) + p.Cmax*ac[j];
-                st(j, jj, F1*(drk[j]*invG - (j == jj ? inv_dz : 0.0)));
+                drk[j] = cmct*(ax[j] - e.sx[j]*sig) + Cmaxj*ac[j];
+                st(j, jj, F1j*(drk[j]*invGj - (j == jj ? idzj : (jreal)0)));
             }
             if (!PBR_ISO) {
-                double sH = 0.0;
+                jreal sH = 0;
 #pragma unroll
-                for (int j = 0; j < R; ++j) sH += drk[j]*e.dH[j];
-                const double dheat = -sH*iGH;
-                const double dD2 = D2*(cmct*(PBR_MILLI*smw - e.M*sig)*iM + cmct*(scp - e.Cpmix*sig)*iCp);
+                for (int j = 0; j < R; ++j) sH += drk[j]*dHj[j];
+                const jreal dheat = -sH*iGH;
+                const jreal dD2 = D2j*(cmct*(smw - Mj*sig)*iM + cmct*(scp - Cpmixj*sig)*iCp);
                 st(R, jj, (dheat - hD2*dD2)*iD2);
             }
         }
         if (!PBR_ISO) {
 #pragma unroll
-            for (int j = 0; j < R; ++j) { drk[j] = p.Tf*e.drT[j]; st(j, R, F1*drk[j]*invG); }
-            double sH = 0.0;
+            for (int j = 0; j < R; ++j) { drk[j] = Tfj*e.drT[j]; st(j, R, F1j*drk[j]*invGj); }
+            jreal sH = 0;
 #pragma unroll
-            for (int j = 0; j < R; ++j) sH += drk[j]*e.dH[j] + p.Tf*e.r[j]*e.dHdT[j];
-            const double dQ = (p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
-            const double dheat = (-sH + dQ)*iGH;
-            const double dD2 = D2*(-p.Tf*pbr_rcp_40bit(T) + p.Tf*e.dCpmixT*iCp);
-            st(R, R, -p.vz*inv_dz + (dheat - hD2*dD2)*iD2);
+            for (int j = 0; j < R; ++j) sH += drk[j]*dHj[j] + Tfj*(jreal)e.r[j]*(jreal)e.dHdT[j];
+            const jreal dQ = (p.Tm == 0.0) ? (jreal)0 : (jreal)(-p.Ua*p.Tf);
+            const jreal dheat = (-sH + dQ)*iGH;
+            const jreal dD2 = D2j*(-Tfj*PBR_JRCP((jreal)T) + Tfj*(jreal)e.dCpmixT*iCp);
+            st(R, R, -vzdz + (dheat - hD2*dD2)*iD2);
         }
     }
     return slope;

@@ -224,3 +224,21 @@ PBR_DEV double pbr_sqrt(double x) {
     return (x == 0.0) ? 0.0 : r;
 #endif
 }
+
+// ---- single-precision helpers of the mixed-precision Jacobian (pbr_rates_jacf): the partial derivatives only build the Newton
+//      matrix, so the hardware approximations (MUFU, ~2 ulp) are what is wanted.
+#ifdef PBR_HOST
+PBR_DEV float pbr_rcpf(float x) { return 1.0f/x; }
+PBR_DEV float pbr_expf(float x) { return expf(x); }
+PBR_DEV float pbr_logf(float x) { return logf(x); }
+PBR_DEV float pbr_log10f(float x) { return log10f(x); }
+PBR_DEV float pbr_sqrtf(float x) { return sqrtf(x); }
+PBR_DEV float pbr_powf(float x, float y) { return powf(x, y); }
+#else
+PBR_DEV float pbr_rcpf(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+PBR_DEV float pbr_expf(float x) { return __expf(x); }
+PBR_DEV float pbr_logf(float x) { return __logf(x); }
+PBR_DEV float pbr_log10f(float x) { return __log10f(x); }
+PBR_DEV float pbr_sqrtf(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+PBR_DEV float pbr_powf(float x, float y) { return __powf(x, y); }
+#endif

@@ -612,6 +612,73 @@ def _emit_body(g, needed, lines, names, ktab=None):
         lines.append(f"    const double t{i} = {rhs};")
 
 
+def _flit(v):
+    s = repr(float(v))
+    return (s if ("e" in s or "." in s or "inf" in s or "nan" in s) else s + ".0") + "f"
+
+
+def _emit_body_mixed(g, primal, needed, lines, names, ktab):
+    """Like _emit_body, but only the nodes in ``primal`` (what the rate VALUES need) are evaluated in double; every other node --
+    the partial derivatives -- is single precision (``const float f<i>``), reading the double values it needs through one cast
+    each.  The partials only build the Newton matrix I - cJ (they steer the iteration, the residual stays FP64), so 24 bits are
+    enough (the contraction of the inexact Newton iteration is ~cond(I - cJ)*6e-8), they halve the registers the
+    Jacobian holds and they run on the FP32 pipe next to the FP64 one."""
+    live, stack = set(), list(needed)
+    while stack:
+        i = stack.pop()
+        if i in live:
+            continue
+        live.add(i)
+        stack.extend(_children(g.nodes[i]))
+    fnames = {}          # node -> name of its float value
+
+    def fl(j):
+        """float operand for node j"""
+        if j in fnames:
+            return fnames[j]
+        n = g.nodes[j]
+        if n[0] == "const":
+            fnames[j] = _flit(n[1]) if n[1] >= 0 else "(" + _flit(n[1]) + ")"
+        else:                                   # a double value (primal node or input): cast once
+            lines.append(f"    const float g{j} = (float)({names[j]});")
+            fnames[j] = f"g{j}"
+        return fnames[j]
+
+    _emit_body(g, [i for i in live if i in primal], lines, names, ktab)
+    for i in sorted(live):
+        if i in primal or i in names:
+            continue
+        n = g.nodes[i]
+        op = n[0]
+        if op == "const":
+            fnames[i] = _flit(n[1]) if n[1] >= 0 else "(" + _flit(n[1]) + ")"
+            continue
+        if op == "in":
+            names[i] = {"T": "T", "P": "P"}.get(n[1]) or {"X": "x", "C": "C", "PAR": "par"}[n[1]] + f"[{n[2]}]"
+            continue
+        a = fl(n[1])
+        if op in ("add", "sub", "mul"):
+            rhs = f"{a} {dict(add='+', sub='-', mul='*')[op]} {fl(n[2])}"
+        elif op == "neg":
+            rhs = f"-{a}"
+        elif op == "rcp":
+            rhs = f"pbr_rcpf({a})"
+        elif op == "powi":
+            e = n[2]
+            rhs = _powi(a, abs(e))
+            if e < 0:
+                rhs = f"pbr_rcpf({rhs})"
+        elif op == "pow":
+            rhs = f"pbr_powf({a}, {fl(n[2])})"
+        elif op in ("exp", "log", "log10", "sqrt"):
+            rhs = f"pbr_{op}f({a})"
+        else:
+            raise RateCompileError(f"no single-precision form of {op}")
+        fnames[i] = f"f{i}"
+        lines.append(f"    const float f{i} = {rhs};")
+    return fnames, fl
+
+
 def _powi(a, e):
     # square-and-multiply, fully expanded (e <= 16)
     if e == 1:
@@ -661,6 +728,34 @@ def _emit(cr):
         for i in range(nc):
             src.append(f"    drx[{j}][{i}] = {names[dj[('X', i)]] if ('X', i) in dj else '0.0'};")
             src.append(f"    drC[{j}][{i}] = {names[dj[('C', i)]] if ('C', i) in dj else '0.0'};")
+    src.append("}")
+    # values in double, partials in single precision (PBR_JAC_F32)
+    primal, stack = set(), list(outs)
+    while stack:
+        i = stack.pop()
+        if i not in primal:
+            primal.add(i)
+            stack.extend(_children(g.nodes[i]))
+    lines, names = [], {}
+    fnames, fl = _emit_body_mixed(g, primal, need, lines, names, ktab)
+    tail = []
+
+    def fout(node):
+        if node is None:
+            return "0.0f"
+        return fl(node)
+    for j, o in enumerate(outs):
+        tail.append(f"    r[{j}] = {names[o]};")
+        dj = derivs[j]
+        tail.append(f"    drT[{j}] = {fout(dj.get(('T', 0)))};")
+        tail.append(f"    drP[{j}] = {fout(dj.get(('P', 0)))};")
+        for i in range(nc):
+            tail.append(f"    drx[{j}][{i}] = {fout(dj.get(('X', i)))};")
+            tail.append(f"    drC[{j}][{i}] = {fout(dj.get(('C', i)))};")
+    src.append(f"PBR_DEV void pbr_rates_jacf({sig}, double* r, float* drT, float* drP, "
+               f"float (*drx)[PBR_NC], float (*drC)[PBR_NC]) {{")
+    src.extend(lines)
+    src.extend(tail)
     src.append("}")
     src.insert(head, ktab.emit())
     return "\n".join(src) + "\n"
