@@ -97,6 +97,18 @@ int pbr_solve_n1(pbr_ctx* ctx, long N, const double* inst_par_dev, double rtol, 
                  int max_steps, double* prof_y_dev, double* outlet_y_dev, int* status_dev, int* stats_dev,
                  void* stream);
 
+/* K2s — K2 with forward sensitivities (BASELINE config 5: parameter-estimation Jacobians without finite differences).
+ * Instance i integrates its reactor together with s = d x / d par_k, k = kp_dev[i] (index into the model's runtime rate
+ * parameters, the `params=` of the rate compiler); the sensitivity equations use the same factorised Newton matrix as the
+ * state (staggered direct method) and take no part in the error test.
+ *   outlet_y_dev, sens_y_dev [nv1][N]: scaled state at z = 1 and d(scaled state)/d par_k.  Models without runtime
+ *   parameters return PBR_E_INVALID. */
+int pbr_solve_n1_sens(pbr_ctx* ctx, long N, const double* inst_par_dev, const int* kp_dev, double rtol, double atol,
+                      int max_steps, double* outlet_y_dev, double* sens_y_dev, int* status_dev, int* stats_dev, void* stream);
+/* K5s — d [x_1..x_n, P, T](z = 1) / d par_k from the scaled outlet state and its sensitivity: out_dev [N][nv1] */
+int pbr_unscale_sens_n1(pbr_ctx* ctx, long N, const double* inst_par_dev, const double* outlet_y_dev,
+                        const double* sens_y_dev, double* out_dev, void* stream);
+
 /* K5 — sortResult4 + mole fractions (solResultAnalysis.py:191-249, pbHomoReactor.py:2973-2983):
  * scaled y [K][nv1][N] -> dataYs [N][nv1][K] = rows x_1..x_n, P [Pa], T [K] */
 int pbr_unscale_n1(pbr_ctx* ctx, long N, int K, const double* inst_par_dev, const double* y_dev, double* out_dev,

@@ -213,8 +213,12 @@ struct PointEval {
     double dCpmixT, dHdT[PBR_NR];
 };
 
+// What the forward-sensitivity integrator needs from one Jacobian evaluation besides J itself: d f / d par_k = (d r / d par_k) * invGw
+// for the extents and -(sum_j (d r_j / d par_k) dH_j) * iGHiDen for theta (par enters f only through the rates).
+struct N1SensAux { double invGw, iGHiDen; double dH[PBR_NR]; double drp[PBR_NR][PBR_NPA]; };
+
 template <bool JAC>
-PBR_DEV void pbr_point(const double* c, double T, double P, const InstPar& p, PointEval& e) {
+PBR_DEV void pbr_point(const double* c, double T, double P, const InstPar& p, PointEval& e, N1SensAux* aux = 0) {
     double Ct = 0.0;
 #pragma unroll
     for (int i = 0; i < PBR_NC; ++i) { e.C[i] = c[i]*p.Cmax; Ct += e.C[i]; }      // :3161-3167
@@ -224,6 +228,10 @@ PBR_DEV void pbr_point(const double* c, double T, double P, const InstPar& p, Po
     for (int i = 0; i < PBR_NC; ++i) { e.x[i] = e.C[i]*e.invCt; M += e.x[i]*PBR_MW[i]; }   // :3176, :3202
     e.M = M*PBR_MILLI;
     e.rho = P*e.M*pbr_rcp(PBR_R*T);                                               // rmtThermo.py:353-369
+#if PBR_NP > 0 && !PBR_JAC_F32
+    if (JAC && aux) pbr_rates_jac_dpar(T, P, e.x, e.C, p.rp, e.r, e.drT, e.drP, e.drx, e.drC, aux->drp);
+    else
+#endif
     if (JAC) PBR_RATES_JAC(T, P, e.x, e.C, p.rp, e.r, e.drT, e.drP, e.drx, e.drC);
     else     pbr_rates(T, P, e.x, e.C, p.rp, e.r);                                // rmtReaction.py:11-61
 #pragma unroll
@@ -284,14 +292,14 @@ PBR_DEV void pbr_dri(const double* drk, double* dri) {
 struct NoStore { PBR_DEV void operator()(int, int, double) const {} };
 
 template <bool JAC, class Store>
-PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st) {
+PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st, N1SensAux* aux = 0) {
     const int n = PBR_NC;
     const double pr = y[n];
     const double th = PBR_ISO ? 0.0 : y[n + (PBR_ISO ? 0 : 1)];
     const double T = th*p.Tf + p.Tf;                                   // :3170
     const double P = pr*p.Pf;                                          // :3173
     PointEval e;
-    pbr_point<JAC>(y, T, P, p, e);
+    pbr_point<JAC>(y, T, P, p, e, aux);
     const double w = (e.Ct*p.Pf)*pbr_rcp(p.Ct0*P);                     // :3180 v/v0 (interstitial == superficial ratio)
     const double vs = p.vs0*w;                                         // :3184
     const double zP = p.zP;                                            // :3219
@@ -305,6 +313,11 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
         Den = (e.rho*p.irho0)*((e.Cpmix*p.iCp0)*p.eps)*w;              // :3284
         fth = Num*pbr_rcp(Den);
         f[n + 1] = fth;
+    }
+    if (JAC && aux) {
+        aux->invGw = invGw; aux->iGHiDen = PBR_ISO ? 0.0 : p.iGH*pbr_rcp(Den);
+#pragma unroll
+        for (int j = 0; j < PBR_NR; ++j) aux->dH[j] = PBR_ISO ? 0.0 : e.dH[j];
     }
     if (JAC) {
         // reciprocals once: an FP64 divide costs ~12 instructions and the columns below would need ~40 of them
@@ -415,9 +428,9 @@ PBR_DEV void pbr_n1x_iscale(const double* x, const InstPar& p, double rtol, doub
 
 // N1 right-hand side and Jacobian in the integrated coordinates.  Not reduced: identical to pbr_n1_eval.
 template <bool JAC, class Store>
-PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& st) {
+PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& st, N1SensAux* aux = 0) {
 #if !PBR_N1_REDUCED
-    pbr_n1_eval<JAC>(x, p, f, st);
+    pbr_n1_eval<JAC>(x, p, f, st, aux);
 #else
     const int n = PBR_NC, R = PBR_NR;
     double y[PBR_NV1];
@@ -427,7 +440,7 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
     const double T = th*p.Tf + p.Tf;
     const double P = pr*p.Pf;
     PointEval e;
-    pbr_point<JAC>(y, T, P, p, e);
+    pbr_point<JAC>(y, T, P, p, e, aux);
     const double w = (e.Ct*p.Pf)*pbr_rcp(p.Ct0*P);
     const double vs = p.vs0*w;
     const double zP = p.zP;
@@ -441,6 +454,11 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
         Den = (e.rho*p.irho0)*((e.Cpmix*p.iCp0)*p.eps)*w;
         fth = Num*pbr_rcp(Den);
         f[R + 1] = fth;
+    }
+    if (JAC && aux) {
+        aux->invGw = invGw; aux->iGHiDen = PBR_ISO ? 0.0 : p.iGH*pbr_rcp(Den);
+#pragma unroll
+        for (int j = 0; j < PBR_NR; ++j) aux->dH[j] = PBR_ISO ? 0.0 : e.dH[j];
     }
     if (JAC) {
         const int NXr = PBR_NX;
@@ -526,6 +544,50 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
 #pragma unroll
             for (int b = 0; b < NXr; ++b) st(a, b, Jx[a][b]);
     }
+#endif
+}
+
+// d f / d par_kp in the integrated coordinates from the auxiliary data of a Jacobian evaluation (forward sensitivities)
+PBR_DEV void pbr_n1x_dfdpar(const N1SensAux& ax, int kp, double* g) {
+    double col[PBR_NR];
+#pragma unroll
+    for (int j = 0; j < PBR_NR; ++j) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < PBR_NP; ++k) if (k == kp) v = ax.drp[j][k];
+        col[j] = v;
+    }
+#pragma unroll
+    for (int v = 0; v < PBR_NX; ++v) g[v] = 0.0;
+#if PBR_N1_REDUCED
+#pragma unroll
+    for (int j = 0; j < PBR_NR; ++j) g[j] = col[j]*ax.invGw;
+#else
+#define PBR_ACC(j, i, nu) g[i] += (nu)*col[j]*ax.invGw;
+    PBR_S_NNZ(PBR_ACC)
+#undef PBR_ACC
+#endif
+    if (!PBR_ISO) {
+        double sH = 0.0;
+#pragma unroll
+        for (int j = 0; j < PBR_NR; ++j) sH += col[j]*ax.dH[j];
+        g[PBR_NX - 1] = -sH*ax.iGHiDen;
+    }
+}
+
+// linear part of pbr_n1x_expand: increment of the integrated vector -> increment of [c, p, theta]
+PBR_DEV void pbr_n1x_expand_lin(const double* v, double* full) {
+#if PBR_N1_REDUCED
+#pragma unroll
+    for (int i = 0; i < PBR_NC; ++i) full[i] = 0.0;
+#define PBR_ACC(j, i, nu) full[i] += (nu)*v[j];
+    PBR_S_NNZ(PBR_ACC)
+#undef PBR_ACC
+    full[PBR_NC] = v[PBR_NR];
+    if (!PBR_ISO) full[PBR_NC + (PBR_ISO ? 0 : 1)] = v[PBR_NR + (PBR_ISO ? 0 : 1)];
+#else
+#pragma unroll
+    for (int i = 0; i < PBR_NV1; ++i) full[i] = v[i];
 #endif
 }
 
@@ -878,6 +940,11 @@ struct LuStore {            // receives Jacobian entries, stores the Newton matr
     PBR_DEV void operator()(int i, int k, double v) const { a[i*PBR_NX + k] = (i == k ? 1.0 : 0.0) - c*v; }
 };
 
+struct LuSensStore {        // as LuStore, and accumulates Js = J * s for the sensitivity right-hand side
+    Strided a; double c; const double* s; double* Js;
+    PBR_DEV void operator()(int i, int k, double v) const { a[i*PBR_NX + k] = (i == k ? 1.0 : 0.0) - c*v; Js[i] += v*s[k]; }
+};
+
 // =====================================================================================================
 // variable-order BDF / NDF (orders 1..5), quasi-constant step, following scipy/integrate/_ivp/bdf.py
 // =====================================================================================================
@@ -1016,10 +1083,20 @@ struct N1Stats { int nsteps, nrej, nfev, nlu, nfail; };
 #ifndef PBR_MID_BARRIER
 #define PBR_MID_BARRIER(bit)
 #endif
-template <class Sink>
+// NS = PBR_NX adds the forward sensitivities s = d x / d par_kp as NS more history columns (staggered direct method): after the
+// state's Newton iteration has converged, s_new = s_pred + (I - cJ)^-1 (c (J s_pred + d f/d par_kp) - psi_s) with the SAME
+// factorised matrix (the sensitivity equations are linear, so this one solve is their whole corrector); J and d f/d par are the
+// ones of the predictor point, and s takes no part in the error test, so the step sequence is the one of the plain solve.
+// s_out receives d [c, p, theta] / d par_kp at z = 1.
+template <int NS, class Sink>
 PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double atol, int n_out, int max_steps,
-                         const Strided& D, const Strided& LU, Sink& out, N1Stats& stt, bool live = true) {
+                         const Strided& D, const Strided& LU, Sink& out, N1Stats& stt, bool live = true, int kp = 0,
+                         double* s_out = 0) {
     const int NV = PBR_NX;                             // integrated variables (extent coordinates when reduced)
+    const int NVT = NV + NS;                           // columns of the difference history (state + sensitivities)
+    const int NSA = NS > 0 ? NS : 1;
+    double sp[NSA], psis[NSA], Js[NSA], gs[NSA];       // sensitivity predictor, its psi, J*s_pred, d f/d par_kp
+    bool sens_started = false;
     const int NO = PBR_NV1;                            // variables the error norms are taken over: [c, p, theta]
     const double t_bound = 1.0;                        // DoLe = 1, pbHomoReactor.py:2856
     const double dz_out = 1.0/(double)(n_out - 1);     // np.linspace(0, 1, zNo+1), :2862
@@ -1047,11 +1124,11 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
                 h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01*d0/d1;
                 h0 = fmin(h0, t_bound);
 #pragma unroll
-                for (int v = 0; v < NV; ++v) { D[0*NV + v] = y[v]; D[1*NV + v] = f[v]; y[v] = y[v] + h0*f[v]; }
+                for (int v = 0; v < NV; ++v) { D[0*NVT + v] = y[v]; D[1*NVT + v] = f[v]; y[v] = y[v] + h0*f[v]; }
             } else {
                 double df[NV];
 #pragma unroll
-                for (int v = 0; v < NV; ++v) df[v] = f[v] - D[1*NV + v];
+                for (int v = 0; v < NV; ++v) df[v] = f[v] - D[1*NVT + v];
                 const double d2 = sqrt(pbr_n1x_norm2(df, iscale)/NO)/h0;
                 const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0*1e-3) : sqrt(0.01/fmax(d1, d2));
                 h = fmin(fmin(100.0*h0, h1), t_bound);
@@ -1060,10 +1137,16 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
     }
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-        D[1*NV + v] = D[1*NV + v]*h;                                 // bdf.py:249-252  D[0] = y0, D[1] = h f0
+        D[1*NVT + v] = D[1*NVT + v]*h;                                 // bdf.py:249-252  D[0] = y0, D[1] = h f0
 #pragma unroll
-        for (int r = 2; r < PBR_DROWS; ++r) D[r*NV + v] = 0.0;
+        for (int r = 2; r < PBR_DROWS; ++r) D[r*NVT + v] = 0.0;
         y[v] = D[v];
+    }
+    if (NS > 0) {
+#pragma unroll
+        for (int v = 0; v < NS; ++v)
+#pragma unroll
+            for (int r = 0; r < PBR_DROWS; ++r) D[r*NVT + NV + v] = 0.0;      // s(0) = 0; D[1] is set at the first evaluation
     }
     out(0, y);
     int next_out = 1;
@@ -1083,7 +1166,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             if (clip) hn = t_bound - t;
             const double fac = clip ? hn*pbr_rcp(h) : pend;
             if (active && fac != 1.0) {
-                pbr_change_D<NV>(D, order, fac); n_equal = 0; h = hn; pend = 1.0;
+                pbr_change_D<NV + NS>(D, order, fac); n_equal = 0; h = hn; pend = 1.0;
             }
             t_new = clip ? t_bound : t + h;
         }
@@ -1096,16 +1179,39 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             double yp = D[v], ps = 0.0;
-            for (int r = 1; r <= PBR_MAXORD; ++r) if (r <= order) { const double Dr = D[r*NV + v]; yp += Dr; ps += Dr*pbr_bdf_gamma(r); }
+            for (int r = 1; r <= PBR_MAXORD; ++r) if (r <= order) { const double Dr = D[r*NVT + v]; yp += Dr; ps += Dr*pbr_bdf_gamma(r); }
             y[v] = yp; psi[v] = ps*ialpha; d[v] = 0.0;
+        }
+        if (NS > 0) {
+#pragma unroll
+            for (int v = 0; v < NS; ++v) {
+                double yp = D[NV + v], ps = 0.0;
+                for (int r = 1; r <= PBR_MAXORD; ++r) if (r <= order) { const double Dr = D[r*NVT + NV + v]; yp += Dr; ps += Dr*pbr_bdf_gamma(r); }
+                sp[v] = yp; psis[v] = ps*ialpha; Js[v] = 0.0;
+            }
         }
         pbr_n1x_iscale(y, p, rtol, atol, iscale);
         PBR_MID_BARRIER(2)
         // ---------------- 3. Jacobian + LU of I - cJ at the predictor (also yields f(y_pred)) ----------------
         bool lu_good = true;
         if (active) {
-            LuStore st = {LU, c};
-            pbr_n1x_eval<true>(y, p, f, st);
+            if (NS > 0) {
+                N1SensAux ax;
+                LuSensStore st = {LU, c, sp, Js};
+                pbr_n1x_eval<true>(y, p, f, st, &ax);
+                pbr_n1x_dfdpar(ax, kp, gs);
+                if (!sens_started) {
+                    // first evaluation: D[1]_s = h * (d s/dz)(0) = h * d f/d par (s(0) = 0), taken at this predictor point
+                    // (O(h^2) from the value at z = 0, the order of the first step's own truncation error)
+#pragma unroll
+                    for (int v = 0; v < NS; ++v) { D[1*NVT + NV + v] = h*gs[v]; sp[v] = h*gs[v]; psis[v] = h*gs[v]*pbr_bdf_gamma(1)*ialpha; }
+                    // J*s_pred was accumulated with s_pred = 0: add J*(h g) to first order is O(h^2) as well and is left out
+                    sens_started = true;
+                }
+            } else {
+                LuStore st = {LU, c};
+                pbr_n1x_eval<true>(y, p, f, st);
+            }
             lu_good = pbr_lu_factor<NV>(LU, piv);
             stt.nlu++; stt.nfev++;
         }
@@ -1167,15 +1273,30 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
         if (accepted) {
             n_equal++; stt.nsteps++;
             t = t_new;
+            if (NS > 0) {                                                 // sensitivity corrector with the factorised Newton matrix
+                double bs[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) bs[v] = c*(Js[v] + gs[v]) - psis[v];
+                pbr_lu_solve<NV>(LU, piv, bs);
+#pragma unroll
+                for (int v = 0; v < NS; ++v) {                            // same history update as the state, bdf.py:416-421
+                    const double dv = bs[v];
+                    const double Dk1 = D[(order + 1)*NVT + NV + v];
+                    if (order < PBR_MAXORD) D[(order + 2)*NVT + NV + v] = dv - Dk1;
+                    D[(order + 1)*NVT + NV + v] = dv;
+                    double acc = dv;
+                    for (int r = PBR_MAXORD; r >= 0; --r) if (r <= order) { acc += D[r*NVT + NV + v]; D[r*NVT + NV + v] = acc; }
+                }
+            }
             double vm[NV], vp[NV];                                        // D[order] and D[order+2] after the update
 #pragma unroll
             for (int v = 0; v < NV; ++v) {                                // bdf.py:416-421
-                const double Dk1 = D[(order + 1)*NV + v];
-                if (order < PBR_MAXORD) D[(order + 2)*NV + v] = d[v] - Dk1;
-                D[(order + 1)*NV + v] = d[v];
+                const double Dk1 = D[(order + 1)*NVT + v];
+                if (order < PBR_MAXORD) D[(order + 2)*NVT + v] = d[v] - Dk1;
+                D[(order + 1)*NVT + v] = d[v];
                 double acc = d[v];
-                for (int r = PBR_MAXORD; r >= 0; --r) if (r <= order) { acc += D[r*NV + v]; D[r*NV + v] = acc; }
-                vm[v] = D[order*NV + v]; vp[v] = d[v] - Dk1;
+                for (int r = PBR_MAXORD; r >= 0; --r) if (r <= order) { acc += D[r*NVT + v]; D[r*NVT + v] = acc; }
+                vm[v] = D[order*NVT + v]; vp[v] = d[v] - Dk1;
             }
             // dense output on (t_old, t], BdfDenseOutput bdf.py:462-484 (division-free: the loop is speculated into every trip)
             while (next_out < n_out && ((next_out == n_out - 1) ? 1.0 : next_out*dz_out) <= t) {
@@ -1188,7 +1309,7 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
                 for (int r = 1; r <= PBR_MAXORD; ++r) if (r <= order) {
                     pr *= ((te - t)*ih + (double)(r - 1))*pbr_bdf_inv(r);           // (te - (t - h (r-1)))/(h r)
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) yo[v] += D[r*NV + v]*pr;
+                    for (int v = 0; v < NV; ++v) yo[v] += D[r*NVT + v]*pr;
                 }
                 out(next_out, yo);
                 next_out++;
@@ -1209,6 +1330,14 @@ PBR_DEV int pbr_n1_solve(const InstPar& p, const double* y0, double rtol, double
             }
             if (!(t < t_bound)) active = false;
         }
+    }
+    if (NS > 0 && s_out && status == PBR_OK) {
+        double sv[NV], full[PBR_NV1];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) sv[v] = (v < NS) ? D[NV + v] : 0.0;
+        pbr_n1x_expand_lin(sv, full);
+#pragma unroll
+        for (int v = 0; v < PBR_NV1; ++v) s_out[v] = full[v];
     }
     return status;
 }
@@ -1756,7 +1885,7 @@ pbr_k2_solve_n1(long N, const double* __restrict__ par, double rtol, double atol
 #endif
     N1Sink sink = {prof_y, outlet_y, N, i, n_out, live, &p};
     N1Stats st;
-    const int rc = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, D, LU, sink, st, live);
+    const int rc = pbr_n1_solve<0>(p, y0, rtol, atol, n_out, max_steps, D, LU, sink, st, live);
     if (!live) return;
     status[i] = rc;
     if (rc != PBR_OK) {                                               // a failed instance must not look like a result: NaN rows
@@ -1769,6 +1898,67 @@ pbr_k2_solve_n1(long N, const double* __restrict__ par, double rtol, double atol
     }
     if (stats) { stats[0*N + i] = st.nsteps; stats[1*N + i] = st.nrej + st.nfail; stats[2*N + i] = st.nfev; stats[3*N + i] = st.nlu; }
 }
+
+// ---- K2s: K2 with forward sensitivities (BASELINE config 5 without finite differences).  Instance i integrates its reactor and
+//      s = d x / d par_kp[i]; outlet_y, sens_y: [NV1][N] scaled state at z = 1 and its derivative.  The host lays the instances
+//      out parameter-major (all reactors for parameter 0, then parameter 1, ...), so a warp shares kp.
+#if PBR_NP > 0 && !PBR_JAC_F32
+#ifndef PBR_N1S_BLOCK
+#define PBR_N1S_BLOCK 32
+#endif
+extern "C" __global__ void __launch_bounds__(PBR_N1S_BLOCK)
+pbr_k2s_solve_n1_sens(long N, const double* __restrict__ par, const int* __restrict__ kp, double rtol, double atol, int max_steps,
+                      double* __restrict__ outlet_y, double* __restrict__ sens_y, int* __restrict__ status, int* __restrict__ stats) {
+    extern __shared__ double pbr_smem[];
+    const long i0 = (long)blockIdx.x*blockDim.x + threadIdx.x;
+    const bool live = i0 < N;
+#if PBR_N1S_BLOCK <= 32
+    if (!live) return;
+#endif
+    const long i = live ? i0 : N - 1;
+    InstPar p; pbr_load_par(par, N, i, p);
+    double y0[PBR_NX];
+#pragma unroll
+    for (int k = 0; k < PBR_NX; ++k) y0[k] = 0.0;
+#if !PBR_N1_REDUCED
+#pragma unroll
+    for (int k = 0; k < PBR_NC; ++k) y0[k] = p.c0[k];
+#endif
+    y0[PBR_NX - (PBR_ISO ? 1 : 2)] = 1.0;
+    const Strided LU = {pbr_smem + threadIdx.x, PBR_N1S_BLOCK};
+    const Strided D = {pbr_smem + (long)PBR_NX*PBR_NX*PBR_N1S_BLOCK + threadIdx.x, PBR_N1S_BLOCK};
+    N1Sink sink = {(double*)0, outlet_y, N, i, 2, live, &p};
+    N1Stats st;
+    double so[PBR_NV1];
+#pragma unroll
+    for (int v = 0; v < PBR_NV1; ++v) so[v] = PBR_NAN_VALUE;
+    int kpar = kp[i];
+    if (kpar < 0 || kpar >= PBR_NP) kpar = 0;
+    const int rc = pbr_n1_solve<PBR_NX>(p, y0, rtol, atol, 2, max_steps, D, LU, sink, st, live, kpar, so);
+    if (!live) return;
+    status[i] = rc;
+#pragma unroll
+    for (int v = 0; v < PBR_NV1; ++v) { sens_y[(long)v*N + i] = so[v]; if (rc != PBR_OK) outlet_y[(long)v*N + i] = PBR_NAN_VALUE; }
+    if (stats) { stats[0*N + i] = st.nsteps; stats[1*N + i] = st.nrej + st.nfail; stats[2*N + i] = st.nfev; stats[3*N + i] = st.nlu; }
+}
+
+// ---- K5s: derivatives of the reported outlet quantities [x_1..x_n, P, T] from the scaled state and its sensitivity:
+//      x_i = C_i / sum C (C_i = c_i Cmax), P = p Pf, T = theta Tf + Tf  ->  dx_i = (dC_i - x_i sum dC)/sum C, dP = Pf dp, dT = Tf dtheta
+extern "C" __global__ void __launch_bounds__(256) pbr_k5_unscale_sens_n1(long N, const double* __restrict__ par, const double* __restrict__ y,
+                                                                         const double* __restrict__ dy, double* __restrict__ out) {
+    const long i = (long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double Cmax = par[PAR_CMAX*N + i], Pf = par[PAR_PF*N + i], Tf = par[PAR_TF*N + i];
+    double Ct = 0.0, dCt = 0.0;
+#pragma unroll
+    for (int v = 0; v < PBR_NC; ++v) { Ct += y[(long)v*N + i]*Cmax; dCt += dy[(long)v*N + i]*Cmax; }
+    double* o = out + (long)i*PBR_NV1;
+#pragma unroll
+    for (int v = 0; v < PBR_NC; ++v) { const double x = y[(long)v*N + i]*Cmax/Ct; o[v] = (dy[(long)v*N + i]*Cmax - x*dCt)/Ct; }
+    o[PBR_NC] = dy[(long)PBR_NC*N + i]*Pf;
+    if (!PBR_ISO) o[PBR_NC + 1] = dy[(long)(PBR_NC + (PBR_ISO ? 0 : 1))*N + i]*Tf;
+}
+#endif
 
 // ---- K5 epilog (N1): scaled y[K][NV1][N] -> reference layout dataYs[N][NV1][K] = [x_i ; P ; T]
 //      solvers/solResultAnalysis.py:191-249, pbHomoReactor.py:2973-2983.  One thread per (instance, point).

@@ -58,6 +58,8 @@ def lib():
         "pbr_rhs_n2": (i, [vp, l, i, dp, dp, dp, vp]),
         "pbr_solve_n1": (i, [vp, l, dp, d, d, i, i, dp, dp, ip, ip, vp]),
         "pbr_unscale_n1": (i, [vp, l, i, dp, dp, dp, vp]),
+        "pbr_solve_n1_sens": (i, [vp, l, dp, ip, d, d, i, dp, dp, ip, ip, vp]),
+        "pbr_unscale_sens_n1": (i, [vp, l, dp, dp, dp, dp, vp]),
         "pbr_solve_n1_host": (i, [vp, l, dp, d, d, i, i, dp, dp, ip, ip]),
         "pbr_solve_n2": (i, [vp, l, i, i, d, dp, d, d, i, dp, ip, ip, vp]),
         "pbr_solve_n2_resume": (i, [vp, l, i, i, i, d, dp, dp, i, d, d, i, dp, ip, ip, vp]),
@@ -77,7 +79,7 @@ def lib():
 
 EXPORTS = ("pbr_create pbr_destroy pbr_last_error pbr_version pbr_set_species pbr_load_rates pbr_model_dims pbr_n1_layout "
            "pbr_model_source pbr_model_cubin pbr_kernel_attr pbr_prolog pbr_rhs_n1 pbr_jac_n1 pbr_rhs_n2 pbr_solve_n1 "
-           "pbr_unscale_n1 pbr_solve_n1_host pbr_solve_n2 pbr_solve_n2_resume pbr_unscale_n2 pbr_solve_n2_host pbr_solve_n2_host_resume "
+           "pbr_unscale_n1 pbr_solve_n1_sens pbr_unscale_sens_n1 pbr_solve_n1_host pbr_solve_n2 pbr_solve_n2_resume pbr_unscale_n2 pbr_solve_n2_host pbr_solve_n2_host_resume "
            "pbr_math_probe pbr_fp64_peak pbr_launch_count").split()
 
 
@@ -269,6 +271,25 @@ class Model:
                                        prof.data_ptr() if profile else None, outlet.data_ptr(), status.data_ptr(),
                                        st.data_ptr() if stats else None, self._stream()))
         return {"prof_y": prof, "outlet_y": outlet, "status": status, "stats": st}
+
+    def solve_n1_sens(self, par, kp, rtol=1e-9, atol=1e-13, max_steps=0):
+        """K2s + K5s: outlet of every instance and its derivative with respect to runtime rate parameter ``kp[i]``.
+
+        par [k_par, N] (CUDA), kp [N] int32 (CUDA).  Returns dict(outlet [N, nv1] = [x_i, P, T], doutlet [N, nv1], status, stats)."""
+        import torch
+        N = par.shape[1]
+        dev = par.device
+        assert kp.shape == (N,) and kp.dtype == torch.int32 and kp.device == dev
+        outlet = torch.empty((self.nv1, N), dtype=torch.float64, device=dev)
+        sens = torch.empty((self.nv1, N), dtype=torch.float64, device=dev)
+        status = torch.empty((N,), dtype=torch.int32, device=dev)
+        st = torch.empty((4, N), dtype=torch.int32, device=dev)
+        self._check(lib().pbr_solve_n1_sens(self._ctx, N, par.data_ptr(), kp.data_ptr(), rtol, atol, max_steps, outlet.data_ptr(),
+                                            sens.data_ptr(), status.data_ptr(), st.data_ptr(), self._stream()))
+        dout = torch.empty((N, self.nv1), dtype=torch.float64, device=dev)
+        self._check(lib().pbr_unscale_sens_n1(self._ctx, N, par.data_ptr(), outlet.data_ptr(), sens.data_ptr(), dout.data_ptr(),
+                                              self._stream()))
+        return {"outlet": self.unscale_n1(par, outlet[None])[:, :, 0], "doutlet": dout, "status": status, "stats": st}
 
     def unscale_n1(self, par, y):
         """K5: scaled y [K,nv1,N] -> dataYs [N,nv1,K]."""

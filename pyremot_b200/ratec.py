@@ -300,7 +300,7 @@ class CompiledRates:
             return c
         need = list(self.outs)
         for dj in derivs:
-            need.extend(dj.values())
+            need.extend(v for k, v in dj.items() if k[0] != "PAR")
         return count(self.outs), count(need)
 
     @property
@@ -460,7 +460,7 @@ def _union(da, db):
 
 
 def _derivatives(g, outs, n_comp):
-    """For every output, partials w.r.t. T, P, X_i, C_i as node ids in ``g`` (sparse: missing = 0)."""
+    """For every output, partials w.r.t. T, P, X_i, C_i and the runtime parameters PAR_k as node ids in ``g`` (sparse: missing = 0)."""
     LN10 = math.log(10.0)
     dmap = {}  # node -> {input key: node}
     n_primal = len(g.nodes)
@@ -471,7 +471,7 @@ def _derivatives(g, outs, n_comp):
         if op == "in":
             if n[1] in ("T", "P"):
                 d[(n[1], 0)] = g.const(1.0)
-            elif n[1] in ("X", "C"):
+            elif n[1] in ("X", "C", "PAR"):
                 d[(n[1], n[2])] = g.const(1.0)
         elif op in ("add", "sub"):
             da, db = dmap[n[1]], dmap[n[2]]
@@ -715,7 +715,7 @@ def _emit(cr):
     lines, names = [], {}
     need = list(outs)
     for dj in derivs:
-        need.extend(dj.values())
+        need.extend(v for k, v in dj.items() if k[0] != "PAR")
     _emit_body(g, need, lines, names, ktab)
     src.append(f"PBR_DEV void pbr_rates_jac({sig}, double* r, double* drT, double* drP, "
                f"double (*drx)[PBR_NC], double (*drC)[PBR_NC]) {{")
@@ -757,5 +757,26 @@ def _emit(cr):
     src.extend(lines)
     src.extend(tail)
     src.append("}")
+    # values + state partials + partials with respect to the runtime parameters (forward sensitivities, config 5)
+    if cr.params:
+        lines, names = [], {}
+        needp = list(need)
+        for dj in derivs:
+            needp.extend(v for k, v in dj.items() if k[0] == "PAR")
+        _emit_body(g, needp, lines, names, ktab)
+        src.append(f"PBR_DEV void pbr_rates_jac_dpar({sig}, double* r, double* drT, double* drP, "
+                   f"double (*drx)[PBR_NC], double (*drC)[PBR_NC], double (*drp)[PBR_NP]) {{")
+        src.extend(lines)
+        for j, o in enumerate(outs):
+            src.append(f"    r[{j}] = {names[o]};")
+            dj = derivs[j]
+            src.append(f"    drT[{j}] = {names[dj[('T', 0)]] if ('T', 0) in dj else '0.0'};")
+            src.append(f"    drP[{j}] = {names[dj[('P', 0)]] if ('P', 0) in dj else '0.0'};")
+            for i in range(nc):
+                src.append(f"    drx[{j}][{i}] = {names[dj[('X', i)]] if ('X', i) in dj else '0.0'};")
+                src.append(f"    drC[{j}][{i}] = {names[dj[('C', i)]] if ('C', i) in dj else '0.0'};")
+            for k in range(len(cr.params)):
+                src.append(f"    drp[{j}][{k}] = {names[dj[('PAR', k)]] if ('PAR', k) in dj else '0.0'};")
+        src.append("}")
     src.insert(head, ktab.emit())
     return "\n".join(src) + "\n"

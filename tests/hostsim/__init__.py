@@ -132,6 +132,17 @@ class HostSim:
                            C.c_int(max_steps), self._p(prof), self._p(status), self._p(stats))
         return prof, status, stats
 
+    def solve_n1_sens(self, par, kp, rtol=1e-9, atol=1e-13, max_steps=1000000):
+        """Forward sensitivities of the outlet w.r.t. runtime rate parameter kp[i]: (outlet [nv1, N], sens [nv1, N]) scaled."""
+        N = par.shape[1]
+        kp = np.ascontiguousarray(kp, dtype=np.int32)
+        outlet = np.zeros((self.nv1, N)); sens = np.zeros((self.nv1, N))
+        status = np.zeros(N, dtype=np.int32)
+        stats = np.zeros((5, N), dtype=np.int32)
+        self.L.hs_solve_n1_sens(C.c_long(N), self._p(par), self._p(kp), C.c_double(rtol), C.c_double(atol), C.c_int(max_steps),
+                                self._p(outlet), self._p(sens), self._p(status), self._p(stats))
+        return outlet, sens, status, stats
+
     def solve_n2(self, par, zNo, tNo, period, rtol=1e-8, atol=1e-12, max_steps=1000000):
         N = par.shape[1]
         snaps = np.zeros((N, tNo, self.nv2, zNo))

@@ -117,10 +117,37 @@ void hs_solve_n1(long N, const double* par, double rtol, double atol, int n_out,
         Strided LUw = {work.data() + PBR_DROWS*PBR_NV1, 1};
         Sink sk = {prof, N, i, n_out, &p};
         N1Stats st;
-        status[i] = pbr_n1_solve(p, y0, rtol, atol, n_out, max_steps, Dw, LUw, sk, st);
+        status[i] = pbr_n1_solve<0>(p, y0, rtol, atol, n_out, max_steps, Dw, LUw, sk, st);
         stats[0*N + i] = st.nsteps; stats[1*N + i] = st.nrej; stats[2*N + i] = st.nfev; stats[3*N + i] = st.nlu; stats[4*N + i] = st.nfail;
     }
 }
+
+#if PBR_NP > 0
+// forward sensitivities: kp[N] parameter index per instance; outlet, sens: [NV1][N] scaled (d [c, p, theta](z = 1) / d par_kp)
+void hs_solve_n1_sens(long N, const double* par, const int* kp, double rtol, double atol, int max_steps, double* outlet, double* sens,
+                      int* status, int* stats) {
+    std::vector<double> work(2*PBR_DROWS*PBR_NV1 + PBR_NV1*PBR_NV1);
+    std::vector<double> prof((size_t)2*PBR_NV1);
+    for (long i = 0; i < N; ++i) {
+        InstPar p; pbr_load_par(par, N, i, p);
+        double y0[PBR_NX];
+        for (int k = 0; k < PBR_NX; ++k) y0[k] = 0.0;
+#if !PBR_N1_REDUCED
+        for (int k = 0; k < PBR_NC; ++k) y0[k] = p.c0[k];
+#endif
+        y0[PBR_NX - (PBR_ISO ? 1 : 2)] = 1.0;
+        Strided Dw = {work.data(), 1};
+        Strided LUw = {work.data() + 2*PBR_DROWS*PBR_NV1, 1};
+        Sink sk = {prof.data(), 1, 0, 2, &p};
+        N1Stats st;
+        double so[PBR_NV1];
+        for (int v = 0; v < PBR_NV1; ++v) so[v] = NAN;
+        status[i] = pbr_n1_solve<PBR_NX>(p, y0, rtol, atol, 2, max_steps, Dw, LUw, sk, st, true, kp[i], so);
+        for (int v = 0; v < PBR_NV1; ++v) { outlet[v*N + i] = prof[(size_t)(1*PBR_NV1 + v)]; sens[v*N + i] = so[v]; }
+        stats[0*N + i] = st.nsteps; stats[1*N + i] = st.nrej; stats[2*N + i] = st.nfev; stats[3*N + i] = st.nlu; stats[4*N + i] = st.nfail;
+    }
+}
+#endif
 
 // snaps: [N][tNo][NV2][zNo] scaled; stats [5][N]
 void hs_solve_n2(long N, int zNo, int tNo, double period, const double* par, double rtol, double atol, int max_steps,

@@ -240,3 +240,41 @@ def test_n2_resume_from_a_saved_snapshot_on_the_simt_emulator():
     bad[1, 0] *= 1.001                                   # H2 alone moved: not reachable through the three reactions
     tail, st3, _ = sim.solve_n2("pbr_k4b_solve_n2", par, zNo, tNo, period, iv=bad, k_first=k)
     assert st3[0] == 0 and st3[1] == 5 and np.isnan(tail[1]).all() and np.isfinite(tail[0]).all()
+
+
+def test_forward_sensitivities_vs_central_differences():
+    """K2's sensitivity integration (pbr_n1_solve<NS>, staggered direct method with the state's factorised
+    Newton matrix; d r / d par from the rate compiler) on the host build: d(scaled outlet)/d(theta_k) of 2 reactors x 6 kinetic
+    constants against central differences of converged plain solves.  The error scales with the integration tolerance."""
+    mi = cases.readme_case("N1", theta_as_vars=True)
+    theta = list(cases.MEOH_DME_THETA)
+    m = engine.Model(mi, params=tuple(theta), device=None)
+    hs = HostSim(m)
+    rows = cases.ensemble_rows(2)
+    tab = m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]})
+    N, p = tab.shape[0], len(theta)
+    J = np.zeros((p, 8, N))
+    rel = 1e-5
+    for k in range(p):
+        tp, tm = tab.copy(), tab.copy()
+        c = 9 + m.n + k
+        tp[:, c] *= 1 + rel
+        tm[:, c] *= 1 - rel
+        up = hs.solve_n1(hs.prolog(tp), rtol=1e-13, atol=1e-17, n_out=2)[0][1]
+        um = hs.solve_n1(hs.prolog(tm), rtol=1e-13, atol=1e-17, n_out=2)[0][1]
+        J[k] = (up - um)/(2*rel*tab[:, c])[None, :]
+    par = hs.prolog(np.concatenate([tab]*p))
+    kp = np.repeat(np.arange(p), N)
+    plain = hs.solve_n1(hs.prolog(tab), rtol=1e-9, atol=1e-13, n_out=2)
+    for rtol, tol in ((1e-9, 5e-5), (1e-11, 1e-5)):
+        out, sens, st, stats = hs.solve_n1_sens(par, kp, rtol=rtol, atol=rtol*1e-4)
+        assert (st == 0).all()
+        S = sens.reshape(8, p, N).transpose(1, 0, 2)
+        for k in range(p):
+            scale = np.abs(J[k]).max()
+            if scale < 1e-9:                 # K3's pre-exponential: the outlet sits at that reaction's equilibrium, d/dK3 ~ 1e-12
+                assert np.abs(S[k]).max() < 1e-9
+                continue
+            assert np.abs(S[k] - J[k]).max() < tol*scale, (rtol, k, np.abs(S[k] - J[k]).max()/scale)
+        if rtol == 1e-9:                     # the sensitivities take no part in the error test: same steps, same outlet
+            assert np.array_equal(stats[0][:N], plain[2][0]) and np.allclose(out[:, :N], plain[0][1], rtol=1e-11, atol=0)

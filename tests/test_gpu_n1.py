@@ -358,3 +358,43 @@ def test_other_kinetics_and_process_types_vs_oracle(torch_cuda):
     ens = O.Ensemble(mi, {k: v[idx] for k, v in sweep.items()})
     _, ref, _ = O.solve_n1(ens, method="BDF", rtol=1e-11, atol=1e-14)
     assert relerr(out["dataYs"][idx], ref) < RTOL_SOLVE
+
+
+def test_parameter_estimation_forward_sensitivities(torch_cuda):
+    """SURVEY.md section 8 f2 / BASELINE config 5 without finite differences: d(outlet)/d(theta) [x_i, P, T] for the six kinetic constants
+    from K2s (exact sensitivity equations), against central differences of the oracle (SciPy at converged tolerance) on 4
+    reactors, and against the forward-difference path on 512."""
+    import parity_helpers as H
+    from pyremot_b200 import estimation
+    mi = cases.readme_case("N1", theta_as_vars=True)
+    theta = list(cases.MEOH_DME_THETA)
+    rows = cases.ensemble_rows(512)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    J, base = estimation.outlet_jacobian_sens(mi, sweep, theta, rtol=1e-10, atol=1e-14)
+    assert J.shape == (512, 8, 6) and np.isfinite(J).all()
+    Jfd, base_fd = estimation.outlet_jacobian_fd(mi, sweep, theta, rel=1e-4)
+    assert relerr(base, base_fd) < 1e-8
+    for k in range(6):
+        scale = np.abs(Jfd[:, :6, k]).max(axis=1)
+        ok = scale > 1e-6*np.abs(Jfd[:, :6, k]).max()
+        assert (np.abs(J[:, :6, k] - Jfd[:, :6, k]).max(axis=1)[ok] < 3e-3*scale[ok]).all(), k      # forward differences: O(rel) truncation
+    idx = [17, 100, 300, 511]
+    nb, rel = len(idx), 1e-5
+    sw = {k: np.concatenate([v[idx]]*12) for k, v in sweep.items()}
+    for k, name in enumerate(theta):
+        col = np.full(12*nb, cases.MEOH_DME_THETA[name])
+        col[(2*k)*nb:(2*k + 1)*nb] *= 1 + rel
+        col[(2*k + 1)*nb:(2*k + 2)*nb] *= 1 - rel
+        sw["VARS:" + name] = col
+    ref = H.oracle_n1(sw, range(12*nb), rtol=1e-13, atol=1e-17, theta_as_vars=True).reshape(6, 2, nb, 8)
+    worst = 0.0
+    for k, name in enumerate(theta):
+        Jref = (ref[k, 0] - ref[k, 1])/(2*rel*cases.MEOH_DME_THETA[name])            # [nb, 8]
+        for b, i in enumerate(idx):
+            scale = np.abs(Jref[b, :6]).max()
+            floor = 2e-13*np.abs(base[i, :6]).max()/(2*rel*cases.MEOH_DME_THETA[name])      # noise of the differenced oracle solves
+            dev = np.abs(J[i, :6, k] - Jref[b, :6]).max()
+            worst = max(worst, dev/(2e-5*scale + floor))
+            assert dev < 2e-5*scale + floor, (i, k, dev, scale, floor)
+            assert abs(J[i, 7, k] - Jref[b, 7]) < 2e-5*abs(Jref[b, 7]) + 2e-13*base[i, 7]/(2*rel*cases.MEOH_DME_THETA[name])
+    print(f"\nforward sensitivities vs oracle central differences: worst deviation {worst:.2f} of the allowed band (2e-5 relative)")
