@@ -413,6 +413,7 @@ def run_gpu(a):
         if world == 1:
             n2c3["cpu_baseline"] = cpu_n2(cores)
         e2e_prof = bench_e2e_profile(model, tab_h, a.steps)
+        cfg5 = bench_config5(model.device)
         kind = "reference" if reference_available() else "port"
         n_cpu = max(16*cores, 128)                      # ~0.3-0.8 s per solve per core -> 5-15 s of CPU work per leg
         # the CPU path is timed at N = 1 only (at N > 1 the other ranks would sit in the final barrier for its duration)
@@ -440,7 +441,7 @@ def run_gpu(a):
                          "mean_steps": float(stats[0].mean()), "mean_nfev": float(stats[2].mean()), "mean_nlu": float(stats[3].mean()),
                          "max_over_mean_nfev": float(stats[2].max()/stats[2].mean())},
             "rhs_n2_roofline": rhs,
-            "n2_config3": n2c3, "n2_config4_slice": n2c4, "e2e_profile": e2e_prof,
+            "n2_config3": n2c3, "n2_config4_slice": n2c4, "e2e_profile": e2e_prof, "config5_estimation": cfg5,
             "cpu_baseline": None if cpu_v is None else {
                 "value": cpu_v, "unit": "solves/s", "cores": cores, "kind": kind, "port_value": port_v,
                 "rhs_evals_per_s_per_core_port": cpu_rhs_rates(),
@@ -494,6 +495,46 @@ def bench_n2(model, N, zNo, label, kernel, fp64_peak, reps=3):
                          "frac": ach/fp64_peak if fp64_peak else None, "algorithmic_flops_per_launch": flops,
                          "flops_per_node_unit": per_unit, "traffic": None,
                          "peak_source": "DFMA probe pbr_k_dfma_peak measured in this run"}}
+
+
+def bench_config5(model_device):
+    """BASELINE configs[4]: parameter-estimation Jacobian d(outlet)/d(theta) [8 x 6] of 16,384 base reactors -- by forward
+    sensitivities (K2s: 98,304 instances at the working tolerance) and by the forward differences the config describes (114,688
+    solves at rtol 1e-11 so that integration noise stays below the perturbation).  Device-resident inputs, CUDA events."""
+    import torch
+    from pyremot_b200 import cases
+    from pyremot_b200.api import get_model
+    mi = cases.readme_case("N1", theta_as_vars=True)
+    theta = list(cases.MEOH_DME_THETA)
+    m = get_model(mi, params=tuple(theta), device=model_device)
+    Nb, p = 16384, len(theta)
+    rows = cases.ensemble_rows(Nb)
+    base = m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]})
+    tab_s = torch.from_numpy(np.concatenate([base]*p)).cuda()
+    kp = torch.arange(p, dtype=torch.int32, device="cuda").repeat_interleave(Nb)
+    blocks = [base]
+    for k in range(p):
+        t = base.copy()
+        t[:, 9 + m.n + k] *= 1.0 + 1e-4
+        blocks.append(t)
+    tab_f = torch.from_numpy(np.concatenate(blocks)).cuda()
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), r
+    ms_s, rs = timed(lambda: m.solve_n1_sens(m.prolog(tab_s), kp, rtol=RTOL, atol=ATOL))
+    ms_f, rf = timed(lambda: m.solve_n1(m.prolog(tab_f), rtol=1e-11, atol=1e-15, n_out=2, profile=False))
+    return {"workload": "d(outlet)/d(theta), 6 kinetic constants x 16384 base reactors (BASELINE configs[4])",
+            "sensitivities": {"kernel": "pbr_k2s_solve_n1_sens", "instances": Nb*p, "rtol": RTOL, "ms": ms_s, "jacobians_per_s": Nb/(ms_s*1e-3),
+                              "failed": int((rs["status"] != 0).sum().item())},
+            "forward_differences": {"kernel": "pbr_k2_solve_n1", "instances": Nb*(p + 1), "rtol": 1e-11, "ms": ms_f,
+                                    "jacobians_per_s": Nb/(ms_f*1e-3), "failed": int((rf["status"] != 0).sum().item())}}
 
 
 def traffic_record(kernel):

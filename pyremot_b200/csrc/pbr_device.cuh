@@ -57,6 +57,10 @@
 #ifndef PBR_JAC_F32
 #define PBR_JAC_F32 0
 #endif
+#if PBR_JAC_F32 && !defined(PBR_HAVE_JACF)
+#undef PBR_JAC_F32
+#define PBR_JAC_F32 0       // the rate compiler found a constant outside the float range: double partials for this model
+#endif
 #if PBR_JAC_F32
 typedef float jreal;
 #define PBR_RATES_JAC pbr_rates_jacf

@@ -612,7 +612,13 @@ def _emit_body(g, needed, lines, names, ktab=None):
         lines.append(f"    const double t{i} = {rhs};")
 
 
+class _NoFloatForm(Exception):
+    pass
+
+
 def _flit(v):
+    if v != 0.0 and not (1.2e-38 < abs(float(v)) < 3.4e38):
+        raise _NoFloatForm(v)                  # not a normal single-precision number: the model keeps double partials
     s = repr(float(v))
     return (s if ("e" in s or "." in s or "inf" in s or "nan" in s) else s + ".0") + "f"
 
@@ -736,27 +742,31 @@ def _emit(cr):
         if i not in primal:
             primal.add(i)
             stack.extend(_children(g.nodes[i]))
-    lines, names = [], {}
-    fnames, fl = _emit_body_mixed(g, primal, need, lines, names, ktab)
-    tail = []
+    try:
+        lines, names = [], {}
+        fnames, fl = _emit_body_mixed(g, primal, need, lines, names, ktab)
+        tail = []
 
-    def fout(node):
-        if node is None:
-            return "0.0f"
-        return fl(node)
-    for j, o in enumerate(outs):
-        tail.append(f"    r[{j}] = {names[o]};")
-        dj = derivs[j]
-        tail.append(f"    drT[{j}] = {fout(dj.get(('T', 0)))};")
-        tail.append(f"    drP[{j}] = {fout(dj.get(('P', 0)))};")
-        for i in range(nc):
-            tail.append(f"    drx[{j}][{i}] = {fout(dj.get(('X', i)))};")
-            tail.append(f"    drC[{j}][{i}] = {fout(dj.get(('C', i)))};")
-    src.append(f"PBR_DEV void pbr_rates_jacf({sig}, double* r, float* drT, float* drP, "
-               f"float (*drx)[PBR_NC], float (*drC)[PBR_NC]) {{")
-    src.extend(lines)
-    src.extend(tail)
-    src.append("}")
+        def fout(node):
+            if node is None:
+                return "0.0f"
+            return fl(node)
+        for j, o in enumerate(outs):
+            tail.append(f"    r[{j}] = {names[o]};")
+            dj = derivs[j]
+            tail.append(f"    drT[{j}] = {fout(dj.get(('T', 0)))};")
+            tail.append(f"    drP[{j}] = {fout(dj.get(('P', 0)))};")
+            for i in range(nc):
+                tail.append(f"    drx[{j}][{i}] = {fout(dj.get(('X', i)))};")
+                tail.append(f"    drC[{j}][{i}] = {fout(dj.get(('C', i)))};")
+        src.append("#define PBR_HAVE_JACF 1")
+        src.append(f"PBR_DEV void pbr_rates_jacf({sig}, double* r, float* drT, float* drP, "
+                   f"float (*drx)[PBR_NC], float (*drC)[PBR_NC]) {{")
+        src.extend(lines)
+        src.extend(tail)
+        src.append("}")
+    except _NoFloatForm:
+        src.append("// no single-precision form of the partials (a constant is outside the float range): PBR_JAC_F32 falls back to double")
     # values + state partials + partials with respect to the runtime parameters (forward sensitivities, config 5)
     if cr.params:
         lines, names = [], {}

@@ -65,7 +65,8 @@ def test_rhs_n1_vs_reference_golden(torch_cuda, golden, tag, pt):
     f = m.rhs_n1(par, torch.from_numpy(np.ascontiguousarray(Y.T)).cuda()).cpu().numpy().T
     assert relerr(f, F, floor=1e-300) < RTOL_RHS
     f2, J = m.jac_n1(par, torch.from_numpy(np.ascontiguousarray(Y.T)).cuda())
-    assert np.array_equal(f2.cpu().numpy().T, f)
+    # same formulas through pbr_rates_jac instead of pbr_rates: identical up to the compiler's FMA contraction choices
+    assert relerr(f2.cpu().numpy().T, f, floor=1e-300) < 1e-12
 
 
 def test_rhs_n1_sweep_and_jacobian(torch_cuda, golden):
@@ -374,10 +375,12 @@ def test_parameter_estimation_forward_sensitivities(torch_cuda):
     assert J.shape == (512, 8, 6) and np.isfinite(J).all()
     Jfd, base_fd = estimation.outlet_jacobian_fd(mi, sweep, theta, rel=1e-4)
     assert relerr(base, base_fd) < 1e-8
-    for k in range(6):
+    for k, name in enumerate(theta):
         scale = np.abs(Jfd[:, :6, k]).max(axis=1)
-        ok = scale > 1e-6*np.abs(Jfd[:, :6, k]).max()
-        assert (np.abs(J[:, :6, k] - Jfd[:, :6, k]).max(axis=1)[ok] < 3e-3*scale[ok]).all(), k      # forward differences: O(rel) truncation
+        # forward differences: O(rel) truncation error, plus the noise of two differenced solves (rtol 1e-11) over the step --
+        # which is all there is in the K3 column (the outlet sits at that reaction's equilibrium, d/dK3 ~ 1e-12)
+        floor = 5e-11*np.abs(base[:, :6]).max(axis=1)/(1e-4*cases.MEOH_DME_THETA[name])
+        assert (np.abs(J[:, :6, k] - Jfd[:, :6, k]).max(axis=1) < 3e-3*scale + floor).all(), k
     idx = [17, 100, 300, 511]
     nb, rel = len(idx), 1e-5
     sw = {k: np.concatenate([v[idx]]*12) for k, v in sweep.items()}
