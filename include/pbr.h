@@ -65,6 +65,12 @@ int pbr_set_species(pbr_ctx* ctx, int n_comp, int n_rxn, const double* MW, const
                     const double* vis_coef, const double* S, const double* dH25, const double* dcp_coef,
                     int iso_thermal);
 
+/* Model variant, to be chosen before pbr_load_rates: 0 (default) = the non-dimensional models N1 / N2; 1 = the dimensional
+ * steady-state model "M7" (rmtCore.py:300-309 -> pbReactor.py runM3 :1170, modelEquationM3 :1371-1577) run through the N1 entry
+ * points.  Variant 1 appends two columns to inst_in: mixture viscosity [Pa.s] (feed['mixture-viscosity']) and the heat-exchange
+ * area per volume (external-heat['EfHeTrAr']), both inputs of that model. */
+int pbr_set_model_variant(pbr_ctx* ctx, int variant);
+
 /* Compile the model: `cuda_src` defines PBR_NP, pbr_rates() and pbr_rates_jac() (output of the rate-expression
  * compiler; replaces reactionRateExe, PyREMOT/docs/rmtReaction.py:11-61).  NVRTC -> sm_100a cubin, cached in
  * `cache_dir` (may be NULL) under a hash of the full program text.  `*log` (may be NULL) receives the NVRTC log. */

@@ -31,8 +31,7 @@ def build(verbose=True):
         os.makedirs(stub, exist_ok=True)
         with open(os.path.join(stub, "__init__.py"), "w") as f:
             f.write("# no-op stand-in: the image has no matplotlib and the reference imports it at package import\n")
-        with open(os.path.join(stub, "pyplot.py"), "w") as f:
-            f.write("def __getattr__(name):\n    return lambda *a, **k: None\n")
+        shutil.copyfile(os.path.join(HERE, "_mplstub", "matplotlib", "pyplot.py"), os.path.join(stub, "pyplot.py"))
         if verbose:
             n = sum(len(fs) for _, _, fs in os.walk(pkg))
             print(f"oracle/_ref: copied {n} files of the reference package from {SRC}")

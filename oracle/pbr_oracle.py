@@ -257,6 +257,9 @@ class Ensemble:
         self.U = col("U", eh["OvHeTrCo"])
         self.Tm = col("Tm", eh["MeTe"])
         self.period = oc.get("period")
+        # dimensional model M7 only (pbReactor.py:1238, :1545): mixture viscosity and heat-exchange area are INPUTS there
+        self.mu_in = col("GaMiVi", fe.get("mixture-viscosity", float("nan")))
+        self.a_in = col("EfHeTrAr", eh.get("EfHeTrAr", float("nan")))
         self.var_overrides = {k[5:]: np.broadcast_to(np.asarray(v, dtype=np.float64), (N,)).copy()
                               for k, v in sweep.items() if k.startswith("VARS:")}
         self.prolog()
@@ -340,6 +343,43 @@ class Ensemble:
             constT1 = 1/(rho_s*(Cp_s*eps)*vi_s)                        # :3257, :3284
             out[:, n+1] = constT1*((-OvHeReT + Qm)/self.GH)            # :3298
         return out
+
+    # ---- M7: dimensional steady-state model (rmtCore.py:300-309 -> pbReactor.py runM3 :1170-1369)
+    def iv_m7(self):
+        """[C0 (n), T, P], pbReactor.py:1243-1247."""
+        return np.concatenate([self.C0, self.T0[:, None], self.P0[:, None]], axis=1)
+
+    def rhs_m7(self, y):
+        """modelEquationM3, pbReactor.py:1371-1577. y = [C_i (n), T, P] dimensional, independent variable z in [0, ReLe] m."""
+        n = self.n
+        y = np.asarray(y, dtype=np.float64)
+        C, T, P = y[:, :n], y[:, n], y[:, n+1]                         # :1448-1452
+        Ct = np.sum(C, axis=1)                                         # :1455
+        x = C/Ct[:, None]                                              # :1458
+        vi = self.vi0*(Ct/self.Ct0)*(self.P0/P)                        # :1462, rmtUtility.py:405-421
+        vs = vi*self.BeVoFr                                            # :1464
+        MoFl = Ct*vs                                                   # :1468, :1474 (area cancels)
+        M = np.sum(x*self.MW, axis=1)*1e-3                             # :1480
+        GaDe = M*Ct                                                    # :1483, rmtThermo.py:338-348 (not the EOS density)
+        eps, dp = self.BeVoFr, self.PaDi
+        ergA = 150*self.mu_in*vs/(dp**2)                               # :1490 (viscosity is an input, :1238)
+        ergB = ((1-eps)**2)/(eps**3)
+        ergC = 1.75*GaDe*(vs**2)/dp
+        ergD = (1-eps)/(eps**3)
+        r = rates(self.rate_expr, T, P, x, C, self.var_overrides)      # :1505-1508
+        ri = r @ self.S                                                # :1517
+        Cpmix, OvHeReT = self._thermo_terms(x, T, r)                   # :1525-1539
+        Qm = self.U*self.a_in*(self.Tm - T)                            # :1543-1551 (no Tm == 0 switch, area from the input)
+        out = np.zeros_like(y)
+        out[:, :n] = ri/vs[:, None]                                    # :1557, :1562
+        out[:, n] = (-OvHeReT + Qm)/(MoFl*Cpmix)                       # :1558, :1566
+        out[:, n+1] = -1*(ergA*ergB + ergC*ergD)                       # :1494, :1570
+        return out
+
+    def unscale_m7(self, y):
+        """runM3 result assembly, pbReactor.py:1305-1322: rows x_i (n), T -- the pressure row is dropped. y: [N, n+2, K]."""
+        C = y[:, :self.n]
+        return np.concatenate([C/np.sum(C, axis=1, keepdims=True), y[:, self.n:self.n+1]], axis=1)
 
     def rhs_n2(self, Y):
         """modelEquationN2, pbHomoReactor.py:3827-4131. Y: [N, nv, zNo] -> same (var-major per instance).
@@ -444,6 +484,26 @@ def solve_n1(ens, method="LSODA", rtol=1e-3, atol=1e-6, zNo=100, instances=None)
     y = np.stack(ys)
     sel = ens if instances is None else _select(ens, list(idx))
     return y, sel.unscale_n1(y), np.array(nfev)
+
+
+def solve_m7(ens, method="LSODA", rtol=1e-3, atol=1e-6, zNo=30, instances=None):
+    """Per-instance solve_ivp over z in [0, ReLe] with t_eval = linspace(0, ReLe, zNo) (zNo = solverSetting['M9']['zNo'] = 30),
+    pbReactor.py:1283-1298.  Returns (y [M, n+2, zNo] dimensional state, dataYs [M, n+1, zNo] = [x_i ; T], nfev [M])."""
+    from scipy.integrate import solve_ivp
+    idx = range(ens.N) if instances is None else instances
+    ys, nfev = [], []
+    for i in idx:
+        e = ens.sub(i)
+        L = float(e.ReLe[0])
+        sol = solve_ivp(lambda t, y: e.rhs_m7(y[None, :])[0], [0, L], e.iv_m7()[0], method=method, t_eval=np.linspace(0, L, zNo),
+                        rtol=rtol, atol=atol)
+        if not sol.success:
+            raise RuntimeError(f"oracle M7 solve failed for instance {i}: {sol.message}")
+        ys.append(sol.y)
+        nfev.append(sol.nfev)
+    y = np.stack(ys)
+    sel = ens if instances is None else _select(ens, list(idx))
+    return y, sel.unscale_m7(y), np.array(nfev)
 
 
 def n2_jac_sparsity(nv, zNo):

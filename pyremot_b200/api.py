@@ -27,6 +27,7 @@ from . import engine
 solverSetting = {
     "N1": {"zNo": 100},
     "N2": {"zNo": 20, "rNo": 5, "tNo": 5, "timesNo": 5},
+    "M9": {"zNo": 30},            # number of output points of model M7 (`PyREMOT/docs/pbReactor.py:1283`)
 }
 
 DEFAULT_RTOL = 1e-9
@@ -55,7 +56,8 @@ def get_model(modelInput, params=(), device=0):
     probe = engine.ratec.compile_rates(modelInput["reaction-rates"], len(modelInput["feed"]["components"]["shell"]),
                                        params=params)
     key = (tuple(modelInput["feed"]["components"]["shell"]), tuple(modelInput["reactions"].items()),
-           modelInput["operating-conditions"]["process-type"], probe.key, tuple(params), device)
+           modelInput["operating-conditions"]["process-type"], probe.key, tuple(params), device,
+           "M7" if modelInput.get("model") == "M7" else "N")
     m = _models.get(key)
     if m is None:
         m = engine.Model(modelInput, params=params, device=device)
@@ -122,6 +124,32 @@ def _run_n1(modelInput, device=0):
     return [_n1_pack(modelInput, model, dataYs, y_scaled, elapsed)]
 
 
+def _run_m7(modelInput, device=0):
+    """Model "M7" (`PyREMOT/docs/rmtCore.py:300-309` -> `pbReactor.py` runM3 `:1170-1369`): dimensional steady-state balances for
+    C_i, T, P over z in [0, ReLe]; result ``{"dataYs": [x_i ; T] (n+1) x K, "XYList", "dataList"}`` with K =
+    ``solverSetting['M9']['zNo']`` (`:1283`) points (`:1305-1367`; the pressure row is not reported).  The reference also plots
+    unconditionally (`:1344`); this does not."""
+    import torch
+    rtol, atol = _tolerances(modelInput)
+    model = get_model(modelInput, device=device)
+    K = solverSetting["M9"]["zNo"]
+    tab = torch.from_numpy(model.instance_table(modelInput)).to(model._dev())
+    par = model.prolog(tab)
+    res = model.solve_n1(par, rtol=rtol, atol=atol, n_out=K, profile=True)
+    st = int(res["status"][0].item())
+    if st != 0:
+        raise RuntimeError(f"M7 integration failed (status {st})")
+    full = model.unscale_n1(par, res["prof_y"])[0].cpu().numpy()           # [x_i ; P ; T] x K
+    compList = list(modelInput["feed"]["components"]["shell"])
+    n = len(compList)
+    dataYs = np.concatenate([full[:n], full[n + 1:n + 2]], axis=0)
+    X = np.linspace(0, modelInput["reactor"]["ReLe"], K)
+    labelList = compList + ["Temperature", "Pressure"]
+    XYList = [[X, row] for row in dataYs]                                   # `PyREMOT/library/plot.py:85-90`
+    dataList = [{"x": X, "y": row, "leg": labelList[i]} for i, row in enumerate(dataYs)]      # `:93-115`
+    return {"dataYs": dataYs, "XYList": XYList, "dataList": dataList}
+
+
 def rmtExe(modelInput, device=0):
     """Check the model input, then run it — same contract as `PyREMOT/rmt.py:21-80`."""
     try:
@@ -136,9 +164,11 @@ def rmtExe(modelInput, device=0):
         elif modelType == "N2":
             from .n2 import run_n2
             resModel = run_n2(modelInput, device=device)
+        elif modelType == "M7":
+            resModel = _run_m7(modelInput, device=device)
         else:
             raise NotImplementedError(f"model {modelType!r}: only the pseudo-homogeneous packed-bed models "
-                                      "N1 and N2 are implemented by pyremot_b200")
+                                      "N1, N2 and the dimensional steady-state model M7 are implemented by pyremot_b200")
         return {"resModel": resModel, "comTime": (time.perf_counter() - tic)*1000}
     except Exception as e:
         print(e)
@@ -164,8 +194,8 @@ def rmtExeBatch(modelInput, sweep, params=(), device=0, rtol=None, atol=None, pr
     if modelInput["model"] == "N2":
         s2 = solverSetting["N2"]
         r = model.solve_n2_host(tab, s2["zNo"], s2["tNo"], modelInput["operating-conditions"]["period"], rtol=rtol, atol=atol)
-    elif modelInput["model"] == "N1":
-        K = n_out or (solverSetting["N1"]["zNo"] + 1)
+    elif modelInput["model"] in ("N1", "M7"):
+        K = n_out or (solverSetting["N1"]["zNo"] + 1 if modelInput["model"] == "N1" else solverSetting["M9"]["zNo"])
         if not return_device:
             r = model.solve_n1_host(tab, rtol=rtol, atol=atol, n_out=K, profile=profile)
         else:

@@ -164,6 +164,16 @@ def readme_case(model="N1", process_type="non-iso-thermal", ivp="default", perio
                         CaDe=1920, CaSpHeCa=960, ivp=ivp)
 
 
+def m7_case(ivp="default", T=523.0, P=5e6, conc=None, U=50.0, Tm=523.0, mixture_viscosity=2.5105175291507334e-05):
+    """The README inputs run through the dimensional steady-state model "M7" (`PyREMOT/docs/rmtCore.py:300-309` ->
+    `pbReactor.py` runM3 `:1170`): same schema plus ``feed['mixture-viscosity']`` [Pa.s] (`:1238`; here the Wilke value of the
+    README feed) -- and ``external-heat['EfHeTrAr']`` IS used by this model (`:1545`)."""
+    mi = readme_case("N1", ivp=ivp, T=T, P=P, conc=conc, U=U, Tm=Tm)
+    mi["model"] = "M7"
+    mi["feed"]["mixture-viscosity"] = mixture_viscosity
+    return mi
+
+
 def feed_mole_fraction(H2COxRatio, CO2COxRatio, float32=False):
     """Feed composition recipe of `PyREMOT/data/initData.py:11-38`.
 

@@ -49,6 +49,14 @@
 #endif
 #define PBR_NX2 ((PBR_N2_REDUCED ? PBR_NR : PBR_NC) + (PBR_ISO ? 0 : 1))
 #define PBR_NPA (PBR_NP > 0 ? PBR_NP : 1)
+// PBR_MODEL_M7 = 1: the reference's dimensional steady-state model "M7" (rmtCore.py:300-309 -> pbReactor.py runM3 :1170,
+// modelEquationM3 :1371-1577) through the same scaled solver.  In the scaled variables c = C/Cmax, p = P/P0, theta = (T-T0)/T0,
+// z' = z/ReLe it is model N1 with four differences: the mixture viscosity and the heat-exchange area are INPUTS (:1238, :1545),
+// the Ergun density is M*Ct (rmtThermo.py:338-348) instead of the EOS density, the energy balance divides by the molar flux times
+// Cp -- dT/dz = (-sum r dH + Q)/(Ct v_s Cp_mix) (:1558, :1566), no bed-porosity factor -- and Q has no "Tm == 0 means adiabatic" switch.
+#ifndef PBR_MODEL_M7
+#define PBR_MODEL_M7 0
+#endif
 
 // Precision of the Jacobian partials.  PBR_JAC_F32=1: the rate partials (pbr_rates_jacf) and the assembly of the Jacobian in the
 // extent-coordinate evaluators run in single precision; the Newton matrix I - cJ, its LU / inverse, the residual and everything
@@ -88,7 +96,8 @@ enum {
 enum {
     IN_T = 0, IN_P, IN_VOFLRA, IN_REINDI, IN_RELE, IN_PADI, IN_BEVOFR, IN_U, IN_TM, IN_C0,
     IN_RP = IN_C0 + PBR_NC,
-    PBR_KIN = IN_RP + PBR_NP
+    IN_MUIN = IN_RP + PBR_NP, IN_AIN,                                   // model M7 only: mixture viscosity [Pa.s], EfHeTrAr [m2/m3]
+    PBR_KIN = IN_RP + PBR_NP + (PBR_MODEL_M7 ? 2 : 0)
 };
 
 struct InstPar {
@@ -182,6 +191,7 @@ PBR_DEV void pbr_prolog_one(const double* in, double* out, long N, long i) {
     }
     const double rho0 = M0*Ct0;                                        // :2796
     const double e3 = eps*eps*eps;
+    if (PBR_MODEL_M7) mumix = in[IN_MUIN];                             // pbReactor.py:1238
     out[PAR_TF*N + i] = T;
     out[PAR_PF*N + i] = P;
     out[PAR_CMAX*N + i] = Cmax;                                        // :2819-2820 "MAX"
@@ -194,8 +204,9 @@ PBR_DEV void pbr_prolog_one(const double* in, double* out, long N, long i) {
     out[PAR_RHO0*N + i] = rho0;
     out[PAR_CPMIX0*N + i] = Cpmix0;
     out[PAR_G*N + i] = (vs0/zf)*Cmax;                                  // :2821
-    out[PAR_GH*N + i] = rho0*vs0*T*(Cpmix0/M0)/zf;                     // :2823
-    out[PAR_UA*N + i] = U*(4.0/D);                                     // :2778 (input EfHeTrAr ignored)
+    out[PAR_GH*N + i] = PBR_MODEL_M7 ? T*vs0/zf                         // M7: d theta/dz' = (zf/(T0 vs0)) (-H + Q)/(Ct Cp w)
+                                     : rho0*vs0*T*(Cpmix0/M0)/zf;      // :2823
+    out[PAR_UA*N + i] = U*(PBR_MODEL_M7 ? in[IN_AIN] : 4.0/D);         // :2778 (input EfHeTrAr ignored by N1/N2, used by M7 :1545)
     out[PAR_TM*N + i] = in[IN_TM];
     out[PAR_MU*N + i] = mumix;
 #pragma unroll
@@ -261,7 +272,7 @@ PBR_DEV void pbr_point(const double* c, double T, double P, const InstPar& p, Po
             Hsum += e.r[j]*e.dH[j];
         }
         e.Hsum = Hsum;
-        e.Q = (p.Tm == 0.0) ? 0.0 : p.Ua*(p.Tm - T);                              // rmtUtility.py:424-452
+        e.Q = (!PBR_MODEL_M7 && p.Tm == 0.0) ? 0.0 : p.Ua*(p.Tm - T);             // rmtUtility.py:424-452; M7: pbReactor.py:1551
     }
     if (JAC) {
 #pragma unroll
@@ -307,14 +318,16 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
     const double w = (e.Ct*p.Pf)*pbr_rcp(p.Ct0*P);                     // :3180 v/v0 (interstitial == superficial ratio)
     const double vs = p.vs0*w;                                         // :3184
     const double zP = p.zP;                                            // :3219
-    f[n] = -(p.E1*vs + p.E2*e.rho*vs*vs)*zP;                           // :3214-3220
+    const double rhoE = PBR_MODEL_M7 ? e.M*e.Ct : e.rho;               // Ergun density: EOS (:3206) / M7: M*Ct (pbReactor.py:1483)
+    f[n] = -(p.E1*vs + p.E2*rhoE*vs*vs)*zP;                            // :3214-3220
     const double invGw = pbr_rcp(p.G*w);                               // :3283, :3288
 #pragma unroll
     for (int i = 0; i < n; ++i) f[i] = e.ri[i]*invGw;
     double Den = 1.0, fth = 0.0;
     if (!PBR_ISO) {
         const double Num = (-e.Hsum + e.Q)*p.iGH;                      // :3298
-        Den = (e.rho*p.irho0)*((e.Cpmix*p.iCp0)*p.eps)*w;              // :3284
+        Den = PBR_MODEL_M7 ? (e.Ct*e.Cpmix)*w                          // pbReactor.py:1558 (molar flux x Cp)
+                           : (e.rho*p.irho0)*((e.Cpmix*p.iCp0)*p.eps)*w;   // :3284
         fth = Num*pbr_rcp(Den);
         f[n + 1] = fth;
     }
@@ -327,7 +340,7 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
         // reciprocals once: an FP64 divide costs ~12 instructions and the columns below would need ~40 of them
         const double cmct = p.Cmax*e.invCt;
         const double iGH = p.iGH, iDen = pbr_rcp(Den), irho = pbr_rcp(e.rho), iCp = PBR_ISO ? 1.0 : pbr_rcp(e.Cpmix), ipr = pbr_rcp(pr);
-        const double dfp_dw = -zP*(p.E1*p.vs0 + 2.0*p.E2*e.rho*p.vs0*p.vs0*w);
+        const double dfp_dw = -zP*(p.E1*p.vs0 + 2.0*p.E2*rhoE*p.vs0*p.vs0*w);
         const double dfp_drho = -zP*(p.E2*vs*vs);
         const double rhoM = e.rho*pbr_rcp(e.M);
         double drk[PBR_NR], dri[PBR_NC];
@@ -337,7 +350,7 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
             pbr_dr_dc(e, p, k, 1.0, drk);
             pbr_dri(drk, dri);
             const double dw = w*cmct;
-            const double drho = rhoM*cmct*(PBR_MWK[k] - e.M);
+            const double drho = PBR_MODEL_M7 ? p.Cmax*PBR_MWK[k] : rhoM*cmct*(PBR_MWK[k] - e.M);
 #pragma unroll
             for (int i = 0; i < n; ++i) st(i, k, dri[i]*invGw - f[i]*cmct);
             st(n, k, dfp_dw*dw + dfp_drho*drho);
@@ -346,7 +359,8 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
 #pragma unroll
                 for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j];
                 const double dNum = -s*iGH;
-                const double dDen = Den*(drho*irho + cmct*(e.cpm[k] - e.Cpmix)*iCp + cmct);
+                const double dDen = PBR_MODEL_M7 ? Den*(cmct*e.cpm[k]*iCp + cmct)
+                                                 : Den*(drho*irho + cmct*(e.cpm[k] - e.Cpmix)*iCp + cmct);
                 st(n + 1, k, (dNum - fth*dDen)*iDen);
             }
         }
@@ -355,7 +369,7 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
 #pragma unroll
             for (int j = 0; j < PBR_NR; ++j) drk[j] = p.Pf*e.drP[j];
             pbr_dri(drk, dri);
-            const double dw = -w*ipr, drho = e.rho*ipr;
+            const double dw = -w*ipr, drho = PBR_MODEL_M7 ? 0.0 : e.rho*ipr;
 #pragma unroll
             for (int i = 0; i < n; ++i) st(i, n, dri[i]*invGw + f[i]*ipr);
             st(n, n, dfp_dw*dw + dfp_drho*drho);
@@ -363,7 +377,7 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
                 double s = 0.0;
 #pragma unroll
                 for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j];
-                st(n + 1, n, (-s*iGH)*iDen);                           // d(rho*w)/dp = 0
+                st(n + 1, n, (-s*iGH)*iDen + (PBR_MODEL_M7 ? fth*ipr : 0.0));   // N1: d(rho*w)/dp = 0; M7: Den ~ w ~ 1/p
             }
         }
         // ---- temperature column
@@ -371,14 +385,14 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
 #pragma unroll
             for (int j = 0; j < PBR_NR; ++j) drk[j] = p.Tf*e.drT[j];
             pbr_dri(drk, dri);
-            const double drho = -e.rho*p.Tf*pbr_rcp(T);
+            const double drho = PBR_MODEL_M7 ? 0.0 : -e.rho*p.Tf*pbr_rcp(T);
 #pragma unroll
             for (int i = 0; i < n; ++i) st(i, n + 1, dri[i]*invGw);
             st(n, n + 1, dfp_drho*drho);
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j] + p.Tf*e.r[j]*e.dHdT[j];
-            const double dQ = (p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
+            const double dQ = (!PBR_MODEL_M7 && p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
             const double dNum = (-s + dQ)*iGH;
             const double dDen = Den*(drho*irho + p.Tf*e.dCpmixT*iCp);
             st(n + 1, n + 1, (dNum - fth*dDen)*iDen);
@@ -448,14 +462,15 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
     const double w = (e.Ct*p.Pf)*pbr_rcp(p.Ct0*P);
     const double vs = p.vs0*w;
     const double zP = p.zP;
-    f[R] = -(p.E1*vs + p.E2*e.rho*vs*vs)*zP;
+    const double rhoE = PBR_MODEL_M7 ? e.M*e.Ct : e.rho;
+    f[R] = -(p.E1*vs + p.E2*rhoE*vs*vs)*zP;
     const double invGw = pbr_rcp(p.G*w);
 #pragma unroll
     for (int j = 0; j < R; ++j) f[j] = e.r[j]*invGw;                 // d x_j / dz = r_j / (G w)
     double Den = 1.0, fth = 0.0;
     if (!PBR_ISO) {
         const double Num = (-e.Hsum + e.Q)*p.iGH;
-        Den = (e.rho*p.irho0)*((e.Cpmix*p.iCp0)*p.eps)*w;
+        Den = PBR_MODEL_M7 ? (e.Ct*e.Cpmix)*w : (e.rho*p.irho0)*((e.Cpmix*p.iCp0)*p.eps)*w;
         fth = Num*pbr_rcp(Den);
         f[R + 1] = fth;
     }
@@ -475,7 +490,7 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
         const jreal invGwj = (jreal)invGw, Cpmixj = (jreal)e.Cpmix, Tfj = (jreal)p.Tf;
         const jreal cmct = Cmaxj*(jreal)e.invCt;
         const jreal iGH = (jreal)p.iGH, iDen = PBR_JRCP(Denj), irho = PBR_JRCP(rhoj), iCp = PBR_ISO ? (jreal)1 : PBR_JRCP(Cpmixj), ipr = PBR_JRCP((jreal)pr);
-        const jreal dfp_dw = (jreal)(-zP*(p.E1*p.vs0 + 2.0*p.E2*e.rho*p.vs0*p.vs0*w));
+        const jreal dfp_dw = (jreal)(-zP*(p.E1*p.vs0 + 2.0*p.E2*rhoE*p.vs0*p.vs0*w));
         const jreal dfp_drho = (jreal)(-zP*(p.E2*vs*vs));
         const jreal rhoM = rhoj*PBR_JRCP(Mj);
         jreal fj[PBR_NR], dHj[PBR_NR], drk[PBR_NR];
@@ -497,7 +512,7 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
 #pragma unroll
             for (int j = 0; j < R; ++j) drk[j] = cmct*(ax[j] - e.sx[j]*sigj) + Cmaxj*ac[j];
             const jreal dw = wj*cmct*sigj;
-            const jreal drho = rhoM*cmct*(smwj - Mj*sigj);
+            const jreal drho = PBR_MODEL_M7 ? Cmaxj*smwj : rhoM*cmct*(smwj - Mj*sigj);
 #pragma unroll
             for (int j = 0; j < R; ++j) Jx[j][jj] = drk[j]*invGwj - fj[j]*(cmct*sigj);
             Jx[R][jj] = dfp_dw*dw + dfp_drho*drho;
@@ -506,7 +521,8 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
 #pragma unroll
                 for (int j = 0; j < R; ++j) sH += drk[j]*dHj[j];
                 const jreal dNum = -sH*iGH;
-                const jreal dDen = Denj*(drho*irho + cmct*(scp - Cpmixj*sigj)*iCp + cmct*sigj);
+                const jreal dDen = PBR_MODEL_M7 ? Denj*(cmct*scp*iCp + cmct*sigj)
+                                                : Denj*(drho*irho + cmct*(scp - Cpmixj*sigj)*iCp + cmct*sigj);
                 Jx[R + (PBR_ISO ? 0 : 1)][jj] = (dNum - fthj*dDen)*iDen;
             }
         }
@@ -515,7 +531,7 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
             const jreal Pfj = (jreal)p.Pf;
 #pragma unroll
             for (int j = 0; j < R; ++j) drk[j] = Pfj*e.drP[j];
-            const jreal dw = -wj*ipr, drho = rhoj*ipr;
+            const jreal dw = -wj*ipr, drho = PBR_MODEL_M7 ? (jreal)0 : rhoj*ipr;
 #pragma unroll
             for (int j = 0; j < R; ++j) Jx[j][R] = drk[j]*invGwj + fj[j]*ipr;
             Jx[R][R] = dfp_dw*dw + dfp_drho*drho;
@@ -523,7 +539,7 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
                 jreal sH = 0;
 #pragma unroll
                 for (int j = 0; j < R; ++j) sH += drk[j]*dHj[j];
-                Jx[R + (PBR_ISO ? 0 : 1)][R] = (-sH*iGH)*iDen;
+                Jx[R + (PBR_ISO ? 0 : 1)][R] = (-sH*iGH)*iDen + (PBR_MODEL_M7 ? fthj*ipr : (jreal)0);
             }
         }
         // ---- temperature column
@@ -531,14 +547,14 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
             const int ct = R + (PBR_ISO ? 0 : 1);
 #pragma unroll
             for (int j = 0; j < R; ++j) drk[j] = Tfj*e.drT[j];
-            const jreal drho = -rhoj*Tfj*PBR_JRCP((jreal)T);
+            const jreal drho = PBR_MODEL_M7 ? (jreal)0 : -rhoj*Tfj*PBR_JRCP((jreal)T);
 #pragma unroll
             for (int j = 0; j < R; ++j) Jx[j][ct] = drk[j]*invGwj;
             Jx[R][ct] = dfp_drho*drho;
             jreal sH = 0;
 #pragma unroll
             for (int j = 0; j < R; ++j) sH += drk[j]*dHj[j] + Tfj*(jreal)e.r[j]*(jreal)e.dHdT[j];
-            const jreal dQ = (p.Tm == 0.0) ? (jreal)0 : (jreal)(-p.Ua*p.Tf);
+            const jreal dQ = (!PBR_MODEL_M7 && p.Tm == 0.0) ? (jreal)0 : (jreal)(-p.Ua*p.Tf);
             const jreal dNum = (-sH + dQ)*iGH;
             const jreal dDen = Denj*(drho*irho + Tfj*(jreal)e.dCpmixT*iCp);
             Jx[ct][ct] = (dNum - fthj*dDen)*iDen;

@@ -46,6 +46,7 @@ def lib():
         "pbr_last_error": (C.c_char_p, [vp]),
         "pbr_version": (C.c_char_p, []),
         "pbr_set_species": (i, [vp, i, i, dp, dp, dp, dp, dp, dp, i]),
+        "pbr_set_model_variant": (i, [vp, i]),
         "pbr_load_rates": (i, [vp, C.c_char_p, i, C.c_char_p, C.POINTER(C.c_char_p)]),
         "pbr_model_dims": (i, [vp] + [C.POINTER(i)]*7),
         "pbr_n1_layout": (i, [vp] + [C.POINTER(i)]*3),
@@ -77,7 +78,7 @@ def lib():
     return L
 
 
-EXPORTS = ("pbr_create pbr_destroy pbr_last_error pbr_version pbr_set_species pbr_load_rates pbr_model_dims pbr_n1_layout "
+EXPORTS = ("pbr_create pbr_destroy pbr_last_error pbr_version pbr_set_species pbr_set_model_variant pbr_load_rates pbr_model_dims pbr_n1_layout "
            "pbr_model_source pbr_model_cubin pbr_kernel_attr pbr_prolog pbr_rhs_n1 pbr_jac_n1 pbr_rhs_n2 pbr_solve_n1 "
            "pbr_unscale_n1 pbr_solve_n1_sens pbr_unscale_sens_n1 pbr_solve_n1_host pbr_solve_n2 pbr_solve_n2_resume pbr_unscale_n2 pbr_solve_n2_host pbr_solve_n2_host_resume "
            "pbr_math_probe pbr_fp64_peak pbr_launch_count").split()
@@ -127,7 +128,7 @@ class Model:
     ``params``: names of scalar VARS entries that become per-instance runtime parameters.
     """
 
-    def __init__(self, modelInput, params=(), device=0, cache_dir=CACHE_DIR):
+    def __init__(self, modelInput, params=(), device=0, cache_dir=CACHE_DIR, variant=None):
         L = lib()
         comps = list(modelInput["feed"]["components"]["shell"])
         for s in comps:
@@ -152,6 +153,10 @@ class Model:
         dh, p_dh = _arr(self.dH25)
         dc, p_dc = _arr(self.dcp)
         self._check(L.pbr_set_species(self._ctx, self.n, self.S.shape[0], p_mw, p_cp, p_vis, p_s, p_dh, p_dc, int(self.iso)))
+        # "M7": the dimensional steady-state model (`PyREMOT/docs/rmtCore.py:300-309`), solved through the N1 kernels
+        self.variant = (modelInput.get("model") if variant is None else variant)
+        self.variant = "M7" if self.variant == "M7" else "N"
+        self._check(L.pbr_set_model_variant(self._ctx, 1 if self.variant == "M7" else 0))
         if cache_dir:
             os.makedirs(cache_dir, exist_ok=True)
         log = C.c_char_p()
@@ -221,6 +226,9 @@ class Model:
         t[:, 9:9 + self.n] = np.asarray(sweep.pop("conc", fe["concentration"]), dtype=np.float64)
         for k, name in enumerate(self.params):
             t[:, 9 + self.n + k] = sweep.pop("VARS:" + name, self.rates.param_defaults[k])
+        if self.variant == "M7":          # `pbReactor.py:1238`, `:1545`: both are inputs of that model
+            t[:, 9 + self.n + len(self.params)] = sweep.pop("GaMiVi", fe["mixture-viscosity"])
+            t[:, 10 + self.n + len(self.params)] = sweep.pop("EfHeTrAr", eh["EfHeTrAr"])
         if sweep:
             raise KeyError(f"unknown sweep keys {sorted(sweep)} (rate parameters must be listed in params=)")
         return t

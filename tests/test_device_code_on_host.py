@@ -278,3 +278,55 @@ def test_forward_sensitivities_vs_central_differences():
             assert np.abs(S[k] - J[k]).max() < tol*scale, (rtol, k, np.abs(S[k] - J[k]).max()/scale)
         if rtol == 1e-9:                     # the sensitivities take no part in the error test: same steps, same outlet
             assert np.array_equal(stats[0][:N], plain[2][0]) and np.allclose(out[:, :N], plain[0][1], rtol=1e-11, atol=0)
+
+
+def test_m7_dimensional_model_vs_reference_golden(golden):
+    """the dimensional steady-state model "M7" (`rmtCore.py:300-309` -> `pbReactor.py` modelEquationM3 `:1371-1577`)
+    as a variant of the scaled N1 evaluators: RHS against 200 reference states, analytic Jacobians (full and extent coordinates)
+    against central differences, and the BDF solve against the reference's converged rmtExe("M7") profile."""
+    g = golden("m7")
+    mi = cases.m7_case()
+    m = engine.Model(mi, device=None)
+    assert m.variant == "M7" and m.k_in == 9 + 6 + 2
+    hs = HostSim(m)
+    Y, F = g["rhs_y"], g["rhs_f"]                       # dimensional [C_i, T, P]
+    K = len(Y)
+    par = hs.prolog(m.instance_table(mi, N=K))
+    Cmax, T0, P0, zf = par[2], par[0], par[1], par[6]
+    y = np.concatenate([Y[:, :6].T/Cmax, (Y[:, 7]/P0)[None], ((Y[:, 6] - T0)/T0)[None]])       # scaled [c, p, theta]
+    f = hs.rhs_n1(par, y)
+    fd = np.concatenate([(f[:6]*Cmax/zf).T, (f[7]*T0/zf)[:, None], (f[6]*P0/zf)[:, None]], axis=1)
+    assert relerr(fd, F, floor=1e-300) < 1e-11
+    # Jacobians of the variant's formulas
+    f2, J = hs.jac_n1(par, y)
+    for k in range(8):
+        h = 1e-6*np.maximum(np.abs(y[k]), 1e-3)
+        yp, ym = y.copy(), y.copy()
+        yp[k] += h
+        ym[k] -= h
+        col = (hs.rhs_n1(par, yp) - hs.rhs_n1(par, ym))/(2*h)
+        scale = np.abs(J).max(axis=(0, 1)) + 1e-300
+        assert np.max(np.abs(J[:, k] - col)/scale) < 1e-6, k
+    # solve: README case through M7, 30 output points (solverSetting['M9']['zNo'])
+    par1 = hs.prolog(m.instance_table(mi))
+    prof, st, stats = hs.solve_n1(par1, rtol=1e-9, atol=1e-13, n_out=30)
+    assert st[0] == 0
+    C = prof[:, :6, 0]*par1[2]
+    data = np.concatenate([(C/C.sum(axis=1, keepdims=True)).T, (prof[:, 7, 0]*par1[0] + par1[0])[None]])
+    assert relerr(data, g["conv_dataYs"]) < 1e-6
+    assert relerr(data, g["default_dataYs"]) < 2e-3                  # the reference's own default-tolerance run
+    ens = O.Ensemble(mi)
+    assert relerr(ens.rhs_m7(Y), F, floor=1e-300) < 1e-12           # the oracle restatement against the same reference states
+    # extent coordinates (what K2 integrates): f = M f_x and M J_x = J M for the variant's formulas as well
+    nx, R = hs.L.hs_nx(), m.n_rxn
+    rows = cases.ensemble_rows(8)
+    par8 = hs.prolog(m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}))
+    rng = np.random.default_rng(1)
+    x = np.zeros((nx, 8))
+    x[:R] = rng.uniform(0, 0.02, (R, 8)); x[R] = rng.uniform(0.8, 1, 8); x[R + 1] = rng.uniform(0, 0.1, 8)
+    yx, fx, Jx = hs.n1x(par8, x)
+    ff, JJ = hs.jac_n1(par8, yx)
+    M = _extent_map(m, hs.nv1, nx)
+    assert relerr(M @ fx, ff, floor=1e-300) < 1e-12
+    for i in range(8):
+        assert np.max(np.abs(M @ Jx[:, :, i] - JJ[:, :, i] @ M)) < 1e-12*np.max(np.abs(JJ[:, :, i]))

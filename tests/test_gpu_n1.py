@@ -401,3 +401,24 @@ def test_parameter_estimation_forward_sensitivities(torch_cuda):
             assert dev < 2e-5*scale + floor, (i, k, dev, scale, floor)
             assert abs(J[i, 7, k] - Jref[b, 7]) < 2e-5*abs(Jref[b, 7]) + 2e-13*base[i, 7]/(2*rel*cases.MEOH_DME_THETA[name])
     print(f"\nforward sensitivities vs oracle central differences: worst deviation {worst:.2f} of the allowed band (2e-5 relative)")
+
+
+def test_rmtExe_m7_matches_converged_reference(torch_cuda, golden):
+    """rmtExe with model "M7" (dimensional steady-state balances, `rmtCore.py:300-309` -> `pbReactor.py:1170`) on the
+    GPU: result layout of the reference (dataYs = [x_i ; T] over 30 points, XYList, dataList), profile within 1e-6 of the
+    reference's converged run; an 8-row sweep through rmtExeBatch against reference-made converged profiles."""
+    from pyremot_b200 import rmtExe, rmtExeBatch
+    g = golden("m7")
+    res = rmtExe(cases.m7_case())["resModel"]
+    assert set(res) == {"dataYs", "XYList", "dataList"} and res["dataYs"].shape == (7, 30)
+    assert [d["leg"] for d in res["dataList"]] == list(g["default_legs"]) and len(res["XYList"]) == 7
+    assert np.allclose(res["XYList"][0][0], g["default_X"]) and np.array_equal(res["dataList"][3]["y"], res["dataYs"][3])
+    assert relerr(res["dataYs"], g["conv_dataYs"]) < RTOL_SOLVE
+    assert relerr(res["dataYs"], g["default_dataYs"]) < 2e-3
+    rows = cases.ensemble_rows(8)
+    out = rmtExeBatch(cases.m7_case(), {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}, profile=True)
+    assert (out["status"] == 0).all() and out["dataYs"].shape == (8, 8, 30)
+    got = np.concatenate([out["dataYs"][:, :6], out["dataYs"][:, 7:8]], axis=1)      # [x_i ; T] (the batch entry keeps the P row)
+    err = relerr(got, g["sweep_conv_dataYs"])
+    print(f"\nM7: 8 swept profiles vs the reference's converged runs: worst rel. error {err:.2e}")
+    assert err < RTOL_SOLVE
