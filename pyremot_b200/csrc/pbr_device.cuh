@@ -1998,6 +1998,39 @@ extern "C" __global__ void __launch_bounds__(256) pbr_k5_unscale_n1(long N, int 
     if (!PBR_ISO) { const double th = y[((long)k*PBR_NV1 + PBR_NC + (PBR_ISO ? 0 : 1))*N + i]; o[(long)(PBR_NC + 1)*K] = th*Tf + Tf; }
 }
 
+// ---- K4: fused N2 solver. Persistent warps: warp g handles instances g, g+G, ... with its own scratch slab.
+extern "C" __global__ void __launch_bounds__(128) pbr_k4_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+                                                                  double rtol, double atol, int max_steps, double* __restrict__ work,
+                                                                  double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
+                                                                  const double* __restrict__ iv, int k_first, int flags) {
+    extern __shared__ double pbr_smem[];
+    const long gw = ((long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const long G = ((long)gridDim.x*blockDim.x) >> 5;
+    WarpCtx w; w.lane = threadIdx.x & 31;
+    w.tile = pbr_smem + (long)(threadIdx.x >> 5)*PBR_N2_TILE_ROWS*32;
+    const N2Ws ws = {work + gw*(long)PBR_N2_WS_ROWS*zNo, zNo};
+    for (long inst = gw; inst < N; inst += G) {
+        InstPar p; pbr_load_par(par, N, inst, p);
+        N2Stats st;
+        const int rc = pbr_n2_solve(w, p, ws, tNo, period, rtol, atol, max_steps, snaps + inst*(long)(tNo - k_first)*PBR_NV2*zNo, st,
+                                    iv ? iv + inst*(long)PBR_NV2*zNo : (const double*)0, k_first, flags);
+        if (w.lane == 0) {
+            status[inst] = rc;
+            if (stats) { stats[0*N + inst] = st.nsteps; stats[1*N + inst] = st.nrej + st.nfail; stats[2*N + inst] = st.nfev; stats[3*N + inst] = st.nlu; }
+        }
+        __syncwarp();
+    }
+}
+
+#endif  // !PBR_HOST (kernels K2, K3, K4)
+
+// The block-per-reactor N2 solver also compiles for the host when PBR_HOST_SIMT is defined: tests/hostsim/simt.h supplies
+// threadIdx/blockDim, __syncthreads and the warp shuffles on top of one fiber per thread, so the kernel body below -- marches,
+// scans, reductions and all -- runs unmodified on the CPU-only build container (test infrastructure, never shipped).
+#if !defined(PBR_HOST) || defined(PBR_HOST_SIMT)
+#ifndef PBR_SHARED
+#define PBR_SHARED __shared__
+#endif
 // ---- K3: fused N2 RHS.  Y, dYdt: [N][NV2][zNo] (the reference's var-major flatten, :3873).
 //      A block of 128 threads owns G consecutive reactors and walks their G*zNo nodes in flattened order, one node
 //      per thread per round, so consecutive lanes touch consecutive nodes (coalesced) and no lane idles on ragged
@@ -2014,8 +2047,8 @@ extern "C" __global__ void __launch_bounds__(256) pbr_k5_unscale_n1(long N, int 
 #define PBR_K3_SPAR (PBR_KPAR + 7)      // staged constants per reactor: the table rows + the derived reciprocals
 extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n2(long N, int zNo, int G, const double* __restrict__ par,
                                                                                   const double* __restrict__ Y, double* __restrict__ dY) {
-    __shared__ double s_par[PBR_K3_MAXG*PBR_K3_SPAR];
-    __shared__ double s_wa[2][4], s_wb[2][4];             // warp totals of the scan, double-buffered by round parity
+    PBR_SHARED double s_par[PBR_K3_MAXG*PBR_K3_SPAR];
+    PBR_SHARED double s_wa[2][4], s_wb[2][4];             // warp totals of the scan, double-buffered by round parity
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long g0 = (long)blockIdx.x*G;
     const int Gb = (int)((N - g0 < G) ? (N - g0) : G);                // reactors in this block
@@ -2107,36 +2140,6 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
     }
 }
 
-// ---- K4: fused N2 solver. Persistent warps: warp g handles instances g, g+G, ... with its own scratch slab.
-extern "C" __global__ void __launch_bounds__(128) pbr_k4_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
-                                                                  double rtol, double atol, int max_steps, double* __restrict__ work,
-                                                                  double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
-                                                                  const double* __restrict__ iv, int k_first, int flags) {
-    extern __shared__ double pbr_smem[];
-    const long gw = ((long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-    const long G = ((long)gridDim.x*blockDim.x) >> 5;
-    WarpCtx w; w.lane = threadIdx.x & 31;
-    w.tile = pbr_smem + (long)(threadIdx.x >> 5)*PBR_N2_TILE_ROWS*32;
-    const N2Ws ws = {work + gw*(long)PBR_N2_WS_ROWS*zNo, zNo};
-    for (long inst = gw; inst < N; inst += G) {
-        InstPar p; pbr_load_par(par, N, inst, p);
-        N2Stats st;
-        const int rc = pbr_n2_solve(w, p, ws, tNo, period, rtol, atol, max_steps, snaps + inst*(long)(tNo - k_first)*PBR_NV2*zNo, st,
-                                    iv ? iv + inst*(long)PBR_NV2*zNo : (const double*)0, k_first, flags);
-        if (w.lane == 0) {
-            status[inst] = rc;
-            if (stats) { stats[0*N + inst] = st.nsteps; stats[1*N + inst] = st.nrej + st.nfail; stats[2*N + inst] = st.nfev; stats[3*N + inst] = st.nlu; }
-        }
-        __syncwarp();
-    }
-}
-
-#endif  // !PBR_HOST (kernels K2, K3, K4)
-
-// The block-per-reactor N2 solver also compiles for the host when PBR_HOST_SIMT is defined: tests/hostsim/simt.h supplies
-// threadIdx/blockDim, __syncthreads and the warp shuffles on top of one fiber per thread, so the kernel body below -- marches,
-// scans, reductions and all -- runs unmodified on the CPU-only build container (test infrastructure, never shipped).
-#if !defined(PBR_HOST) || defined(PBR_HOST_SIMT)
 // ---- K4b: fused N2 solver, ONE BLOCK PER REACTOR, ONE THREAD PER AXIAL NODE, all integrator state on chip.
 //      Used when the reactor's working set fits shared memory (119*zNo doubles: zNo <= ~230); larger grids use K4.
 //      Shared memory (element e of node z at base[e*zNo + z], conflict-free): BDF history D[7][NV2], inverse of the

@@ -40,6 +40,25 @@ class SimtSim:
         self.L = _build(model.source, "simt_driver.cpp", extra=("simt.h",))
         self.nv2 = model.nv2
 
+    def set_order(self, mode, seed=0):
+        """Thread resume order inside a scheduling round: 0 ascending, 1 descending, 2 random per round (race check)."""
+        self.L.hs_simt_set_order(C.c_int(mode), C.c_ulonglong(seed))
+
+    def race_demo(self, racy):
+        out = np.zeros(64)
+        self.L.hs_simt_race_demo(C.c_int(int(racy)), HostSim._p(out))
+        return out
+
+    def rhs_n2(self, par, Y, G):
+        """K3 through the emulator; G reactors per 128-thread block."""
+        par = np.ascontiguousarray(par, dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        N, nv, zNo = Y.shape
+        dY = np.zeros_like(Y)
+        p = HostSim._p
+        self.L.hs_simt_rhs_n2(C.c_long(N), C.c_int(zNo), C.c_int(G), p(par), p(Y), p(dY))
+        return dY
+
     def solve_n2(self, kernel, par, zNo, tNo, period, rtol=1e-9, atol=1e-13, max_steps=50000, grid=None, iv=None, k_first=0,
                  flags=0):
         par = np.ascontiguousarray(par, dtype=np.float64)

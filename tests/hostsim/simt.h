@@ -25,6 +25,23 @@ static ucontext_t sched_ctx;
 static int cur = -1, nthreads = 0;
 static SimtDim3 block_idx = {0, 0, 0}, block_dim = {1, 1, 1}, grid_dim = {1, 1, 1};
 static double slots[64][32];                      // per warp: the values being shuffled
+// Order in which runnable threads are resumed inside one scheduling round: 0 ascending, 1 descending, 2 a fresh pseudo-random
+// permutation per round.  A data race -- two threads touching the same shared/global location, one of them writing, with no
+// barrier or warp synchronisation in between -- makes the result depend on this order; the tests run every block kernel under
+// all three and demand bit-identical results (the pool's compute-sanitizer is closed, this is the race check we can run).
+static int order_mode = 0;
+static unsigned long long order_state = 88172645463325252ull;
+static std::vector<int> perm;
+static void next_perm() {
+    perm.resize(nthreads);
+    for (int t = 0; t < nthreads; ++t) perm[t] = order_mode == 1 ? nthreads - 1 - t : t;
+    if (order_mode == 2)
+        for (int t = nthreads - 1; t > 0; --t) {
+            order_state ^= order_state << 13; order_state ^= order_state >> 7; order_state ^= order_state << 17;
+            const int j = (int)(order_state % (unsigned long long)(t + 1));
+            const int tmp = perm[t]; perm[t] = perm[j]; perm[j] = tmp;
+        }
+}
 static std::function<void()>* body = nullptr;
 
 static void trampoline() { (*body)(); fibers[cur].state = DONE; swapcontext(&fibers[cur].ctx, &sched_ctx); }
@@ -46,8 +63,11 @@ static void run_block(std::function<void()> f) {
     }
     for (;;) {
         bool progressed = false;
-        for (int t = 0; t < nthreads; ++t)
+        next_perm();
+        for (int q = 0; q < nthreads; ++q) {
+            const int t = perm[q];
             if (fibers[t].state == RUN) { cur = t; swapcontext(&sched_ctx, &fibers[t].ctx); progressed = true; }
+        }
         // release complete warps
         for (int w = 0; w < nthreads/32; ++w) {
             int at = 0;
@@ -81,7 +101,8 @@ static inline SimtDim3 simt_thread_idx() { return SimtDim3{(unsigned)simt::cur, 
 #define __device__
 #define __forceinline__ inline
 #define __noinline__
-#define __shared__            /* only `extern __shared__ double pbr_smem[]` is used: the driver defines the array */
+#define __shared__            /* `extern __shared__ double pbr_smem[]`: the driver defines the array; static shared arrays use PBR_SHARED */
+#define PBR_SHARED static     /* one block runs at a time, so a function-local static IS the block's shared array */
 #define __launch_bounds__(...)
 
 static inline void __syncthreads() { simt::yield(simt::AT_BLOCK); }

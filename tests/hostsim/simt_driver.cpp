@@ -28,6 +28,26 @@ void hs_simt_eval(int zNo, const double* par, const double* x, double* f) {
     });
 }
 
+void hs_simt_set_order(int mode, unsigned long long seed) { simt::order_mode = mode; if (seed) simt::order_state = seed; }
+
+// Negative control of the race check: thread t publishes a value and reads its neighbour's WITHOUT a barrier in between
+// (racy == 1) or with one (racy == 0).  Under different resume orders the racy version must give different results.
+void hs_simt_race_demo(int racy, double* out) {
+    simt::launch(1, 64, [&]() {
+        const int t = threadIdx.x;
+        pbr_smem[t] = 0.0;
+        __syncthreads();
+        pbr_smem[t] = 1.0 + t;
+        if (!racy) __syncthreads();
+        out[t] = pbr_smem[(t + 1) % 64];
+    });
+}
+
+// K3 (the fused N2 RHS kernel) on the emulator: 128-thread blocks owning G reactors each
+void hs_simt_rhs_n2(long N, int zNo, int G, const double* par, const double* Y, double* dY) {
+    simt::launch((unsigned)((N + G - 1)/G), 128, [&]() { pbr_k3_rhs_n2(N, zNo, G, par, Y, dY); });
+}
+
 // kernel: 0 = pbr_k4b_solve_n2, 1 = pbr_k4bs_solve_n2, 2 = pbr_k4c_solve_n2, 3 = pbr_k4d_solve_n2.  par [KPAR][N]; snaps [N][tNo][NV2][zNo];
 // stats [4][N].  grid < N exercises the kernels' loop over instances.  iv (or NULL) [N][NV2][zNo], k_first, flags: resume arguments
 // (snaps then holds tNo - k_first interval ends per instance).

@@ -330,3 +330,52 @@ def test_m7_dimensional_model_vs_reference_golden(golden):
     assert relerr(M @ fx, ff, floor=1e-300) < 1e-12
     for i in range(8):
         assert np.max(np.abs(M @ Jx[:, :, i] - JJ[:, :, i] @ M)) < 1e-12*np.max(np.abs(JJ[:, :, i]))
+
+
+def test_block_kernels_do_not_depend_on_the_thread_schedule():
+    """Race check (compute-sanitizer is closed on the GPU pool): the emulator resumes the threads of a block in ascending,
+    descending and per-round random order.  A shared-memory race -- a read and a write of the same location with no barrier or
+    warp synchronisation in between -- makes the result depend on that order; every block kernel of the N2 path (serial march,
+    scan march, slab history, on-chip 512-thread variant, resume projection) and K3 (block scan with double-buffered totals, one
+    barrier per round) must give bit-identical results under all three."""
+    mi, m, hs, sim = _simt_case(lambda: cases.readme_case("N2"))
+    rows = cases.ensemble_rows(3)
+    par = hs.prolog(m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}))
+    zNo, tNo, period = 40, 2, 0.02
+    rng = np.random.default_rng(2)
+    Y = np.zeros((3, m.nv2, 45))
+    Y[:, :6] = par[16:22].T[:, :, None]*np.exp(rng.normal(0, 0.2, (3, 6, 45)))
+    Y[:, 6] = rng.uniform(0, 0.2, (3, 45))
+    ref_rhs = hs.rhs_n2(par, Y)
+    base = {}
+    try:
+        # negative control: the check must see a real race (a neighbour exchange without a barrier) and pass its fixed version
+        demo = {}
+        for mode in (0, 1, 2):
+            sim.set_order(mode, seed=99)
+            demo[mode] = (sim.race_demo(True), sim.race_demo(False))
+        assert not np.array_equal(demo[0][0], demo[1][0]) and not np.array_equal(demo[0][0], demo[2][0])
+        assert np.array_equal(demo[0][1], demo[1][1]) and np.array_equal(demo[0][1], demo[2][1])
+        for mode in (0, 1, 2):
+            sim.set_order(mode, seed=12345 + mode)
+            for kernel in ("pbr_k4b_solve_n2", "pbr_k4bs_solve_n2", "pbr_k4c_solve_n2", "pbr_k4d_solve_n2"):
+                snaps, status, stats = sim.solve_n2(kernel, par, zNo, tNo, period, grid=2)
+                assert (status == 0).all()
+                if mode == 0:
+                    base[kernel] = (snaps, stats)
+                else:
+                    assert np.array_equal(snaps, base[kernel][0]) and np.array_equal(stats, base[kernel][1]), (kernel, mode)
+            tail, st, _ = sim.solve_n2("pbr_k4b_solve_n2", par, zNo, tNo, period, iv=base["pbr_k4b_solve_n2"][0][:, 0], k_first=1)
+            if mode == 0:
+                base["resume"] = tail
+            else:
+                assert np.array_equal(tail, base["resume"]), mode
+            for G in (1, 3):                                   # 45 nodes per reactor: ragged rounds, several reactors per block
+                dY = sim.rhs_n2(par, Y, G)
+                assert relerr(dY, ref_rhs, floor=1e-12) < 1e-12, (mode, G)
+                if mode == 0:
+                    base[("k3", G)] = dY
+                else:
+                    assert np.array_equal(dY, base[("k3", G)]), (mode, G)
+    finally:
+        sim.set_order(0)

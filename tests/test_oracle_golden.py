@@ -88,3 +88,18 @@ def test_n2_rhs_vs_reference(golden, tag, mk, zNo):
         assert np.allclose(f[0][:, 0], [-1.8481007150019408, -1.0894938433835588, 2.1453598702699304,
                                         0.7101904075743676, -1.7324286179635533, 1.0558660268863722,
                                         0.5319153449678685], rtol=1e-10)
+
+
+def test_m7_oracle_vs_reference(golden):
+    """Dimensional steady-state model M7: the oracle's restatement of modelEquationM3 (`pbReactor.py:1371-1577`) against 200
+    reference states, and its SciPy solve against the reference's converged rmtExe("M7") profile and 2 swept rows."""
+    g = golden("m7")
+    ens = O.Ensemble(cases.m7_case(), N=len(g["rhs_y"]))
+    f = ens.rhs_m7(g["rhs_y"])
+    assert np.max(np.abs(f - g["rhs_f"])/(np.abs(g["rhs_f"]) + 1e-300)) < 1e-12
+    _, data, _ = O.solve_m7(O.Ensemble(cases.m7_case()), method="LSODA", rtol=1e-12, atol=1e-12)
+    assert np.max(np.abs(data[0] - g["conv_dataYs"])/np.abs(g["conv_dataYs"])) < 1e-8
+    rows = cases.ensemble_rows(8)
+    sw = {"T": rows["T"][:2], "P": rows["P"][:2], "conc": rows["conc"][:2], "Tm": rows["T"][:2]}
+    _, data, _ = O.solve_m7(O.Ensemble(cases.m7_case(), sw), method="LSODA", rtol=1e-12, atol=1e-12)
+    assert np.max(np.abs(data - g["sweep_conv_dataYs"][:2])/np.abs(g["sweep_conv_dataYs"][:2])) < 1e-8
