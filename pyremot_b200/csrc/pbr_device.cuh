@@ -2045,13 +2045,42 @@ extern "C" __global__ void __launch_bounds__(128) pbr_k4_solve_n2(long N, int zN
 #endif
 #define PBR_K3_MAXG 16
 #define PBR_K3_SPAR (PBR_KPAR + 7)      // staged constants per reactor: the table rows + the derived reciprocals
+//      staged != 0: the block first copies the state of its G reactors (one contiguous piece of Y) into shared memory with
+//      16-byte asynchronous copies (cp.async, no register staging) while the per-reactor constants are being staged, and every
+//      node -- and its upstream neighbour -- is then read from the tile: the HBM latency is paid once per block instead of once per
+//      round (ncu round 2: long-scoreboard 1.0 cycles per issue with per-round global loads), and the stencil needs no second
+//      global read.  The launcher stages whenever the tile of G reactors fits a quarter of an SM's shared memory.
+PBR_DEV void pbr_k3_stage(double* tile, const double* __restrict__ src, int cnt, int tid) {
+#if defined(PBR_HOST)
+    for (int k = tid; k < cnt; k += 128) tile[k] = src[k];
+#else
+    if (((((unsigned long long)src) & 15ull) == 0ull) && (cnt & 1) == 0) {
+        for (int k = 2*tid; k < cnt; k += 256) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(tile + k);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src + k) : "memory");
+        }
+    } else {
+        for (int k = tid; k < cnt; k += 128) tile[k] = src[k];
+    }
+#endif
+}
+PBR_DEV void pbr_k3_stage_wait() {
+#if !defined(PBR_HOST)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n2(long N, int zNo, int G, const double* __restrict__ par,
-                                                                                  const double* __restrict__ Y, double* __restrict__ dY) {
+                                                                                  const double* __restrict__ Y, double* __restrict__ dY,
+                                                                                  int staged) {
+    extern __shared__ double pbr_smem[];
     PBR_SHARED double s_par[PBR_K3_MAXG*PBR_K3_SPAR];
     PBR_SHARED double s_wa[2][4], s_wb[2][4];             // warp totals of the scan, double-buffered by round parity
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long g0 = (long)blockIdx.x*G;
     const int Gb = (int)((N - g0 < G) ? (N - g0) : G);                // reactors in this block
+    double* tile = pbr_smem;                                           // [Gb][NV2][zNo] when staged
+    if (staged) pbr_k3_stage(tile, Y + g0*(long)PBR_NV2*zNo, Gb*PBR_NV2*zNo, tid);
     for (int k = tid; k < Gb*PBR_KPAR; k += 128) { const int g = k / PBR_KPAR, r = k % PBR_KPAR; s_par[g*PBR_K3_SPAR + r] = par[(long)r*N + g0 + g]; }
     __syncthreads();
     if (tid < Gb) {                                                    // derived reciprocals once per reactor
@@ -2063,6 +2092,7 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
         sp[PBR_KPAR + 0] = q.iG; sp[PBR_KPAR + 1] = q.iGH; sp[PBR_KPAR + 2] = q.irho0; sp[PBR_KPAR + 3] = q.iCp0;
         sp[PBR_KPAR + 4] = q.F1; sp[PBR_KPAR + 5] = q.zP; sp[PBR_KPAR + 6] = q.vz;
     }
+    if (staged) pbr_k3_stage_wait();
     __syncthreads();
     const double dz = 1.0/(double)(zNo - 1), inv_dz = (double)(zNo - 1);   // :3439
     const int total = Gb*zNo;
@@ -2079,7 +2109,7 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
         // Only what the pressure map needs is read before the scan; everything else is read from shared memory AFTER the scan's
         // last barrier (loads cannot move across a barrier, so values read up here would sit in registers through the scan:
         // round 1 held all 35 staged constants = 70 registers and spilled at the 128-register cap).
-        const double* Yi = Y + (g0 + g)*(long)PBR_NV2*zNo;
+        const double* Yi = staged ? tile + (long)g*PBR_NV2*zNo : Y + (g0 + g)*(long)PBR_NV2*zNo;
         double yc[PBR_NV2], yb[PBR_NV2];
 #pragma unroll
         for (int v = 0; v < PBR_NV2; ++v) {

@@ -49,14 +49,14 @@ class SimtSim:
         self.L.hs_simt_race_demo(C.c_int(int(racy)), HostSim._p(out))
         return out
 
-    def rhs_n2(self, par, Y, G):
-        """K3 through the emulator; G reactors per 128-thread block."""
+    def rhs_n2(self, par, Y, G, staged=1):
+        """K3 through the emulator; G reactors per 128-thread block; staged: state tile in shared memory."""
         par = np.ascontiguousarray(par, dtype=np.float64)
         Y = np.ascontiguousarray(Y, dtype=np.float64)
         N, nv, zNo = Y.shape
         dY = np.zeros_like(Y)
         p = HostSim._p
-        self.L.hs_simt_rhs_n2(C.c_long(N), C.c_int(zNo), C.c_int(G), p(par), p(Y), p(dY))
+        self.L.hs_simt_rhs_n2(C.c_long(N), C.c_int(zNo), C.c_int(G), p(par), p(Y), p(dY), C.c_int(staged))
         return dY
 
     def solve_n2(self, kernel, par, zNo, tNo, period, rtol=1e-9, atol=1e-13, max_steps=50000, grid=None, iv=None, k_first=0,

@@ -44,8 +44,8 @@ void hs_simt_race_demo(int racy, double* out) {
 }
 
 // K3 (the fused N2 RHS kernel) on the emulator: 128-thread blocks owning G reactors each
-void hs_simt_rhs_n2(long N, int zNo, int G, const double* par, const double* Y, double* dY) {
-    simt::launch((unsigned)((N + G - 1)/G), 128, [&]() { pbr_k3_rhs_n2(N, zNo, G, par, Y, dY); });
+void hs_simt_rhs_n2(long N, int zNo, int G, const double* par, const double* Y, double* dY, int staged) {
+    simt::launch((unsigned)((N + G - 1)/G), 128, [&]() { pbr_k3_rhs_n2(N, zNo, G, par, Y, dY, staged); });
 }
 
 // kernel: 0 = pbr_k4b_solve_n2, 1 = pbr_k4bs_solve_n2, 2 = pbr_k4c_solve_n2, 3 = pbr_k4d_solve_n2.  par [KPAR][N]; snaps [N][tNo][NV2][zNo];

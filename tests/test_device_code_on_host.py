@@ -341,7 +341,7 @@ def test_block_kernels_do_not_depend_on_the_thread_schedule():
     mi, m, hs, sim = _simt_case(lambda: cases.readme_case("N2"))
     rows = cases.ensemble_rows(3)
     par = hs.prolog(m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}))
-    zNo, tNo, period = 40, 2, 0.02
+    zNo, tNo, period = 40, 2, 0.01
     rng = np.random.default_rng(2)
     Y = np.zeros((3, m.nv2, 45))
     Y[:, :6] = par[16:22].T[:, :, None]*np.exp(rng.normal(0, 0.2, (3, 6, 45)))
@@ -370,12 +370,12 @@ def test_block_kernels_do_not_depend_on_the_thread_schedule():
                 base["resume"] = tail
             else:
                 assert np.array_equal(tail, base["resume"]), mode
-            for G in (1, 3):                                   # 45 nodes per reactor: ragged rounds, several reactors per block
-                dY = sim.rhs_n2(par, Y, G)
-                assert relerr(dY, ref_rhs, floor=1e-12) < 1e-12, (mode, G)
+            for G, staged in ((1, 1), (3, 1), (3, 0)):         # 45 nodes per reactor: ragged rounds, several reactors per block
+                dY = sim.rhs_n2(par, Y, G, staged)
+                assert relerr(dY, ref_rhs, floor=1e-12) < 1e-12, (mode, G, staged)
                 if mode == 0:
-                    base[("k3", G)] = dY
+                    base[("k3", G, staged)] = dY
                 else:
-                    assert np.array_equal(dY, base[("k3", G)]), (mode, G)
+                    assert np.array_equal(dY, base[("k3", G, staged)]), (mode, G, staged)
     finally:
         sim.set_order(0)
