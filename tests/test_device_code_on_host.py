@@ -341,7 +341,7 @@ def test_block_kernels_do_not_depend_on_the_thread_schedule():
     mi, m, hs, sim = _simt_case(lambda: cases.readme_case("N2"))
     rows = cases.ensemble_rows(3)
     par = hs.prolog(m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}))
-    zNo, tNo, period = 40, 2, 0.01
+    zNo, tNo, period = 40, 2, 0.004
     rng = np.random.default_rng(2)
     Y = np.zeros((3, m.nv2, 45))
     Y[:, :6] = par[16:22].T[:, :, None]*np.exp(rng.normal(0, 0.2, (3, 6, 45)))
@@ -359,13 +359,15 @@ def test_block_kernels_do_not_depend_on_the_thread_schedule():
         for mode in (0, 1, 2):
             sim.set_order(mode, seed=12345 + mode)
             for kernel in ("pbr_k4b_solve_n2", "pbr_k4bs_solve_n2", "pbr_k4c_solve_n2", "pbr_k4d_solve_n2"):
-                snaps, status, stats = sim.solve_n2(kernel, par, zNo, tNo, period, grid=2)
+                if mode == 1 and kernel in ("pbr_k4c_solve_n2", "pbr_k4d_solve_n2"):
+                    continue                                   # same body as the first two (template flags); modes 0 and 2 cover them
+                snaps, status, stats = sim.solve_n2(kernel, par[:, :2], zNo, tNo, period, grid=1)
                 assert (status == 0).all()
                 if mode == 0:
                     base[kernel] = (snaps, stats)
                 else:
                     assert np.array_equal(snaps, base[kernel][0]) and np.array_equal(stats, base[kernel][1]), (kernel, mode)
-            tail, st, _ = sim.solve_n2("pbr_k4b_solve_n2", par, zNo, tNo, period, iv=base["pbr_k4b_solve_n2"][0][:, 0], k_first=1)
+            tail, st, _ = sim.solve_n2("pbr_k4b_solve_n2", par[:, :2], zNo, tNo, period, iv=base["pbr_k4b_solve_n2"][0][:, 0], k_first=1)
             if mode == 0:
                 base["resume"] = tail
             else:
