@@ -81,9 +81,16 @@ def solve_n1_sharded(modelInput, sweep, params=(), rtol=None, atol=None, balance
     mine = perm[lo:hi]
     local_sweep = {k: np.asarray(v)[mine] for k, v in sweep.items()}
     dev = torch.cuda.current_device() if device is None else device
-    r = rmtExeBatch(modelInput, local_sweep, params=params, device=dev, rtol=rtol, atol=atol, return_device=True)
-    full = gather_rows(r["outlet"].contiguous(), N, world, rank)
-    return undeal(perm, full.cpu().numpy()), r["status"].cpu().numpy()
+    if hi > lo:
+        r = rmtExeBatch(modelInput, local_sweep, params=params, device=dev, rtol=rtol, atol=atol, return_device=True)
+        outlet, status = r["outlet"].contiguous(), r["status"].cpu().numpy()
+    else:                                   # empty shard (fewer reactors than ranks): nothing to solve, still take part in the gather
+        from .api import get_model
+        nv1 = get_model(modelInput, params=params, device=dev).nv1
+        outlet = torch.empty((0, nv1), dtype=torch.float64, device=torch.device("cuda", dev))
+        status = np.empty((0,), dtype=np.int32)
+    full = gather_rows(outlet, N, world, rank)
+    return undeal(perm, full.cpu().numpy()), status
 
 
 def chunk_bounds(N, chunk):

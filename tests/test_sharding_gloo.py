@@ -48,6 +48,13 @@ local = torch.from_numpy(table[perm[lo:hi]]*2.0)          # stand-in for "solve 
 full = ensemble.gather_rows(local, N, world, rank)
 out = ensemble.undeal(perm, full.numpy())
 assert np.array_equal(out, table*2.0), (rank, out)
+# fewer reactors than ranks: rank 1's shard is EMPTY (ADVICE r1: it must not crash or hang the gather)
+N1 = 1
+lo, hi = ensemble.shard_bounds(N1, rank, world)
+assert (hi - lo) == (1 if rank == 0 else 0)
+local = torch.from_numpy(table[lo:hi]*3.0)
+full = ensemble.gather_rows(local, N1, world, rank)
+assert full.shape == (1, K) and np.array_equal(full.numpy(), table[:1]*3.0), (rank, full)
 print("rank", rank, "ok", flush=True)
 dist.destroy_process_group()
 '''
