@@ -2212,6 +2212,15 @@ struct BlkCtx {
 // Measured and rejected variants of this kernel (records: profiles/r1l_*, r1m_*, r1n_* and DESIGN.md section 4): a march in which every
 // lane does the whole mat-vec, the 4x4 inverse in registers, a NaN-poisoned failure flag instead of the block reduction,
 // Jacobian / inverse reuse across steps, the RHS-only evaluation out of line.  Their code is gone; the history has it.
+// Row stride of the inverse blocks in shared memory: the four marching lanes read rows 4*stride doubles apart; with the plain
+// stride zNo = 100 (or 400) all four land in the same banks (ncu round 2: ALL 3.2e8 excess shared-memory wavefronts of the
+// kernel came from these eight loads, a 4-way conflict each).  An odd stride (PBR_K4B_PAD=1) spreads them over banks 0 / 8 / 16 / 24
+// -- and was measured SLOWER (K4b 161.4 vs 156.2 ms, K4d 158.8 vs 156.0 ms, bit-identical results): the loads are issued ahead of
+// the serial chain, so their conflicts are off the critical path, while the odd stride costs index arithmetic.  Default off.
+#ifndef PBR_K4B_PAD
+#define PBR_K4B_PAD 0
+#endif
+#define PBR_K4B_ASTRIDE(zNo) (PBR_K4B_PAD ? ((zNo) | 1) : (zNo))
 struct SmStore {         // Jacobian entries of this thread's node -> I - c*J in its shared-memory column
     Strided a; double c;
     __device__ __forceinline__ void operator()(int i, int k, double v) const { a[i*PBR_NX2 + k] = (i == k ? 1.0 : 0.0) - c*v; }
@@ -2247,7 +2256,7 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
     double bad = 0.0;
     if (act) {
         if (JAC) {
-            const Strided blk = {Asm + z, zNo};
+            const Strided blk = {Asm + z, PBR_K4B_ASTRIDE(zNo)};
             SmStore st = {blk, c};
             pbr_n2x_node<true>(y, yb, z == 0, Pz, inv_dz, p, f, st, sub);
             if (!pbr_invert<PBR_NX2>(blk)) bad = 1.0;          // Ainv replaces I - c*J in place
@@ -2290,7 +2299,7 @@ __device__ __forceinline__ void pbr_k4b_march_scan(const BlkCtx& cx, int zNo, bo
         double acc = 0.0;
 #pragma unroll
         for (int k = 0; k < NXm; ++k) {
-            const double aik = act ? Asm[(i*NXm + k)*zNo + z] : 0.0;
+            const double aik = act ? Asm[(i*NXm + k)*PBR_K4B_ASTRIDE(zNo) + z] : 0.0;
             acc += aik*b[k];
             B[i*NXm + k] = act ? aik*cs[k] : (i == k ? 1.0 : 0.0);       // padding lanes carry the identity map
         }
@@ -2358,6 +2367,7 @@ __device__ __forceinline__ void pbr_k4b_march_scan(const BlkCtx& cx, int zNo, bo
 __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool act, const double* Asm, double* gsm,
                                               const double* cs, double* b) {
     const int z = cx.tid;
+    const int zA = PBR_K4B_ASTRIDE(zNo);
     const int nwz = (zNo + 31) >> 5;                       // warps that own nodes
     __syncthreads();                                       // gsm (= Ysm) is no longer read as the iterate
     if (act) {
@@ -2365,7 +2375,7 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
         for (int i = 0; i < PBR_NX2; ++i) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < PBR_NX2; ++k) acc += Asm[(i*PBR_NX2 + k)*zNo + z]*b[k];
+            for (int k = 0; k < PBR_NX2; ++k) acc += Asm[(i*PBR_NX2 + k)*zA + z]*b[k];
             gsm[i*zNo + z] = acc;
         }
     }
@@ -2394,9 +2404,9 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
 #pragma unroll
                 for (int k = 0; k < PBR_NX2; ++k) {
 #if PBR_N2_REDUCED
-                    brow[k] = Asm[(row*PBR_NX2 + k)*zNo + zl]*csu[k];
+                    brow[k] = Asm[(row*PBR_NX2 + k)*zA + zl]*csu[k];
 #else
-                    brow[k] = Asm[(row*PBR_NX2 + k)*zNo + zl]*__shfl_sync(0xffffffffu, cs[k], l);
+                    brow[k] = Asm[(row*PBR_NX2 + k)*zA + zl]*__shfl_sync(0xffffffffu, cs[k], l);
 #endif
                 }
                 double s0 = gsm[row*zNo + zl], s1 = 0.0;
@@ -2435,7 +2445,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
     const int NO = PBR_NV2;                                // variables the error norms are taken over: [c, theta]
     double* Dsm = D_GLOBAL ? gwork + (long)blockIdx.x*PBR_DROWS*NV*zNo : pbr_smem;     // [PBR_DROWS*NV][zNo]
     double* Asm = D_GLOBAL ? pbr_smem : Dsm + (long)PBR_DROWS*NV*zNo;                  // [NV*NV][zNo]
-    double* Ysm = Asm + (long)NV*NV*zNo;                   // [NV][zNo]
+    double* Ysm = Asm + (long)NV*NV*PBR_K4B_ASTRIDE(zNo);  // [NV][zNo] (the inverse blocks have a padded row stride)
     double* Psm = Ysm + (long)NV*zNo;                      // psi
     double* Ism = Psm + (long)NV*zNo;                      // 1/scale [NO][zNo]
     BlkCtx cx; cx.red = Ism + (long)NO*zNo; cx.tid = threadIdx.x; cx.lane = threadIdx.x & 31; cx.wid = threadIdx.x >> 5; cx.nw = blockDim.x >> 5;

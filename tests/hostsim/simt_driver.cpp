@@ -17,7 +17,7 @@ int hs_simt_nx2() { return PBR_NX2; }
 void hs_simt_eval(int zNo, const double* par, const double* x, double* f) {
     const unsigned block = (unsigned)((zNo + 31)/32*32);
     simt::launch(1, block, [&]() {
-        double* Asm = pbr_smem; double* Ysm = Asm + PBR_NX2*PBR_NX2*zNo; double* red = Ysm + PBR_NX2*zNo;
+        double* Asm = pbr_smem; double* Ysm = Asm + PBR_NX2*PBR_NX2*PBR_K4B_ASTRIDE(zNo); double* red = Ysm + PBR_NX2*zNo;
         BlkCtx cx; cx.red = red; cx.tid = threadIdx.x; cx.lane = threadIdx.x & 31; cx.wid = threadIdx.x >> 5; cx.nw = blockDim.x >> 5;
         InstPar p; pbr_load_par(par, 1, 0, p);
         const int z = threadIdx.x; const bool act = z < zNo;
@@ -54,7 +54,7 @@ void hs_simt_rhs_n2(long N, int zNo, int G, const double* par, const double* Y, 
 int hs_simt_solve_n2(int kernel, long N, int zNo, int tNo, double period, const double* par, double rtol, double atol,
                      int max_steps, int grid, double* snaps, int* status, int* stats, const double* iv, int k_first, int flags) {
     const unsigned block = (unsigned)((zNo + 31)/32*32);
-    if ((size_t)(7*PBR_NX2 + PBR_NX2*PBR_NX2 + 2*PBR_NX2 + PBR_NV2)*zNo + 400 > sizeof(pbr_smem)/sizeof(double)) return -1;
+    if ((size_t)(7*PBR_NX2 + PBR_NX2*PBR_NX2 + 2*PBR_NX2 + PBR_NV2)*zNo + PBR_NX2*PBR_NX2 + 400 > sizeof(pbr_smem)/sizeof(double)) return -1;
     if (grid < 1) grid = 1;
     std::vector<double> gwork((size_t)grid*PBR_DROWS*PBR_NX2*zNo);
     double* gw = gwork.data();
