@@ -387,6 +387,7 @@ def run_gpu(a):
     assert (rh["status"] == 0).all()
     assert np.array_equal(rh["outlet"], out.view(N, model.nv1).cpu().numpy()), "host and device paths disagree"
 
+    northstar = bench_northstar(model, mi, world, rank)        # every rank takes part (strong-scaling record, outside the timed region)
     tt = torch.tensor([t_dev, t_e2e, t_k2], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -444,6 +445,7 @@ def run_gpu(a):
                          "max_over_mean_nfev": float(stats[2].max()/stats[2].mean())},
             "rhs_n2_roofline": rhs,
             "n2_config3": n2c3, "n2_config4_slice": n2c4, "e2e_profile": e2e_prof, "config5_estimation": cfg5,
+            "northstar_1m": northstar,
             "cpu_baseline": None if cpu_v is None else {
                 "value": cpu_v, "unit": "solves/s", "cores": cores, "kind": kind, "port_value": port_v,
                 "rhs_evals_per_s_per_core_port": cpu_rhs_rates(),
@@ -537,6 +539,47 @@ def bench_config5(model_device):
                               "failed": int((rs["status"] != 0).sum().item())},
             "forward_differences": {"kernel": "pbr_k2_solve_n1", "instances": Nb*(p + 1), "rtol": 1e-11, "ms": ms_f,
                                     "jacobians_per_s": Nb/(ms_f*1e-3), "failed": int((rf["status"] != 0).sum().item())}}
+
+
+def bench_northstar(model, mi, world, rank):
+    """North-star workload: 1,048,576 N1 reactors over the `world` GPUs of the job (strong scaling: the total is fixed), rows dealt
+    to the ranks by `ensemble.deal` on the inlet temperature (the stiffness proxy of DESIGN.md), ONE all-gather of outlet rows.
+    Called by every rank; device-timed, max over ranks.  Returns the record on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from pyremot_b200 import cases, ensemble
+    NT = 1048576
+    rows = cases.ensemble_rows(NT)
+    perm = ensemble.deal(rows["T"], world) if world > 1 else np.arange(NT)
+    lo, hi = ensemble.shard_bounds(NT, rank, world)
+    mine = perm[lo:hi]
+    tab = torch.from_numpy(model.instance_table(mi, {"T": rows["T"][mine], "P": rows["P"][mine], "conc": rows["conc"][mine],
+                                                       "Tm": rows["T"][mine]})).cuda()
+
+    def run():
+        par = model.prolog(tab)
+        r = model.solve_n1(par, rtol=RTOL, atol=ATOL, n_out=101, profile=False, stats=False)
+        out = model.unscale_n1(par, r["outlet_y"][None])[:, :, 0].contiguous()
+        return ensemble.gather_rows(out, NT, world, rank), r
+    full, r = run()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    full, r = run()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1), float((r["status"] != 0).sum().item())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t[0] = tm[0]
+    ms, failed = float(t[0].item()), int(t[1].item())
+    return {"workload": "1,048,576 N1 reactors over the job's GPUs (north star; strong scaling), rows dealt by ensemble.deal, one all-gather",
+            "reactors": NT, "gpus": world, "ms": ms, "value": NT/(ms*1e-3), "unit": "solves/s", "failed": failed,
+            "gathered_rows": int(full.shape[0])}
 
 
 def traffic_record(kernel):

@@ -33,7 +33,8 @@ solverSetting = {
 DEFAULT_RTOL = 1e-9
 DEFAULT_ATOL = 1e-13
 
-_models = {}
+_models = {}          # compiled models, most recently used last; bounded (each holds a CUDA module and scratch)
+_MAX_MODELS = 16
 
 
 def rmtCom():
@@ -58,10 +59,12 @@ def get_model(modelInput, params=(), device=0):
     key = (tuple(modelInput["feed"]["components"]["shell"]), tuple(modelInput["reactions"].items()),
            modelInput["operating-conditions"]["process-type"], probe.key, tuple(params), device,
            "M7" if modelInput.get("model") == "M7" else "N")
-    m = _models.get(key)
+    m = _models.pop(key, None)
     if m is None:
         m = engine.Model(modelInput, params=params, device=device)
-        _models[key] = m
+        while len(_models) >= _MAX_MODELS:                  # least recently used first
+            _models.pop(next(iter(_models))).close()
+    _models[key] = m
     return m
 
 
@@ -169,7 +172,13 @@ def rmtExe(modelInput, device=0):
         else:
             raise NotImplementedError(f"model {modelType!r}: only the pseudo-homogeneous packed-bed models "
                                       "N1, N2 and the dimensional steady-state model M7 are implemented by pyremot_b200")
-        return {"resModel": resModel, "comTime": (time.perf_counter() - tic)*1000}
+        # "resModel" / "comTime" are the reference's two keys (`rmt.py:73-77`).  "solver" is added so that the result itself says
+        # what integrated it: the reference runs SciPy at rtol 1e-3 (its `ivp` choice), this returns the converged solution.
+        sc = modelInput["solver-config"]
+        return {"resModel": resModel, "comTime": (time.perf_counter() - tic)*1000,
+                "solver": {"integrator": "libpbr batched BDF(1-5)/Newton, analytic Jacobian (sm_100a)",
+                           "rtol": float(sc.get("rtol", DEFAULT_RTOL)), "atol": float(sc.get("atol", DEFAULT_ATOL)),
+                           "ivp_requested": sc["ivp"], "ivp_honoured": False}}
     except Exception as e:
         print(e)
         raise

@@ -114,6 +114,7 @@ def test_rmtExe_n1_matches_converged_reference(torch_cuda, golden, tag, pt):
     from pyremot_b200 import rmtExe
     g = golden("n1_solve")
     res = rmtExe(cases.readme_case("N1", pt))
+    assert {"resModel", "comTime"} <= set(res) and res["solver"]["ivp_requested"] == "default" and res["solver"]["rtol"] == 1e-9
     d = res["resModel"][0]
     assert set(d) == {"modelId", "processType", "successStatus", "computation-time", "dataShape", "labelList",
                       "indexList", "dataTime", "dataXs", "dataYCons1", "dataYCons2", "dataYTemp1", "dataYTemp2", "dataYs"}
