@@ -2041,7 +2041,7 @@ extern "C" __global__ void __launch_bounds__(128) pbr_k4_solve_n2(long N, int zN
 //      maps (warp shuffles + a 4-entry shared-memory hand-over between warps and rounds).
 //      Per-reactor constants are staged in shared memory; the upstream neighbour is re-read through L1.
 #ifndef PBR_K3_MINBLOCKS
-#define PBR_K3_MINBLOCKS 4       // 4 blocks x 4 warps per SM (<=128 registers/thread)
+#define PBR_K3_MINBLOCKS 4       // 4 blocks x 4 warps per SM (<=128 registers/thread); 3 / 5 / 6 / 8 and two nodes per thread are slower
 #endif
 #define PBR_K3_MAXG 16
 #define PBR_K3_SPAR (PBR_KPAR + 7)      // staged constants per reactor: the table rows + the derived reciprocals
@@ -2169,7 +2169,6 @@ extern "C" __global__ void __launch_bounds__(128, PBR_K3_MINBLOCKS) pbr_k3_rhs_n
         }
     }
 }
-
 // ---- K4b: fused N2 solver, ONE BLOCK PER REACTOR, ONE THREAD PER AXIAL NODE, all integrator state on chip.
 //      Used when the reactor's working set fits shared memory (119*zNo doubles: zNo <= ~230); larger grids use K4.
 //      Shared memory (element e of node z at base[e*zNo + z], conflict-free): BDF history D[7][NV2], inverse of the
