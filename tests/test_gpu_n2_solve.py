@@ -261,3 +261,29 @@ def test_resume_from_saved_snapshot(zNo):
         bad[1, 0] *= 1.001
         tb = m.solve_n2_host(tab, zNo, tNo, period, iv=bad, k_first=k)
         assert tb["status"][1] == 5 and np.isnan(tb["dataYs"][1]).all() and (tb["status"][[0, 2]] == 0).all()
+
+
+def test_saved_shards_are_resume_points(tmp_path):
+    """SURVEY.md section 8 f4 end to end: a dynamic ensemble run is written with `io.save_shard` (two ranks' worth of rows), read back with
+    `io.load_shards`, and continued from its LAST snapshot over a second period -- the same states as continuing in memory."""
+    from pyremot_b200 import io
+    from pyremot_b200.api import get_model
+    N, zNo, tNo, period = 6, 100, 2, 0.04
+    rows = cases.ensemble_rows(N, offset=21)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}
+    mi = cases.readme_case("N2")
+    m = get_model(mi)
+    tab = m.instance_table(mi, sweep)
+    first = m.solve_n2_host(tab, zNo, tNo, period)
+    assert (first["status"] == 0).all()
+    for rank, (lo, hi) in enumerate(((0, 4), (4, 6))):
+        io.save_shard(str(tmp_path), {k: (v[:, lo:hi] if k == "stats" else v[lo:hi]) for k, v in first.items()}, lo, hi, rank=rank,
+                      meta={"zNo": zNo, "tNo": tNo, "period": period})
+    saved, meta = io.load_shards(str(tmp_path))
+    assert meta["zNo"] == zNo and np.array_equal(saved["snaps_y"], first["snaps_y"])
+    # the run continues on a grid of 2*tNo intervals over 2*period: intervals tNo .. 2*tNo-1 start from the saved last snapshot
+    cont = m.solve_n2_host(tab, zNo, 2*tNo, 2*period, iv=saved["snaps_y"][:, -1], k_first=tNo)
+    whole = m.solve_n2_host(tab, zNo, 2*tNo, 2*period)
+    assert (cont["status"] == 0).all() and cont["dataYs"].shape == (N, tNo, 7, zNo)
+    assert np.allclose(whole["dataYs"][:, :tNo], first["dataYs"], rtol=1e-12, atol=0)        # same first half
+    assert relerr(cont["dataYs"], whole["dataYs"][:, tNo:]) < RTOL_SOLVE
