@@ -489,10 +489,19 @@ def bench_n2(model, N, zNo, label, kernel, fp64_peak, reps=3):
     launches = m2.launch_count - l0
     t = float(np.mean(ms))*1e-3
     st = r["stats"].cpu().numpy()
+    # end to end through the host-buffer C-ABI call: host table in, dataYs [N][tNo][n+1][zNo] + status + counters out
+    tab_h = tab.cpu().numpy()
+    m2.solve_n2_host(tab_h, zNo, tNo, period, rtol=RTOL, atol=ATOL, scaled=False)
+    t0 = time.perf_counter()
+    rh = m2.solve_n2_host(tab_h, zNo, tNo, period, rtol=RTOL, atol=ATOL, scaled=False)
+    t_e2e = time.perf_counter() - t0
+    assert (rh["status"] == 0).all()
     flops, per_unit = algorithmic_flops_n2(m2, st, zNo)
     ach = flops/t/1e12
     return {"workload": label, "kernel": kernel, "instances": N, "zNo": zNo, "tNo": tNo, "period_s": period, "rtol": RTOL, "atol": ATOL,
             "ms": 1e3*t, "ms_each": ms, "value": N/t, "unit": "solves/s", "failed": int((r["status"] != 0).sum().item()),
+            "e2e": {"value": N/t_e2e, "unit": "solves/s", "ms": 1e3*t_e2e, "h2d_bytes_per_step": int(tab_h.nbytes),
+                    "d2h_bytes_per_step": int(rh["dataYs"].nbytes + rh["status"].nbytes + rh["stats"].nbytes)},
             "mean_steps": float(st[0].mean()), "mean_nfev": float(st[2].mean()), "node_steps_per_s": float(st[0].sum())*zNo/t,
             "gpu_launches": int(launches),
             "roofline": {"kernel": kernel, "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
