@@ -2208,6 +2208,10 @@ struct BlkCtx {
     }
 };
 
+// Measured and rejected in round 2 (profiles/r2_ab_instruction_level.md): an odd row stride for the inverse blocks (removes every
+// shared-memory bank conflict of the kernel, 3 % slower) and a two-level march (each warp propagates the affine response of its 32
+// nodes for an unknown input, the segment maps are chained, the warps re-march at once: serial depth 64 instead of 100 node steps,
+// 20 % slower -- the SM's other three blocks already fill the marching warp's shadow, so the extra march instructions only cost).
 // Measured and rejected variants of this kernel (records: profiles/r1l_*, r1m_*, r1n_* and DESIGN.md section 4): a march in which every
 // lane does the whole mat-vec, the 4x4 inverse in registers, a NaN-poisoned failure flag instead of the block reduction,
 // Jacobian / inverse reuse across steps, the RHS-only evaluation out of line.  Their code is gone; the history has it.
@@ -2288,6 +2292,7 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
 #ifndef PBR_K4C_MARCH_SCAN
 #define PBR_K4C_MARCH_SCAN 1          // 0: serial march in pbr_k4c_solve_n2 (A/B)
 #endif
+
 __device__ __forceinline__ void pbr_k4b_march_scan(const BlkCtx& cx, int zNo, bool act, const double* Asm, double* gsm,
                                                    const double* cs, double* b) {
     const int NXm = PBR_NX2;

@@ -54,7 +54,7 @@ void hs_simt_rhs_n2(long N, int zNo, int G, const double* par, const double* Y, 
 int hs_simt_solve_n2(int kernel, long N, int zNo, int tNo, double period, const double* par, double rtol, double atol,
                      int max_steps, int grid, double* snaps, int* status, int* stats, const double* iv, int k_first, int flags) {
     const unsigned block = (unsigned)((zNo + 31)/32*32);
-    if ((size_t)(7*PBR_NX2 + PBR_NX2*PBR_NX2 + 2*PBR_NX2 + PBR_NV2)*zNo + PBR_NX2*PBR_NX2 + 400 > sizeof(pbr_smem)/sizeof(double)) return -1;
+    if ((size_t)(7*PBR_NX2 + PBR_NX2*PBR_NX2 + 2*PBR_NX2 + PBR_NV2)*zNo + PBR_NX2*PBR_NX2 + 800 > sizeof(pbr_smem)/sizeof(double)) return -1;
     if (grid < 1) grid = 1;
     std::vector<double> gwork((size_t)grid*PBR_DROWS*PBR_NX2*zNo);
     double* gw = gwork.data();
