@@ -66,9 +66,11 @@ int pbr_set_species(pbr_ctx* ctx, int n_comp, int n_rxn, const double* MW, const
                     int iso_thermal);
 
 /* Model variant, to be chosen before pbr_load_rates: 0 (default) = the non-dimensional models N1 / N2; 1 = the dimensional
- * steady-state model "M7" (rmtCore.py:300-309 -> pbReactor.py runM3 :1170, modelEquationM3 :1371-1577) run through the N1 entry
- * points.  Variant 1 appends two columns to inst_in: mixture viscosity [Pa.s] (feed['mixture-viscosity']) and the heat-exchange
- * area per volume (external-heat['EfHeTrAr']), both inputs of that model. */
+ * steady-state model "M7" (rmtCore.py:300-309 -> pbReactor.py runM3 :1170, modelEquationM3 :1371-1577); 2 = "M8"
+ * (rmtCore.py:311-320 -> runM4 :1580, modelEquationM4 :1778-1995: the superficial velocity is a fourth kind of unknown) -- both
+ * run through the N1 entry points.  Variant 1 appends two columns to inst_in: mixture viscosity [Pa.s] (feed['mixture-viscosity'])
+ * and the heat-exchange area per volume (external-heat['EfHeTrAr']), both inputs of those models; variant 2 a third one, the inlet
+ * superficial velocity [m/s] (feed['superficial-velocity']), and its state / profiles have one more row (nv1 = n_comp + 3: v). */
 int pbr_set_model_variant(pbr_ctx* ctx, int variant);
 
 /* Compile the model: `cuda_src` defines PBR_NP, pbr_rates() and pbr_rates_jac() (output of the rate-expression

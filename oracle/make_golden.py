@@ -274,7 +274,65 @@ def g_m7():
     save("m7", **out)
 
 
-GROUPS = {"m7": g_m7, "props": g_props, "n1_rhs": g_n1_rhs, "n2_rhs": g_n2_rhs, "n1_solve": g_n1_solve,
+def g_m8():
+    """Dimensional steady-state model M8 (rmtCore.py:311-320 -> pbReactor.py runM4 / modelEquationM4): RHS on random states,
+    rmtExe at the default tolerances, converged profiles for the README case and 8 swept rows."""
+    import functools
+    import scipy.integrate as si
+    PyREMOT, H, setting = ref.load()
+    import PyREMOT.docs.pbReactor as R
+    cls = R.PackedBedReactorClass
+    orig = cls.modelEquationM4
+    cap = {}
+
+    def spy(t, y, a, b, c):
+        cap.setdefault("args", (a, b, c))
+        return orig(t, y, a, b, c)
+
+    def run(mi, rtol=None, atol=None):
+        saved = R.solve_ivp
+        try:
+            if rtol is not None:
+                R.solve_ivp = functools.partial(si.solve_ivp, rtol=rtol, atol=atol)
+            with ref.quiet():
+                return PyREMOT.rmtExe(mi)["resModel"]
+        finally:
+            R.solve_ivp = saved
+
+    def series(res):            # [x_i ; T ; P ; v] from the plotted series (dataYs itself holds only x_i and T)
+        return np.array([xy[1] for xy in res["XYList"]])
+    out = {}
+    cls.modelEquationM4 = spy
+    try:
+        res = run(cases.m8_case())
+    finally:
+        cls.modelEquationM4 = orig
+    out["default_dataYs"] = np.array(res["dataYs"])
+    out["default_series"] = series(res)
+    out["default_X"] = np.array(res["XYList"][0][0])
+    out["default_legs"] = np.array([d["leg"] for d in res["dataList"]])
+    rng = np.random.default_rng(808)
+    mi = cases.m8_case()
+    y0 = np.array(list(mi["feed"]["concentration"]) + [523.0, 5e6, mi["feed"]["superficial-velocity"]])
+    Y = np.tile(y0, (200, 1))
+    Y[:, :6] *= np.exp(rng.normal(0, 0.4, (200, 6)))*10.0**(rng.uniform(-1, 2, (200, 6))*(y0[:6] < 1.0))
+    Y[:, 6] = rng.uniform(490, 700, 200)
+    Y[:, 7] *= rng.uniform(0.9, 1.0, 200)
+    Y[:, 8] *= rng.uniform(0.7, 1.3, 200)
+    Y[0] = y0
+    with ref.quiet():
+        out["rhs_y"], out["rhs_f"] = Y, np.array([orig(0.5, list(y), *cap["args"]) for y in Y])
+    t = time.time()
+    res = run(cases.m8_case(), rtol=1e-12, atol=1e-12)
+    out["conv_series"] = series(res)
+    rows = cases.ensemble_rows(8)
+    out["sweep_conv_series"] = np.array([series(run(cases.m8_case(T=float(rows["T"][i]), P=float(rows["P"][i]), conc=rows["conc"][i],
+                                                                 Tm=float(rows["T"][i])), rtol=1e-12, atol=1e-12)) for i in range(8)])
+    print(f"m8 converged runs {time.time()-t:.1f}s", flush=True)
+    save("m8", **out)
+
+
+GROUPS = {"m7": g_m7, "m8": g_m8, "props": g_props, "n1_rhs": g_n1_rhs, "n2_rhs": g_n2_rhs, "n1_solve": g_n1_solve,
           "n1_sweep": g_n1_sweep, "n2_solve": g_n2_solve}
 
 if __name__ == "__main__":

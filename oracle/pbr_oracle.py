@@ -260,6 +260,7 @@ class Ensemble:
         # dimensional model M7 only (pbReactor.py:1238, :1545): mixture viscosity and heat-exchange area are INPUTS there
         self.mu_in = col("GaMiVi", fe.get("mixture-viscosity", float("nan")))
         self.a_in = col("EfHeTrAr", eh.get("EfHeTrAr", float("nan")))
+        self.v_in = col("SuGaVe0", fe.get("superficial-velocity", float("nan")))      # M8: the inlet velocity is an input (pbReactor.py:1626)
         self.var_overrides = {k[5:]: np.broadcast_to(np.asarray(v, dtype=np.float64), (N,)).copy()
                               for k, v in sweep.items() if k.startswith("VARS:")}
         self.prolog()
@@ -380,6 +381,61 @@ class Ensemble:
         """runM3 result assembly, pbReactor.py:1305-1322: rows x_i (n), T -- the pressure row is dropped. y: [N, n+2, K]."""
         C = y[:, :self.n]
         return np.concatenate([C/np.sum(C, axis=1, keepdims=True), y[:, self.n:self.n+1]], axis=1)
+
+    # ---- M8: dimensional steady-state model with the velocity as an unknown (rmtCore.py:311-320 -> pbReactor.py runM4 :1580-1776)
+    def iv_m8(self):
+        """[C0 (n), T, P, v0], pbReactor.py:1651-1656 (v0 = feed['superficial-velocity'])."""
+        return np.concatenate([self.C0, self.T0[:, None], self.P0[:, None], self.v_in[:, None]], axis=1)
+
+    def rhs_m8(self, y):
+        """modelEquationM4, pbReactor.py:1778-1995. y = [C_i (n), T, P, v] dimensional.  The kinetics are NOT the user's rate
+        expressions: the reference calls its built-in methanol/DME rates `1000*modelReactions(P, T, MoFri, CaBeDe)` (:1897-1899,
+        :8850-8930), which are the README kinetics; `rates_m8` below restates them."""
+        n = self.n
+        y = np.asarray(y, dtype=np.float64)
+        C, T, P, v = y[:, :n], y[:, n], y[:, n+1], y[:, n+2]           # :1857-1864
+        Ct = np.sum(C, axis=1)                                         # :1867
+        x = C/Ct[:, None]                                              # :1870
+        MoFl = Ct*v                                                    # :1873, :1879
+        M = np.sum(x*self.MW, axis=1)*1e-3                             # :1885
+        GaDe = M*Ct                                                    # :1888
+        eps, dp = self.BeVoFr, self.PaDi
+        dPdz = -1*(150*self.mu_in*v/(dp**2)*((1-eps)**2)/(eps**3) + 1.75*GaDe*(v**2)/dp*(1-eps)/(eps**3))   # :1893-1897
+        r = 1000*self.rates_m8(T, P, x)                                # :1903-1905
+        ri = r @ self.S                                                # :1909-1916
+        OvR = np.sum(ri, axis=1)                                       # :1919
+        Cpmix, OvHeReT = self._thermo_terms(x, T, r)                   # :1923-1936
+        Qm = self.U*self.a_in*(self.Tm - T)                            # :1940-1948
+        dTdz = (-OvHeReT + Qm)/(MoFl*Cpmix)                            # :1956, :1960
+        dvdz = (1/Ct)*((-v/R_CONST)*((1/T)*dPdz - (P/T**2)*dTdz) + OvR)   # :1964-1965
+        out = np.zeros_like(y)
+        out[:, :n] = (-C*dvdz[:, None] + ri)/v[:, None]                # :1969-1971
+        out[:, n] = dTdz
+        out[:, n+1] = dPdz
+        out[:, n+2] = dvdz
+        return out
+
+    def rates_m8(self, T, P, x):
+        """PackedBedReactorClass.modelReactions, pbReactor.py:8850-8930 [kmol/m3/s]: the methanol/DME kinetics with CaBeDe from the
+        reactor spec; x = mole fractions of (H2, CO2, H2O, CO, CH3OH, DME)."""
+        CaBeDe = float(self.mi["reactor"]["CaBeDe"])
+        RT = R_CONST*T
+        K1 = 35.45*np.exp(-1.7069e4/RT); K2 = 7.3976*np.exp(-2.0436e4/RT); K3 = 8.2894e4*np.exp(-5.2940e4/RT)
+        KH2 = 0.249*np.exp(3.4394e4/RT); KCO2 = 1.02e-7*np.exp(6.74e4/RT); KCO = 7.99e-7*np.exp(5.81e4/RT)
+        KP1 = np.exp(4213/T - 5.752*np.log(T) - 1.707e-3*T + 2.682e-6*T**2 - 7.232e-10*T**3 + 17.6)
+        KP2 = np.power(10.0, 2167/T - 0.5194*np.log10(T) + 1.037e-3*T - 2.331e-7*T**2 - 1.2777)
+        KP3 = np.exp(4019/T + 3.707*np.log(T) - 2.783e-3*T + 3.8e-7*T**2 - 6.56e-4/T**3 - 26.64)
+        PH2, PCO2, PH2O, PCO, PCH3OH, PDME = [P*x[:, i]*1e-5 for i in range(6)]
+        ra2 = 1 + KCO2*PCO2 + KCO*PCO + np.sqrt(KH2*PH2)
+        r1 = K1*((PCO2*PH2)/ra2**3)*(1 - (1/KP1)*((PH2O*PCH3OH)/(PCO2*PH2**3)))*CaBeDe
+        r2 = K2*(1/ra2)*(PH2O - (1/KP2)*((PCO2*PH2)/PCO))*CaBeDe
+        r3 = K3*(PCH3OH**2/PH2O - PDME/KP3)*CaBeDe
+        return np.stack([r1, r2, r3], axis=1)
+
+    def unscale_m8(self, y):
+        """runM4 result assembly, pbReactor.py:1706-1722: dataYs rows x_i (n), T; the plotted series add P and v."""
+        C = y[:, :self.n]
+        return np.concatenate([C/np.sum(C, axis=1, keepdims=True), y[:, self.n:]], axis=1)       # [x_i ; T ; P ; v]
 
     def rhs_n2(self, Y):
         """modelEquationN2, pbHomoReactor.py:3827-4131. Y: [N, nv, zNo] -> same (var-major per instance).
@@ -504,6 +560,26 @@ def solve_m7(ens, method="LSODA", rtol=1e-3, atol=1e-6, zNo=30, instances=None):
     y = np.stack(ys)
     sel = ens if instances is None else _select(ens, list(idx))
     return y, sel.unscale_m7(y), np.array(nfev)
+
+
+def solve_m8(ens, rtol=1e-3, atol=1e-6, zNo=25, instances=None):
+    """runM4: LSODA over z in [0, ReLe], t_eval = linspace(0, ReLe, solverSetting['S3']['timesNo'] = 25), pbReactor.py:1690-1701.
+    Returns (y [M, n+3, zNo] dimensional, series [M, n+3, zNo] = [x_i ; T ; P ; v], nfev [M])."""
+    from scipy.integrate import solve_ivp
+    idx = range(ens.N) if instances is None else instances
+    ys, nfev = [], []
+    for i in idx:
+        e = ens.sub(i)
+        L = float(e.ReLe[0])
+        sol = solve_ivp(lambda t, y: e.rhs_m8(y[None, :])[0], [0, L], e.iv_m8()[0], method="LSODA", t_eval=np.linspace(0, L, zNo),
+                        rtol=rtol, atol=atol)
+        if not sol.success:
+            raise RuntimeError(f"oracle M8 solve failed for instance {i}: {sol.message}")
+        ys.append(sol.y)
+        nfev.append(sol.nfev)
+    y = np.stack(ys)
+    sel = ens if instances is None else _select(ens, list(idx))
+    return y, sel.unscale_m8(y), np.array(nfev)
 
 
 def n2_jac_sparsity(nv, zNo):

@@ -28,6 +28,7 @@ solverSetting = {
     "N1": {"zNo": 100},
     "N2": {"zNo": 20, "rNo": 5, "tNo": 5, "timesNo": 5},
     "M9": {"zNo": 30},            # number of output points of model M7 (`PyREMOT/docs/pbReactor.py:1283`)
+    "S3": {"timesNo": 25},        # number of output points of model M8 (`PyREMOT/docs/pbReactor.py:1690`)
 }
 
 DEFAULT_RTOL = 1e-9
@@ -58,7 +59,7 @@ def get_model(modelInput, params=(), device=0):
                                        params=params)
     key = (tuple(modelInput["feed"]["components"]["shell"]), tuple(modelInput["reactions"].items()),
            modelInput["operating-conditions"]["process-type"], probe.key, tuple(params), device,
-           "M7" if modelInput.get("model") == "M7" else "N")
+           modelInput.get("model") if modelInput.get("model") in ("M7", "M8") else "N")
     m = _models.pop(key, None)
     if m is None:
         m = engine.Model(modelInput, params=params, device=device)
@@ -153,6 +154,46 @@ def _run_m7(modelInput, device=0):
     return {"dataYs": dataYs, "XYList": XYList, "dataList": dataList}
 
 
+def _m8_input(modelInput):
+    """Model "M8" integrates the reference's BUILT-IN methanol/DME kinetics (`pbReactor.py:1903`, `modelReactions` `:8850-8930`,
+    times 1000: kmol -> mol), not ``modelInput['reaction-rates']``: the compiled model gets exactly those."""
+    from . import cases
+    comps = list(modelInput["feed"]["components"]["shell"])
+    if comps != cases.MEOH_DME_COMPONENTS:
+        raise Exception("model M8 uses the reference's built-in methanol/DME kinetics: components must be " +
+                        ",".join(cases.MEOH_DME_COMPONENTS))
+    mi = dict(modelInput)
+    v, r = cases.methanol_dme_kinetics(modelInput["reactor"]["CaBeDe"])
+    mi["reaction-rates"] = {"VARS": v, "RATES": r}
+    return mi
+
+
+def _run_m8(modelInput, device=0):
+    """Model "M8" (`PyREMOT/docs/rmtCore.py:311-320` -> `pbReactor.py` runM4 `:1580-1776`): C_i, T, P and the superficial velocity
+    over z in [0, ReLe]; result ``{"dataYs": [x_i ; T] (n+1) x K, "XYList" / "dataList": the n+3 series [x_i ; T ; P ; v]}`` with
+    K = ``solverSetting['S3']['timesNo']`` (`:1690`) points (`:1706-1760`)."""
+    import torch
+    rtol, atol = _tolerances(modelInput)
+    mi = _m8_input(modelInput)
+    model = get_model(mi, device=device)
+    K = solverSetting["S3"]["timesNo"]
+    tab = torch.from_numpy(model.instance_table(mi)).to(model._dev())
+    par = model.prolog(tab)
+    res = model.solve_n1(par, rtol=rtol, atol=atol, n_out=K, profile=True)
+    st = int(res["status"][0].item())
+    if st != 0:
+        raise RuntimeError(f"M8 integration failed (status {st})")
+    full = model.unscale_n1(par, res["prof_y"])[0].cpu().numpy()           # [x_i ; P ; T ; v] x K
+    compList = list(modelInput["feed"]["components"]["shell"])
+    n = len(compList)
+    series = np.concatenate([full[:n], full[n + 1:n + 2], full[n:n + 1], full[n + 2:n + 3]], axis=0)    # [x_i ; T ; P ; v]
+    X = np.linspace(0, modelInput["reactor"]["ReLe"], K)
+    labelList = compList + ["Temperature", "Pressure", "Velocity"]
+    XYList = [[X, row] for row in series]
+    dataList = [{"x": X, "y": row, "leg": labelList[i]} for i, row in enumerate(series)]
+    return {"dataYs": series[:n + 1], "XYList": XYList, "dataList": dataList}
+
+
 def rmtExe(modelInput, device=0):
     """Check the model input, then run it — same contract as `PyREMOT/rmt.py:21-80`."""
     try:
@@ -169,9 +210,11 @@ def rmtExe(modelInput, device=0):
             resModel = run_n2(modelInput, device=device)
         elif modelType == "M7":
             resModel = _run_m7(modelInput, device=device)
+        elif modelType == "M8":
+            resModel = _run_m8(modelInput, device=device)
         else:
             raise NotImplementedError(f"model {modelType!r}: only the pseudo-homogeneous packed-bed models "
-                                      "N1, N2 and the dimensional steady-state model M7 are implemented by pyremot_b200")
+                                      "N1, N2 and the dimensional steady-state models M7, M8 are implemented by pyremot_b200")
         # "resModel" / "comTime" are the reference's two keys (`rmt.py:73-77`).  "solver" is added so that the result itself says
         # what integrated it: the reference runs SciPy at rtol 1e-3 (its `ivp` choice), this returns the converged solution.
         sc = modelInput["solver-config"]
@@ -198,13 +241,15 @@ def rmtExeBatch(modelInput, sweep, params=(), device=0, rtol=None, atol=None, pr
     r0, a0 = _tolerances(modelInput)
     rtol = r0 if rtol is None else rtol
     atol = a0 if atol is None else atol
+    if modelInput["model"] == "M8":
+        modelInput = _m8_input(modelInput)              # the reference's built-in kinetics, not modelInput['reaction-rates']
     model = get_model(modelInput, params=params, device=device)
     tab = model.instance_table(modelInput, sweep)
     if modelInput["model"] == "N2":
         s2 = solverSetting["N2"]
         r = model.solve_n2_host(tab, s2["zNo"], s2["tNo"], modelInput["operating-conditions"]["period"], rtol=rtol, atol=atol)
-    elif modelInput["model"] in ("N1", "M7"):
-        K = n_out or (solverSetting["N1"]["zNo"] + 1 if modelInput["model"] == "N1" else solverSetting["M9"]["zNo"])
+    elif modelInput["model"] in ("N1", "M7", "M8"):
+        K = n_out or {"N1": solverSetting["N1"]["zNo"] + 1, "M7": solverSetting["M9"]["zNo"], "M8": solverSetting["S3"]["timesNo"]}[modelInput["model"]]
         if not return_device:
             r = model.solve_n1_host(tab, rtol=rtol, atol=atol, n_out=K, profile=profile)
         else:

@@ -174,6 +174,18 @@ def m7_case(ivp="default", T=523.0, P=5e6, conc=None, U=50.0, Tm=523.0, mixture_
     return mi
 
 
+def m8_case(T=523.0, P=5e6, conc=None, U=50.0, Tm=523.0, superficial_velocity=None):
+    """The README inputs through the dimensional steady-state model "M8" (`PyREMOT/docs/rmtCore.py:311-320` -> `pbReactor.py`
+    runM4 `:1580`): unknowns C_i, T, P and the superficial velocity v, whose inlet value is the input
+    ``feed['superficial-velocity']`` (`:1626`; default here: volumetric flow rate / cross-section).  The reference integrates this
+    model with its BUILT-IN methanol/DME kinetics (`modelReactions`, `:8850`), not with ``reaction-rates``."""
+    mi = m7_case(T=T, P=P, conc=conc, U=U, Tm=Tm)
+    mi["model"] = "M8"
+    A = math.pi*mi["reactor"]["ReInDi"]**2/4
+    mi["feed"]["superficial-velocity"] = mi["feed"]["volumetric-flowrate"]/A if superficial_velocity is None else superficial_velocity
+    return mi
+
+
 def feed_mole_fraction(H2COxRatio, CO2COxRatio, float32=False):
     """Feed composition recipe of `PyREMOT/data/initData.py:11-38`.
 

@@ -18,8 +18,15 @@
 //   K5 epilog      solvers/solResultAnalysis.py:191-301, pbHomoReactor.py:2973-2983, :3655-3661
 #pragma once
 
+// PBR_MODEL_M8 = 1: the reference's dimensional steady-state model "M8" (rmtCore.py:311-320 -> pbReactor.py runM4 :1580,
+// modelEquationM4 :1778-1995): unknowns C_i, T, P and the superficial velocity v.  d(C_i v)/dz = r_i, so in flux variables
+// phi_i = C_i v/(Cmax v0) it has the same extent structure as N1 (phi = c0 + S^T x); the integrated vector gets one more entry
+// u = v/v0, the reported state one more row.  Its Jacobian is taken by forward differences of the (cheap) RHS inside the kernel.
+#ifndef PBR_MODEL_M8
+#define PBR_MODEL_M8 0
+#endif
 #ifndef PBR_NV1
-#define PBR_NV1 (PBR_NC + (PBR_ISO ? 1 : 2))   // N1 state: c_1..c_n, p, [theta]
+#define PBR_NV1 (PBR_NC + (PBR_ISO ? 1 : 2) + (PBR_MODEL_M8 ? 1 : 0))   // N1 state: c_1..c_n, p, [theta], [u]
 #endif
 #define PBR_NV2 (PBR_NC + (PBR_ISO ? 0 : 1))   // N2 per-node state: c_1..c_n, [theta]
 // N1 is INTEGRATED in reaction-extent coordinates when there are fewer reactions than species: every species balance is
@@ -34,7 +41,7 @@
 #define PBR_N1_REDUCED 0
 #endif
 #endif
-#define PBR_NX ((PBR_N1_REDUCED ? PBR_NR : PBR_NC) + (PBR_ISO ? 1 : 2))
+#define PBR_NX ((PBR_N1_REDUCED ? PBR_NR : PBR_NC) + (PBR_ISO ? 1 : 2) + (PBR_MODEL_M8 ? 1 : 0))
 // N2 (block-per-reactor kernels K4b/K4c): the same change of variables holds per node because the velocity is constant in
 // N2 (pbHomoReactor.py:3937, 4066): w_i = c_i - c0_i - sum_j nu_ji x_j obeys the homogeneous upwind advection equation
 // with w = 0 in the feed-filled bed and at the inlet, hence w == 0 and dx_j/dt = F1 (-(x_j - x_j,up)/dz + r_j/G).
@@ -57,6 +64,7 @@
 #ifndef PBR_MODEL_M7
 #define PBR_MODEL_M7 0
 #endif
+#define PBR_MODEL_DIM (PBR_MODEL_M7 || PBR_MODEL_M8)      // the dimensional models read viscosity / heat-exchange area from the input
 
 // Precision of the Jacobian partials.  PBR_JAC_F32=1: the rate partials (pbr_rates_jacf) and the assembly of the Jacobian in the
 // extent-coordinate evaluators run in single precision; the Newton matrix I - cJ, its LU / inverse, the residual and everything
@@ -96,8 +104,9 @@ enum {
 enum {
     IN_T = 0, IN_P, IN_VOFLRA, IN_REINDI, IN_RELE, IN_PADI, IN_BEVOFR, IN_U, IN_TM, IN_C0,
     IN_RP = IN_C0 + PBR_NC,
-    IN_MUIN = IN_RP + PBR_NP, IN_AIN,                                   // model M7 only: mixture viscosity [Pa.s], EfHeTrAr [m2/m3]
-    PBR_KIN = IN_RP + PBR_NP + (PBR_MODEL_M7 ? 2 : 0)
+    IN_MUIN = IN_RP + PBR_NP, IN_AIN,                                   // models M7 / M8: mixture viscosity [Pa.s], EfHeTrAr [m2/m3]
+    IN_VIN,                                                             // model M8: inlet superficial velocity [m/s]
+    PBR_KIN = IN_RP + PBR_NP + (PBR_MODEL_M8 ? 3 : (PBR_MODEL_M7 ? 2 : 0))
 };
 
 struct InstPar {
@@ -159,7 +168,7 @@ PBR_DEV void pbr_prolog_one(const double* in, double* out, long N, long i) {
 #pragma unroll
     for (int k = 0; k < PBR_NC; ++k) { C0[k] = in[IN_C0 + k]; Ct0 += C0[k]; Cmax = fmax(Cmax, C0[k]); }
     const double A = PBR_PI*(D*D)/4;                                   // pbHomoReactor.py:2751
-    const double vs0 = in[IN_VOFLRA]/A;                                // :2763
+    const double vs0 = PBR_MODEL_M8 ? in[IN_VIN] : in[IN_VOFLRA]/A;    // :2763; M8: feed['superficial-velocity'], pbReactor.py:1626
     double M0 = 0.0, Cpmix0 = 0.0;
 #pragma unroll
     for (int k = 0; k < PBR_NC; ++k) {
@@ -191,7 +200,7 @@ PBR_DEV void pbr_prolog_one(const double* in, double* out, long N, long i) {
     }
     const double rho0 = M0*Ct0;                                        // :2796
     const double e3 = eps*eps*eps;
-    if (PBR_MODEL_M7) mumix = in[IN_MUIN];                             // pbReactor.py:1238
+    if (PBR_MODEL_DIM) mumix = in[IN_MUIN];                            // pbReactor.py:1238, :1633
     out[PAR_TF*N + i] = T;
     out[PAR_PF*N + i] = P;
     out[PAR_CMAX*N + i] = Cmax;                                        // :2819-2820 "MAX"
@@ -204,9 +213,9 @@ PBR_DEV void pbr_prolog_one(const double* in, double* out, long N, long i) {
     out[PAR_RHO0*N + i] = rho0;
     out[PAR_CPMIX0*N + i] = Cpmix0;
     out[PAR_G*N + i] = (vs0/zf)*Cmax;                                  // :2821
-    out[PAR_GH*N + i] = PBR_MODEL_M7 ? T*vs0/zf                         // M7: d theta/dz' = (zf/(T0 vs0)) (-H + Q)/(Ct Cp w)
+    out[PAR_GH*N + i] = PBR_MODEL_DIM ? T*vs0/zf                        // M7: d theta/dz' = (zf/(T0 vs0)) (-H + Q)/(Ct Cp w)
                                      : rho0*vs0*T*(Cpmix0/M0)/zf;      // :2823
-    out[PAR_UA*N + i] = U*(PBR_MODEL_M7 ? in[IN_AIN] : 4.0/D);         // :2778 (input EfHeTrAr ignored by N1/N2, used by M7 :1545)
+    out[PAR_UA*N + i] = U*(PBR_MODEL_DIM ? in[IN_AIN] : 4.0/D);        // :2778 (input EfHeTrAr ignored by N1/N2, used by M7 :1545, M8 :1944)
     out[PAR_TM*N + i] = in[IN_TM];
     out[PAR_MU*N + i] = mumix;
 #pragma unroll
@@ -272,7 +281,7 @@ PBR_DEV void pbr_point(const double* c, double T, double P, const InstPar& p, Po
             Hsum += e.r[j]*e.dH[j];
         }
         e.Hsum = Hsum;
-        e.Q = (!PBR_MODEL_M7 && p.Tm == 0.0) ? 0.0 : p.Ua*(p.Tm - T);             // rmtUtility.py:424-452; M7: pbReactor.py:1551
+        e.Q = (!PBR_MODEL_DIM && p.Tm == 0.0) ? 0.0 : p.Ua*(p.Tm - T);            // rmtUtility.py:424-452; M7 / M8: pbReactor.py:1551, :1948
     }
     if (JAC) {
 #pragma unroll
@@ -306,8 +315,59 @@ PBR_DEV void pbr_dri(const double* drk, double* dri) {
 // =====================================================================================================
 struct NoStore { PBR_DEV void operator()(int, int, double) const {} };
 
+#if PBR_MODEL_M8
+// ---- M8 (modelEquationM4, pbReactor.py:1778-1995) in the scaled flux variables y = [phi_1..phi_n, p, theta, u]:
+//      phi_i = C_i v/(Cmax v0), p = P/P0, theta = (T - T0)/T0, u = v/v0, z' = z/ReLe.  f = dy/dz'; rG[j] = r_j/G (extent rates).
+PBR_DEV void pbr_m8_core(const double* y, const InstPar& p, double* f, double* rG) {
+    const int n = PBR_NC;
+    const double pr = y[n], th = y[n + 1], u = y[n + 2];
+    const double T = th*p.Tf + p.Tf, P = pr*p.Pf, v = u*p.vs0;        // :1860-1864
+    const double iu = pbr_rcp(u);
+    double c[PBR_NC];
+#pragma unroll
+    for (int i = 0; i < n; ++i) c[i] = y[i]*iu;                         // C_i/Cmax = phi_i/u
+    PointEval e;
+    pbr_point<false>(c, T, P, p, e);                                    // C, Ct, x, M, rates (built-in kinetics, :1903), Cp, dH, Q
+    const double rhoE = e.M*e.Ct;                                       // :1888
+    const double dPdz = -(p.E1*v + p.E2*rhoE*v*v);                      // :1893-1897 [Pa/m]
+    const double dTdz = (-e.Hsum + e.Q)*pbr_rcp((e.Ct*v)*e.Cpmix);      // :1956, :1960 [K/m]
+    double OvR = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) OvR += e.ri[i];                         // :1919
+    const double iT = pbr_rcp(T);
+    const double dvdz = pbr_rcp(e.Ct)*((-v*pbr_rcp(PBR_R))*(iT*dPdz - (P*iT*iT)*dTdz) + OvR);   // :1964-1965
+#pragma unroll
+    for (int i = 0; i < n; ++i) f[i] = e.ri[i]*p.iG;                    // d(C_i v)/dz = r_i (:1969-1971 rearranged), scaled by G = Cmax v0/zf
+    f[n] = dPdz*p.zP;
+    f[n + 1] = dTdz*p.zf*pbr_rcp(p.Tf);
+    f[n + 2] = dvdz*p.zf*pbr_rcp(p.vs0);
+#pragma unroll
+    for (int j = 0; j < PBR_NR; ++j) rG[j] = e.r[j]*p.iG;
+}
+#endif
+
+
 template <bool JAC, class Store>
 PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st, N1SensAux* aux = 0) {
+#if PBR_MODEL_M8
+    {   // M8: RHS in the flux variables; Jacobian by forward differences (rolled loop: one copy of the RHS code)
+        double rG[PBR_NR];
+        pbr_m8_core(y, p, f, rG);
+        if (JAC) {
+#pragma unroll 1
+            for (int k = 0; k < PBR_NV1; ++k) {
+                double yk[PBR_NV1], fk[PBR_NV1], hk = 0.0;
+#pragma unroll
+                for (int v = 0; v < PBR_NV1; ++v) { const double hv = 1e-7*fmax(fabs(y[v]), 1e-2); yk[v] = y[v] + (v == k ? hv : 0.0); if (v == k) hk = hv; }
+                pbr_m8_core(yk, p, fk, rG);
+                const double ih = pbr_rcp(hk);
+#pragma unroll
+                for (int a = 0; a < PBR_NV1; ++a) st(a, k, (fk[a] - f[a])*ih);
+            }
+        }
+        return;
+    }
+#endif
     const int n = PBR_NC;
     const double pr = y[n];
     const double th = PBR_ISO ? 0.0 : y[n + (PBR_ISO ? 0 : 1)];
@@ -400,6 +460,7 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
     }
 }
 
+
 // ---- extent coordinates: x[NX] <-> full scaled state y[NV1] = [c_1..c_n, p, theta]
 PBR_DEV void pbr_n1x_expand(const double* x, const InstPar& p, double* y) {
 #if PBR_N1_REDUCED
@@ -410,6 +471,7 @@ PBR_DEV void pbr_n1x_expand(const double* x, const InstPar& p, double* y) {
 #undef PBR_ACC
     y[PBR_NC] = x[PBR_NR];
     if (!PBR_ISO) y[PBR_NC + (PBR_ISO ? 0 : 1)] = x[PBR_NR + (PBR_ISO ? 0 : 1)];
+    if (PBR_MODEL_M8) y[PBR_NV1 - 1] = x[PBR_NX - 1];
 #else
 #pragma unroll
     for (int i = 0; i < PBR_NV1; ++i) y[i] = x[i];
@@ -427,6 +489,7 @@ PBR_DEV double pbr_n1x_norm2(const double* v, const double* iscale) {
 #undef PBR_ACC
     full[PBR_NC] = v[PBR_NR];
     if (!PBR_ISO) full[PBR_NC + (PBR_ISO ? 0 : 1)] = v[PBR_NR + (PBR_ISO ? 0 : 1)];
+    if (PBR_MODEL_M8) full[PBR_NV1 - 1] = v[PBR_NX - 1];
 #else
 #pragma unroll
     for (int i = 0; i < PBR_NV1; ++i) full[i] = v[i];
@@ -449,6 +512,30 @@ template <bool JAC, class Store>
 PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& st, N1SensAux* aux = 0) {
 #if !PBR_N1_REDUCED
     pbr_n1_eval<JAC>(x, p, f, st, aux);
+#elif PBR_MODEL_M8
+    {   // M8 in extent coordinates x = [x_1..x_R, p, theta, u]: f_x = [r_j/G, f_p, f_theta, f_u]; forward-difference Jacobian
+        const int n = PBR_NC, R = PBR_NR;
+        double y[PBR_NV1], ff[PBR_NV1], rG[PBR_NR];
+        pbr_n1x_expand(x, p, y);
+        pbr_m8_core(y, p, ff, rG);
+#pragma unroll
+        for (int j = 0; j < R; ++j) f[j] = rG[j];
+        f[R] = ff[n]; f[R + 1] = ff[n + 1]; f[R + 2] = ff[n + 2];
+        if (JAC) {
+#pragma unroll 1
+            for (int k = 0; k < PBR_NX; ++k) {
+                double xk[PBR_NX], hk = 0.0;
+#pragma unroll
+                for (int v = 0; v < PBR_NX; ++v) { const double hv = 1e-7*fmax(fabs(x[v]), 1e-2); xk[v] = x[v] + (v == k ? hv : 0.0); if (v == k) hk = hv; }
+                pbr_n1x_expand(xk, p, y);
+                pbr_m8_core(y, p, ff, rG);
+                const double ih = pbr_rcp(hk);
+#pragma unroll
+                for (int j = 0; j < R; ++j) st(j, k, (rG[j] - f[j])*ih);
+                st(R, k, (ff[n] - f[R])*ih); st(R + 1, k, (ff[n + 1] - f[R + 1])*ih); st(R + 2, k, (ff[n + 2] - f[R + 2])*ih);
+            }
+        }
+    }
 #else
     const int n = PBR_NC, R = PBR_NR;
     double y[PBR_NV1];
@@ -605,6 +692,7 @@ PBR_DEV void pbr_n1x_expand_lin(const double* v, double* full) {
 #undef PBR_ACC
     full[PBR_NC] = v[PBR_NR];
     if (!PBR_ISO) full[PBR_NC + (PBR_ISO ? 0 : 1)] = v[PBR_NR + (PBR_ISO ? 0 : 1)];
+    if (PBR_MODEL_M8) full[PBR_NV1 - 1] = v[PBR_NX - 1];
 #else
 #pragma unroll
     for (int i = 0; i < PBR_NV1; ++i) full[i] = v[i];
@@ -1895,7 +1983,8 @@ pbr_k2_solve_n1(long N, const double* __restrict__ par, double rtol, double atol
 #pragma unroll
     for (int k = 0; k < PBR_NC; ++k) y0[k] = p.c0[k];
 #endif
-    y0[PBR_NX - (PBR_ISO ? 1 : 2)] = 1.0;
+    y0[PBR_NX - (PBR_ISO ? 1 : 2) - (PBR_MODEL_M8 ? 1 : 0)] = 1.0;     // p = 1
+    if (PBR_MODEL_M8) y0[PBR_NX - 1] = 1.0;                            // u = v/v0 = 1
     const Strided LU = {pbr_smem + threadIdx.x, PBR_N1_BLOCK};
 #if PBR_N1_D_LOCAL
     double Dloc[PBR_DROWS*PBR_NX];
@@ -1922,7 +2011,7 @@ pbr_k2_solve_n1(long N, const double* __restrict__ par, double rtol, double atol
 // ---- K2s: K2 with forward sensitivities (BASELINE config 5 without finite differences).  Instance i integrates its reactor and
 //      s = d x / d par_kp[i]; outlet_y, sens_y: [NV1][N] scaled state at z = 1 and its derivative.  The host lays the instances
 //      out parameter-major (all reactors for parameter 0, then parameter 1, ...), so a warp shares kp.
-#if PBR_NP > 0 && !PBR_JAC_F32
+#if PBR_NP > 0 && !PBR_JAC_F32 && !PBR_MODEL_M8
 #ifndef PBR_N1S_BLOCK
 #define PBR_N1S_BLOCK 32
 #endif
@@ -1996,6 +2085,7 @@ extern "C" __global__ void __launch_bounds__(256) pbr_k5_unscale_n1(long N, int 
     for (int v = 0; v < PBR_NC; ++v) o[(long)v*K] = C[v]/Ct;
     o[(long)PBR_NC*K] = y[((long)k*PBR_NV1 + PBR_NC)*N + i]*Pf;
     if (!PBR_ISO) { const double th = y[((long)k*PBR_NV1 + PBR_NC + (PBR_ISO ? 0 : 1))*N + i]; o[(long)(PBR_NC + 1)*K] = th*Tf + Tf; }
+    if (PBR_MODEL_M8) o[(long)(PBR_NV1 - 1)*K] = y[((long)k*PBR_NV1 + PBR_NV1 - 1)*N + i]*par[PAR_VS0*N + i];       // v [m/s]
 }
 
 // ---- K4: fused N2 solver. Persistent warps: warp g handles instances g, g+G, ... with its own scratch slab.

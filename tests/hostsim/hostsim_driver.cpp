@@ -112,7 +112,8 @@ void hs_solve_n1(long N, const double* par, double rtol, double atol, int n_out,
 #if !PBR_N1_REDUCED
         for (int k = 0; k < PBR_NC; ++k) y0[k] = p.c0[k];
 #endif
-        y0[PBR_NX - (PBR_ISO ? 1 : 2)] = 1.0;
+        y0[PBR_NX - (PBR_ISO ? 1 : 2) - (PBR_MODEL_M8 ? 1 : 0)] = 1.0;
+        if (PBR_MODEL_M8) y0[PBR_NX - 1] = 1.0;
         Strided Dw = {work.data(), 1};
         Strided LUw = {work.data() + PBR_DROWS*PBR_NV1, 1};
         Sink sk = {prof, N, i, n_out, &p};

@@ -381,3 +381,56 @@ def test_block_kernels_do_not_depend_on_the_thread_schedule():
                     assert np.array_equal(dY, base[("k3", G, staged)]), (mode, G, staged)
     finally:
         sim.set_order(0)
+
+
+def test_m8_dimensional_model_with_velocity_vs_reference_golden(golden):
+    """SURVEY.md section 8 f3: model "M8" (`rmtCore.py:311-320` -> `pbReactor.py` modelEquationM4 `:1778-1995`; unknowns C_i, T, P, v;
+    the reference's built-in kinetics) in the scaled flux variables: RHS against 200 reference states, f = M f_x between full and
+    extent coordinates, the forward-difference Jacobian against central differences, and the BDF solve against the reference's
+    converged rmtExe("M8") series [x_i ; T ; P ; v]."""
+    from pyremot_b200 import api
+    g = golden("m8")
+    mi = api._m8_input(cases.m8_case())
+    m = engine.Model(mi, device=None)
+    assert m.variant == "M8" and m.k_in == 9 + 6 + 3 and m.nv1 == 9 and m.n1_vars == 6
+    hs = HostSim(m)
+    Y, F = g["rhs_y"], g["rhs_f"]                        # dimensional [C_i, T, P, v]
+    K = len(Y)
+    par = hs.prolog(m.instance_table(mi, N=K))
+    Cmax, T0, P0, zf, v0 = par[2], par[0], par[1], par[6], par[4]
+    C, T, P, v = Y[:, :6].T, Y[:, 6], Y[:, 7], Y[:, 8]
+    y = np.concatenate([C*v/(Cmax*v0), (P/P0)[None], ((T - T0)/T0)[None], (v/v0)[None]])        # [phi, p, theta, u]
+    f = hs.rhs_n1(par, y)
+    dT, dP, dv = f[7]*T0/zf, f[6]*P0/zf, f[8]*v0/zf
+    dC = (f[:6]*Cmax*v0/zf - C*dv)/v                     # d(C v)/dz = r  ->  dC/dz = (r - C dv/dz)/v, the reference's form (:1969-1971)
+    fd = np.concatenate([dC.T, dT[:, None], dP[:, None], dv[:, None]], axis=1)
+    assert relerr(fd, F, floor=1e-300) < 1e-10
+    # extent coordinates and the forward-difference Jacobian
+    nx, R = hs.L.hs_nx(), m.n_rxn
+    rows = cases.ensemble_rows(6)
+    A = np.pi*0.0381**2/4
+    par6 = hs.prolog(m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}))
+    rng = np.random.default_rng(4)
+    x = np.zeros((nx, 6))
+    x[:R] = rng.uniform(0, 0.02, (R, 6)); x[R] = rng.uniform(0.9, 1, 6); x[R + 1] = rng.uniform(0, 0.1, 6); x[R + 2] = rng.uniform(0.9, 1.1, 6)
+    yx, fx, Jx = hs.n1x(par6, x)
+    ff = hs.rhs_n1(par6, yx)
+    Mx = np.zeros((9, nx))
+    Mx[:6, :R] = m.S.T; Mx[6, R] = Mx[7, R + 1] = Mx[8, R + 2] = 1.0
+    assert relerr(Mx @ fx, ff, floor=1e-300) < 1e-12
+    for k in range(nx):
+        h = 1e-6*np.maximum(np.abs(x[k]), 1e-2)
+        xp, xm = x.copy(), x.copy()
+        xp[k] += h; xm[k] -= h
+        col = (hs.n1x(par6, xp)[1] - hs.n1x(par6, xm)[1])/(2*h)
+        assert np.max(np.abs(Jx[:, k] - col)/(np.abs(Jx).max(axis=(0, 1)) + 1e-300)) < 1e-5, k
+    # solve: README inputs through M8, 25 output points (solverSetting['S3']['timesNo'])
+    par1 = hs.prolog(m.instance_table(mi))
+    prof, st, stats = hs.solve_n1(par1, rtol=1e-9, atol=1e-13, n_out=25)
+    assert st[0] == 0
+    phi = prof[:, :6, 0]
+    series = np.concatenate([(phi/phi.sum(axis=1, keepdims=True)).T, (prof[:, 7, 0]*par1[0] + par1[0])[None], (prof[:, 6, 0]*par1[1])[None],
+                             (prof[:, 8, 0]*par1[4])[None]])
+    assert relerr(series, g["conv_series"]) < 1e-6
+    assert relerr(series[:7], g["default_dataYs"]) < 2e-3
+    assert relerr(O.Ensemble(cases.m8_case()).rhs_m8(Y), F, floor=1e-300) < 1e-12

@@ -423,3 +423,28 @@ def test_rmtExe_m7_matches_converged_reference(torch_cuda, golden):
     err = relerr(got, g["sweep_conv_dataYs"])
     print(f"\nM7: 8 swept profiles vs the reference's converged runs: worst rel. error {err:.2e}")
     assert err < RTOL_SOLVE
+
+
+def test_rmtExe_m8_matches_converged_reference(torch_cuda, golden):
+    """rmtExe with model "M8" (velocity as an unknown, the reference's built-in kinetics; `rmtCore.py:311-320` ->
+    `pbReactor.py:1580`) on the GPU: result layout of the reference (dataYs = [x_i ; T] over 25 points; XYList / dataList with the
+    n+3 series x_i, T, P, v), all series within 1e-6 of the reference's converged run; an 8-row sweep through rmtExeBatch."""
+    from pyremot_b200 import rmtExe, rmtExeBatch
+    g = golden("m8")
+    res = rmtExe(cases.m8_case())["resModel"]
+    assert set(res) == {"dataYs", "XYList", "dataList"} and res["dataYs"].shape == (7, 25)
+    assert [d["leg"] for d in res["dataList"]] == list(g["default_legs"]) and len(res["XYList"]) == 9
+    series = np.array([xy[1] for xy in res["XYList"]])
+    assert np.allclose(res["XYList"][0][0], g["default_X"]) and np.array_equal(series[:7], res["dataYs"])
+    assert relerr(series, g["conv_series"]) < RTOL_SOLVE
+    assert relerr(res["dataYs"], g["default_dataYs"]) < 2e-3
+    mi = cases.m8_case()
+    mi["reaction-rates"] = {"VARS": {}, "RATES": {"r1": lambda x: 0.0, "r2": lambda x: 0.0, "r3": lambda x: 0.0}}
+    assert np.array_equal(rmtExe(mi)["resModel"]["dataYs"], res["dataYs"])       # like the reference, M8 ignores the user's rates
+    rows = cases.ensemble_rows(8)
+    out = rmtExeBatch(cases.m8_case(), {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]}, profile=True)
+    assert (out["status"] == 0).all() and out["dataYs"].shape == (8, 9, 25)
+    got = out["dataYs"][:, [0, 1, 2, 3, 4, 5, 7, 6, 8]]                         # batch rows are [x_i ; P ; T ; v]
+    err = relerr(got, g["sweep_conv_series"])
+    print(f"\nM8: 8 swept series [x_i, T, P, v] vs the reference's converged runs: worst rel. error {err:.2e}")
+    assert err < RTOL_SOLVE

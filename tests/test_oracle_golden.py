@@ -103,3 +103,14 @@ def test_m7_oracle_vs_reference(golden):
     sw = {"T": rows["T"][:2], "P": rows["P"][:2], "conc": rows["conc"][:2], "Tm": rows["T"][:2]}
     _, data, _ = O.solve_m7(O.Ensemble(cases.m7_case(), sw), method="LSODA", rtol=1e-12, atol=1e-12)
     assert np.max(np.abs(data - g["sweep_conv_dataYs"][:2])/np.abs(g["sweep_conv_dataYs"][:2])) < 1e-8
+
+
+def test_m8_oracle_vs_reference(golden):
+    """Model M8: the oracle's restatement of modelEquationM4 (`pbReactor.py:1778-1995`, built-in kinetics `:8850-8930`) against 200
+    reference states, and its SciPy solve against the reference's converged rmtExe("M8") series."""
+    g = golden("m8")
+    ens = O.Ensemble(cases.m8_case(), N=len(g["rhs_y"]))
+    f = ens.rhs_m8(g["rhs_y"])
+    assert np.max(np.abs(f - g["rhs_f"])/(np.abs(g["rhs_f"]) + 1e-300)) < 1e-12
+    _, series, _ = O.solve_m8(O.Ensemble(cases.m8_case()), rtol=1e-12, atol=1e-12)
+    assert np.max(np.abs(series[0] - g["conv_series"])/np.abs(g["conv_series"])) < 1e-8
