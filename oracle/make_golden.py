@@ -332,7 +332,66 @@ def g_m8():
     save("m8", **out)
 
 
-GROUPS = {"m7": g_m7, "m8": g_m8, "props": g_props, "n1_rhs": g_n1_rhs, "n2_rhs": g_n2_rhs, "n1_solve": g_n1_solve,
+def g_m9():
+    """Dynamic dimensional model M9 (rmtCore.py:322-331 -> pbReactor.py runM5 / modelEquationM5): RHS on random states at two
+    grids, and rmtExe (which reports the temperature profile of every interval end) at reduced grids -- one reference solve at the
+    default grid (100 nodes, Python loops, a print per RHS call) takes hours."""
+    import functools
+    import scipy.integrate as si
+    PyREMOT, H, setting = ref.load()
+    import PyREMOT.docs.pbReactor as R
+    cls = R.PackedBedReactorClass
+    orig = cls.modelEquationM5
+    cap = {}
+
+    def spy(t, y, a, b, c):
+        cap["args"] = (a, b, c)
+        raise RuntimeError("captured")
+
+    def run(mi, zNo, tNo, rtol=None, atol=None):
+        saved, old = R.solve_ivp, dict(setting["S2"])
+        setting["S2"].update({"zNo": zNo, "tNo": tNo, "timesNo": 5})
+        try:
+            if rtol is not None:
+                R.solve_ivp = functools.partial(si.solve_ivp, rtol=rtol, atol=atol)
+            with ref.quiet():
+                return PyREMOT.rmtExe(mi)["resModel"]
+        finally:
+            R.solve_ivp = saved
+            setting["S2"].update(old)
+    out = {}
+    rng = np.random.default_rng(909)
+    for zNo in (12, 40):
+        cls.modelEquationM5 = spy
+        try:
+            run(cases.m9_case(), zNo, 2)
+        except Exception:
+            pass
+        finally:
+            cls.modelEquationM5 = orig
+        mi = cases.m9_case()
+        K = 12 if zNo == 12 else 4
+        Y = np.zeros((K, 7, zNo))
+        c0 = np.array(mi["feed"]["concentration"])
+        Y[:, :6, :] = c0[None, :, None]*np.exp(rng.normal(0, 0.3, (K, 6, zNo)))*10.0**(rng.uniform(-1, 2, (K, 6, zNo))*(c0[None, :, None] < 1.0))
+        Y[:, 6, :] = rng.uniform(500, 650, (K, zNo))
+        Y[1::3, 2, zNo//2] = -1e-7               # below the 1e-30 clamp (:2424, :2552)
+        with ref.quiet():
+            F = np.array([np.array(orig(0.5, y.reshape(-1), *cap["args"])).reshape(7, zNo) for y in Y])
+        out[f"rhs_y_z{zNo}"], out[f"rhs_f_z{zNo}"] = Y, F
+    t = time.time()
+    for tag, mi, zNo, tNo in (("z12", cases.m9_case(period=0.2), 12, 2), ("z20", cases.m9_case(period=0.1, T=540.0, Tm=530.0), 20, 2)):
+        res = run(mi, zNo, tNo)
+        out[f"{tag}_default_T"] = np.array([xy[1] for xy in res["XYList"]])
+        out[f"{tag}_legs"] = np.array([d["leg"] for d in res["dataList"]])
+        out[f"{tag}_X"] = np.array(res["XYList"][0][0])
+        res = run(mi, zNo, tNo, rtol=1e-10, atol=1e-12)
+        out[f"{tag}_conv_T"] = np.array([xy[1] for xy in res["XYList"]])
+        print(f"m9 {tag} {time.time()-t:.1f}s", flush=True)
+    save("m9", **out)
+
+
+GROUPS = {"m7": g_m7, "m8": g_m8, "m9": g_m9, "props": g_props, "n1_rhs": g_n1_rhs, "n2_rhs": g_n2_rhs, "n1_solve": g_n1_solve,
           "n1_sweep": g_n1_sweep, "n2_solve": g_n2_solve}
 
 if __name__ == "__main__":

@@ -437,6 +437,57 @@ class Ensemble:
         C = y[:, :self.n]
         return np.concatenate([C/np.sum(C, axis=1, keepdims=True), y[:, self.n:]], axis=1)       # [x_i ; T ; P ; v]
 
+    # ---- M9: dynamic dimensional model with marched pressure AND velocity (rmtCore.py:322-331 -> pbReactor.py runM5 :1997-2294)
+    def iv_m9(self, zNo):
+        """IV2D[(n+1), zNo] = C0 everywhere, T0 (dimensional), pbReactor.py:2063-2075. Returns [N, n+1, zNo]."""
+        Y = np.zeros((self.N, self.n + 1, zNo))
+        Y[:, :self.n, :] = self.C0[:, :, None]
+        Y[:, self.n, :] = self.T0[:, None]
+        return Y
+
+    def rhs_m9(self, Y):
+        """modelEquationM5, pbReactor.py:2296-2666. Y: [N, n+1, zNo] dimensional [C_i ; T] per node (var-major), t in seconds.
+        Pressure and velocity are marched node by node inside the evaluation (:2459, :2535), the rate evaluation of node z sits in
+        that chain (:2466-2470); the velocity slope carries the reference's 1000 factors (:2531-2533) and the heat exchange its
+        kJ conversion (rmtUtility.py:424-452 with unit 'kJ/m^3.s'); catalyst heat capacity (1-eps) CaDe CaSpHeCa in the energy balance."""
+        n = self.n
+        Y = np.asarray(Y, dtype=np.float64)
+        N, nv, zNo = Y.shape
+        eps, dp = self.BeVoFr, self.PaDi
+        CaDe = float(self.mi["reactor"]["CaDe"]); CaSpHeCa = float(self.mi["reactor"]["CaSpHeCa"])
+        dz = self.ReLe/(zNo - 1)                                       # :2058
+        Pz = self.P0.copy()                                            # :2397
+        vz = self.v_in.copy()                                          # :2400
+        out = np.zeros_like(Y)
+        for z in range(zNo):
+            Cc = Y[:, :n, z]
+            C = np.maximum(Cc, EPS_CONST)                              # :2424
+            Ct = np.sum(C, axis=1)
+            T = Y[:, n, z]
+            x = C/Ct[:, None]
+            MoFl = Ct*vz                                               # :2441, :2447
+            M = np.sum(x*self.MW, axis=1)*1e-3
+            GaDe = M*Ct                                                # :2453
+            dPdz = -1*(150*self.mu_in*vz/(dp**2)*((1-eps)**2)/(eps**3) + 1.75*GaDe*(vz**2)/dp*(1-eps)/(eps**3))   # :2456-2461
+            r = rates(self.rate_expr, T, Pz, x, C, self.var_overrides)  # :2466-2470
+            ri = r @ self.S
+            OvR = np.sum(ri, axis=1)                                   # :2480
+            Cpmix, OvHeReT = self._thermo_terms(x, T, r)               # :2484-2497
+            Qm = self.U*self.a_in*(self.Tm - T)
+            Qm = np.where(self.Tm == 0, 0.0, Qm)*1e-3                  # :2508-2509, rmtUtility.py:424-452 ('kJ/m^3.s')
+            Tb = self.T0 if z == 0 else Y[:, n, z-1]                   # :2513-2516
+            dTdz = (T - Tb)/dz                                         # :2518
+            dvdz = (1/(Ct*1000))*((-vz/R_CONST)*((1/T)*dPdz - (Pz/T**2)*dTdz) + OvR*1000)   # :2531-2533
+            cT1 = MoFl*Cpmix                                           # :2539
+            cT2 = 1/(Ct*Cpmix*eps + (1-eps)*CaDe*CaSpHeCa)             # :2540
+            Cb = self.C0 if z == 0 else np.maximum(Y[:, :n, z-1], EPS_CONST)   # :2548-2552
+            out[:, :n, z] = (1/eps)[:, None]*(-vz[:, None]*(Cc - Cb)/dz[:, None] - Cc*dvdz[:, None] + ri)   # :2554-2556
+            out[:, n, z] = cT2*(-cT1*dTdz + (-OvHeReT + Qm))           # :2571
+            vz_next = dvdz*dz + vz                                     # :2535
+            Pz = dPdz*dz + Pz                                          # :2462
+            vz = vz_next
+        return out
+
     def rhs_n2(self, Y):
         """modelEquationN2, pbHomoReactor.py:3827-4131. Y: [N, nv, zNo] -> same (var-major per instance).
 
@@ -580,6 +631,33 @@ def solve_m8(ens, rtol=1e-3, atol=1e-6, zNo=25, instances=None):
     y = np.stack(ys)
     sel = ens if instances is None else _select(ens, list(idx))
     return y, sel.unscale_m8(y), np.array(nfev)
+
+
+def solve_m9(ens, zNo=100, tNo=10, timesNo=5, method="LSODA", rtol=1e-3, atol=1e-6, instances=None):
+    """runM5's interval loop with solver restart, pbReactor.py:2108-2148 (zNo, tNo, timesNo from solverSetting['S2']).
+    Returns (Y [M, tNo, n+1, zNo] dimensional snapshots at the interval ends, T [M, tNo, zNo] -- what rmtExe("M9") reports --, nfev)."""
+    from scipy.integrate import solve_ivp
+    idx = range(ens.N) if instances is None else instances
+    out, nfev = [], []
+    for i in idx:
+        e = ens.sub(i)
+        IV = e.iv_m9(zNo)[0].reshape(-1)
+        nv = IV.size//zNo
+        span = np.linspace(0, float(e.period), tNo + 1)
+        snaps, nf = [], 0
+        for k in range(tNo):
+            t = [span[k], span[k+1]]
+            sol = solve_ivp(lambda t, y: e.rhs_m9(y.reshape(1, nv, zNo))[0].reshape(-1), t, IV, method=method,
+                            t_eval=np.linspace(t[0], t[1], timesNo), rtol=rtol, atol=atol)
+            if not sol.success:
+                raise RuntimeError(f"oracle M9 solve failed for instance {i}: {sol.message}")
+            IV = sol.y[:, -1]
+            nf += sol.nfev
+            snaps.append(IV.reshape(nv, zNo).copy())
+        out.append(np.stack(snaps))
+        nfev.append(nf)
+    Y = np.stack(out)
+    return Y, Y[:, :, -1, :], np.array(nfev)
 
 
 def n2_jac_sparsity(nv, zNo):

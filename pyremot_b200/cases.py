@@ -186,6 +186,17 @@ def m8_case(T=523.0, P=5e6, conc=None, U=50.0, Tm=523.0, superficial_velocity=No
     return mi
 
 
+def m9_case(period=0.5, T=523.0, P=5e6, conc=None, U=50.0, Tm=523.0, ivp="default"):
+    """The README inputs through the dynamic dimensional model "M9" (`PyREMOT/docs/rmtCore.py:322-331` -> `pbReactor.py` runM5
+    `:1997`): C_i and T per node, pressure and velocity marched along the bed; same extra inputs as M8.  Grid and intervals come
+    from ``solverSetting['S2']`` (`solSetting.py`: zNo 100, tNo 10)."""
+    mi = m8_case(T=T, P=P, conc=conc, U=U, Tm=Tm)
+    mi["model"] = "M9"
+    mi["operating-conditions"]["period"] = period
+    mi["solver-config"]["ivp"] = ivp
+    return mi
+
+
 def feed_mole_fraction(H2COxRatio, CO2COxRatio, float32=False):
     """Feed composition recipe of `PyREMOT/data/initData.py:11-38`.
 
