@@ -70,7 +70,11 @@ int pbr_set_species(pbr_ctx* ctx, int n_comp, int n_rxn, const double* MW, const
  * (rmtCore.py:311-320 -> runM4 :1580, modelEquationM4 :1778-1995: the superficial velocity is a fourth kind of unknown) -- both
  * run through the N1 entry points.  Variant 1 appends two columns to inst_in: mixture viscosity [Pa.s] (feed['mixture-viscosity'])
  * and the heat-exchange area per volume (external-heat['EfHeTrAr']), both inputs of those models; variant 2 a third one, the inlet
- * superficial velocity [m/s] (feed['superficial-velocity']), and its state / profiles have one more row (nv1 = n_comp + 3: v). */
+ * superficial velocity [m/s] (feed['superficial-velocity']), and its state / profiles have one more row (nv1 = n_comp + 3: v).
+ * 3 = the dynamic dimensional model "M9" (rmtCore.py:322-331 -> runM5 :1997, modelEquationM5 :2296-2666: pressure AND velocity
+ * marched along the bed inside every evaluation, catalyst heat capacity in the energy balance); it runs through the N2 entry
+ * points (pbr_rhs_n2, pbr_solve_n2*, warp-per-reactor kernel, state y = [C_i/Cmax ; (T - T0)/T0] per node) and appends five
+ * columns to inst_in: the three of variant 2, then reactor['CaDe'] [kg/m3] and reactor['CaSpHeCa']. */
 int pbr_set_model_variant(pbr_ctx* ctx, int variant);
 
 /* Compile the model: `cuda_src` defines PBR_NP, pbr_rates() and pbr_rates_jac() (output of the rate-expression

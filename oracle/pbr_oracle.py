@@ -633,7 +633,7 @@ def solve_m8(ens, rtol=1e-3, atol=1e-6, zNo=25, instances=None):
     return y, sel.unscale_m8(y), np.array(nfev)
 
 
-def solve_m9(ens, zNo=100, tNo=10, timesNo=5, method="LSODA", rtol=1e-3, atol=1e-6, instances=None):
+def solve_m9(ens, zNo=100, tNo=10, timesNo=5, method="LSODA", rtol=1e-3, atol=1e-6, instances=None, sparse=False):
     """runM5's interval loop with solver restart, pbReactor.py:2108-2148 (zNo, tNo, timesNo from solverSetting['S2']).
     Returns (Y [M, tNo, n+1, zNo] dimensional snapshots at the interval ends, T [M, tNo, zNo] -- what rmtExe("M9") reports --, nfev)."""
     from scipy.integrate import solve_ivp
@@ -647,8 +647,10 @@ def solve_m9(ens, zNo=100, tNo=10, timesNo=5, method="LSODA", rtol=1e-3, atol=1e
         snaps, nf = [], 0
         for k in range(tNo):
             t = [span[k], span[k+1]]
+            kw = {"jac_sparsity": n2_jac_sparsity(nv, zNo)} if (sparse and method in ("BDF", "Radau")) else {}   # grouping only: the
+            # upstream (P, v) coupling missing from the pattern makes the FD Jacobian inexact, which costs Newton iterations, not accuracy
             sol = solve_ivp(lambda t, y: e.rhs_m9(y.reshape(1, nv, zNo))[0].reshape(-1), t, IV, method=method,
-                            t_eval=np.linspace(t[0], t[1], timesNo), rtol=rtol, atol=atol)
+                            t_eval=np.linspace(t[0], t[1], timesNo), rtol=rtol, atol=atol, **kw)
             if not sol.success:
                 raise RuntimeError(f"oracle M9 solve failed for instance {i}: {sol.message}")
             IV = sol.y[:, -1]

@@ -29,6 +29,7 @@ solverSetting = {
     "N2": {"zNo": 20, "rNo": 5, "tNo": 5, "timesNo": 5},
     "M9": {"zNo": 30},            # number of output points of model M7 (`PyREMOT/docs/pbReactor.py:1283`)
     "S3": {"timesNo": 25},        # number of output points of model M8 (`PyREMOT/docs/pbReactor.py:1690`)
+    "S2": {"zNo": 100, "tNo": 10, "timesNo": 5},   # grid / intervals of the dynamic model M9 (`PyREMOT/docs/pbReactor.py:2056`, `:2141-2145`)
 }
 
 DEFAULT_RTOL = 1e-9
@@ -59,7 +60,7 @@ def get_model(modelInput, params=(), device=0):
                                        params=params)
     key = (tuple(modelInput["feed"]["components"]["shell"]), tuple(modelInput["reactions"].items()),
            modelInput["operating-conditions"]["process-type"], probe.key, tuple(params), device,
-           modelInput.get("model") if modelInput.get("model") in ("M7", "M8") else "N")
+           modelInput.get("model") if modelInput.get("model") in ("M7", "M8", "M9") else "N")
     m = _models.pop(key, None)
     if m is None:
         m = engine.Model(modelInput, params=params, device=device)
@@ -194,6 +195,29 @@ def _run_m8(modelInput, device=0):
     return {"dataYs": series[:n + 1], "XYList": XYList, "dataList": dataList}
 
 
+def _run_m9(modelInput, device=0):
+    """Model "M9" (`PyREMOT/docs/rmtCore.py:322-331` -> `pbReactor.py` runM5 `:1997-2294`): the dynamic dimensional model, C_i and T
+    on ``solverSetting['S2']['zNo']`` nodes over ``tNo`` intervals of ``period``, pressure and velocity marched along the bed inside
+    every evaluation.  The reference returns what its last plotting loop leaves behind (`:2258-2292`): the TEMPERATURE profile at the
+    end of every interval, ``XYList`` = [[z, T(z, t_k)]], ``dataList`` = the same with the legend "Temperature at t=<t_k>".
+    ``dataYs`` [tNo, n+1, zNo] = [x_i ; T] of every interval end is added (the reference computes it and drops it)."""
+    rtol, atol = _tolerances(modelInput)
+    model = get_model(modelInput, device=device)
+    s2 = solverSetting["S2"]
+    zNo, tNo = s2["zNo"], s2["tNo"]
+    opT = modelInput["operating-conditions"]["period"]
+    r = model.solve_n2_host(model.instance_table(modelInput), zNo, tNo, opT, rtol=rtol, atol=atol)
+    st = int(r["status"][0])
+    if st != 0:
+        raise RuntimeError(f"M9 integration failed (status {st})")
+    data = r["dataYs"][0]                                                     # [tNo, n+1, zNo]
+    X = np.linspace(0, modelInput["reactor"]["ReLe"], zNo)
+    opTSpan = np.linspace(0, opT, tNo + 1)
+    XYList = [[X, data[k, -1]] for k in range(tNo)]
+    dataList = [{"x": X, "y": data[k, -1], "leg": "Temperature at t=" + str(opTSpan[k + 1])} for k in range(tNo)]
+    return {"XYList": XYList, "dataList": dataList, "dataYs": data}
+
+
 def rmtExe(modelInput, device=0):
     """Check the model input, then run it — same contract as `PyREMOT/rmt.py:21-80`."""
     try:
@@ -212,9 +236,11 @@ def rmtExe(modelInput, device=0):
             resModel = _run_m7(modelInput, device=device)
         elif modelType == "M8":
             resModel = _run_m8(modelInput, device=device)
+        elif modelType == "M9":
+            resModel = _run_m9(modelInput, device=device)
         else:
             raise NotImplementedError(f"model {modelType!r}: only the pseudo-homogeneous packed-bed models "
-                                      "N1, N2 and the dimensional steady-state models M7, M8 are implemented by pyremot_b200")
+                                      "N1, N2 and the dimensional models M7, M8 (steady) and M9 (dynamic) are implemented by pyremot_b200")
         # "resModel" / "comTime" are the reference's two keys (`rmt.py:73-77`).  "solver" is added so that the result itself says
         # what integrated it: the reference runs SciPy at rtol 1e-3 (its `ivp` choice), this returns the converged solution.
         sc = modelInput["solver-config"]
@@ -245,8 +271,8 @@ def rmtExeBatch(modelInput, sweep, params=(), device=0, rtol=None, atol=None, pr
         modelInput = _m8_input(modelInput)              # the reference's built-in kinetics, not modelInput['reaction-rates']
     model = get_model(modelInput, params=params, device=device)
     tab = model.instance_table(modelInput, sweep)
-    if modelInput["model"] == "N2":
-        s2 = solverSetting["N2"]
+    if modelInput["model"] in ("N2", "M9"):
+        s2 = solverSetting["N2" if modelInput["model"] == "N2" else "S2"]
         r = model.solve_n2_host(tab, s2["zNo"], s2["tNo"], modelInput["operating-conditions"]["period"], rtol=rtol, atol=atol)
     elif modelInput["model"] in ("N1", "M7", "M8"):
         K = n_out or {"N1": solverSetting["N1"]["zNo"] + 1, "M7": solverSetting["M9"]["zNo"], "M8": solverSetting["S3"]["timesNo"]}[modelInput["model"]]

@@ -64,7 +64,15 @@
 #ifndef PBR_MODEL_M7
 #define PBR_MODEL_M7 0
 #endif
-#define PBR_MODEL_DIM (PBR_MODEL_M7 || PBR_MODEL_M8)      // the dimensional models read viscosity / heat-exchange area from the input
+// PBR_MODEL_M9 = 1: the reference's dynamic dimensional model "M9" (rmtCore.py:322-331 -> pbReactor.py runM5 :1997, modelEquationM5
+// :2296-2666): C_i and T per node; pressure AND velocity are marched along the bed inside every evaluation, the rate evaluation of
+// node z sits in that chain, the energy balance carries the catalyst's heat capacity.  Solved by the warp-per-reactor N2 kernel
+// (full coordinates); see pbr_m9_node / pbr_n2_sweep_eval.
+#ifndef PBR_MODEL_M9
+#define PBR_MODEL_M9 0
+#endif
+#define PBR_MODEL_DIM (PBR_MODEL_M7 || PBR_MODEL_M8 || PBR_MODEL_M9)   // the dimensional models read viscosity / heat-exchange area from the input
+#define PBR_Q_NO_SWITCH (PBR_MODEL_M7 || PBR_MODEL_M8)                  // M7 / M8: Q = Ua (Tm - T) without the "Tm == 0 is adiabatic" switch
 
 // Precision of the Jacobian partials.  PBR_JAC_F32=1: the rate partials (pbr_rates_jacf) and the assembly of the Jacobian in the
 // extent-coordinate evaluators run in single precision; the Newton matrix I - cJ, its LU / inverse, the residual and everything
@@ -98,19 +106,21 @@ enum {
     PAR_TF = 0, PAR_PF, PAR_CMAX, PAR_CT0, PAR_VS0, PAR_EPS, PAR_ZF, PAR_E1, PAR_E2, PAR_RHO0,
     PAR_CPMIX0, PAR_G, PAR_GH, PAR_UA, PAR_TM, PAR_MU, PAR_C0,          // c0[NC] follows
     PAR_RP = PAR_C0 + PBR_NC,                                           // rate parameters [NP]
-    PBR_KPAR = PAR_RP + PBR_NP
+    PAR_TMASS = PAR_RP + PBR_NP,                                        // M9 only: (1 - eps) CaDe CaSpHeCa [J/m3/K]
+    PBR_KPAR = PAR_RP + PBR_NP + (PBR_MODEL_M9 ? 1 : 0)
 };
 // ---- columns of the raw per-instance input table inst_in[N][KIN] (AoS, as the host assembles it)
 enum {
     IN_T = 0, IN_P, IN_VOFLRA, IN_REINDI, IN_RELE, IN_PADI, IN_BEVOFR, IN_U, IN_TM, IN_C0,
     IN_RP = IN_C0 + PBR_NC,
     IN_MUIN = IN_RP + PBR_NP, IN_AIN,                                   // models M7 / M8: mixture viscosity [Pa.s], EfHeTrAr [m2/m3]
-    IN_VIN,                                                             // model M8: inlet superficial velocity [m/s]
-    PBR_KIN = IN_RP + PBR_NP + (PBR_MODEL_M8 ? 3 : (PBR_MODEL_M7 ? 2 : 0))
+    IN_VIN,                                                             // models M8 / M9: inlet superficial velocity [m/s]
+    IN_CADE, IN_CASPHECA,                                               // model M9: catalyst density [kg/m3], specific heat capacity
+    PBR_KIN = IN_RP + PBR_NP + (PBR_MODEL_M9 ? 5 : (PBR_MODEL_M8 ? 3 : (PBR_MODEL_M7 ? 2 : 0)))
 };
 
 struct InstPar {
-    double Tf, Pf, Cmax, Ct0, vs0, eps, zf, E1, E2, rho0, Cpmix0, G, GH, Ua, Tm;
+    double Tf, Pf, Cmax, Ct0, vs0, eps, zf, E1, E2, rho0, Cpmix0, G, GH, Ua, Tm, tmass;
     double c0[PBR_NC];
     double rp[PBR_NPA];
     const double* src; long srcN, srci;        // where it was loaded from (for out-of-line helpers)
@@ -133,6 +143,7 @@ PBR_DEV void pbr_load_par(const double* __restrict__ par, long N, long i, InstPa
     p.rho0 = par[PAR_RHO0*N + i];   p.Cpmix0 = par[PAR_CPMIX0*N + i];
     p.G = par[PAR_G*N + i];         p.GH = par[PAR_GH*N + i];     p.Ua = par[PAR_UA*N + i];
     p.Tm = par[PAR_TM*N + i];
+    p.tmass = PBR_MODEL_M9 ? par[PAR_TMASS*N + i] : 0.0;
 #pragma unroll
     for (int k = 0; k < PBR_NC; ++k) p.c0[k] = par[(PAR_C0 + k)*N + i];
 #pragma unroll
@@ -168,7 +179,7 @@ PBR_DEV void pbr_prolog_one(const double* in, double* out, long N, long i) {
 #pragma unroll
     for (int k = 0; k < PBR_NC; ++k) { C0[k] = in[IN_C0 + k]; Ct0 += C0[k]; Cmax = fmax(Cmax, C0[k]); }
     const double A = PBR_PI*(D*D)/4;                                   // pbHomoReactor.py:2751
-    const double vs0 = PBR_MODEL_M8 ? in[IN_VIN] : in[IN_VOFLRA]/A;    // :2763; M8: feed['superficial-velocity'], pbReactor.py:1626
+    const double vs0 = (PBR_MODEL_M8 || PBR_MODEL_M9) ? in[IN_VIN] : in[IN_VOFLRA]/A;    // :2763; M8 / M9: feed['superficial-velocity'], pbReactor.py:1626, :2034
     double M0 = 0.0, Cpmix0 = 0.0;
 #pragma unroll
     for (int k = 0; k < PBR_NC; ++k) {
@@ -215,7 +226,8 @@ PBR_DEV void pbr_prolog_one(const double* in, double* out, long N, long i) {
     out[PAR_G*N + i] = (vs0/zf)*Cmax;                                  // :2821
     out[PAR_GH*N + i] = PBR_MODEL_DIM ? T*vs0/zf                        // M7: d theta/dz' = (zf/(T0 vs0)) (-H + Q)/(Ct Cp w)
                                      : rho0*vs0*T*(Cpmix0/M0)/zf;      // :2823
-    out[PAR_UA*N + i] = U*(PBR_MODEL_DIM ? in[IN_AIN] : 4.0/D);        // :2778 (input EfHeTrAr ignored by N1/N2, used by M7 :1545, M8 :1944)
+    out[PAR_UA*N + i] = U*(PBR_MODEL_DIM ? in[IN_AIN] : 4.0/D)*(PBR_MODEL_M9 ? 1e-3 : 1.0);   // :2778 (input EfHeTrAr ignored by N1/N2, used by M7 :1545, M8 :1944, M9 :2504 -- there in kJ, rmtUtility.py:447-449)
+    if (PBR_MODEL_M9) out[PAR_TMASS*N + i] = (1.0 - eps)*in[IN_CADE]*in[IN_CASPHECA];         // pbReactor.py:2540
     out[PAR_TM*N + i] = in[IN_TM];
     out[PAR_MU*N + i] = mumix;
 #pragma unroll
@@ -281,7 +293,7 @@ PBR_DEV void pbr_point(const double* c, double T, double P, const InstPar& p, Po
             Hsum += e.r[j]*e.dH[j];
         }
         e.Hsum = Hsum;
-        e.Q = (!PBR_MODEL_DIM && p.Tm == 0.0) ? 0.0 : p.Ua*(p.Tm - T);            // rmtUtility.py:424-452; M7 / M8: pbReactor.py:1551, :1948
+        e.Q = (!PBR_Q_NO_SWITCH && p.Tm == 0.0) ? 0.0 : p.Ua*(p.Tm - T);          // rmtUtility.py:424-452; M7 / M8: pbReactor.py:1551, :1948
     }
     if (JAC) {
 #pragma unroll
@@ -452,7 +464,7 @@ PBR_DEV void pbr_n1_eval(const double* y, const InstPar& p, double* f, Store& st
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < PBR_NR; ++j) s += drk[j]*e.dH[j] + p.Tf*e.r[j]*e.dHdT[j];
-            const double dQ = (!PBR_MODEL_M7 && p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
+            const double dQ = (!PBR_Q_NO_SWITCH && p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
             const double dNum = (-s + dQ)*iGH;
             const double dDen = Den*(drho*irho + p.Tf*e.dCpmixT*iCp);
             st(n + 1, n + 1, (dNum - fth*dDen)*iDen);
@@ -641,7 +653,7 @@ PBR_DEV void pbr_n1x_eval(const double* x, const InstPar& p, double* f, Store& s
             jreal sH = 0;
 #pragma unroll
             for (int j = 0; j < R; ++j) sH += drk[j]*dHj[j] + Tfj*(jreal)e.r[j]*(jreal)e.dHdT[j];
-            const jreal dQ = (!PBR_MODEL_M7 && p.Tm == 0.0) ? (jreal)0 : (jreal)(-p.Ua*p.Tf);
+            const jreal dQ = (!PBR_Q_NO_SWITCH && p.Tm == 0.0) ? (jreal)0 : (jreal)(-p.Ua*p.Tf);
             const jreal dNum = (-sH + dQ)*iGH;
             const jreal dDen = Denj*(drho*irho + Tfj*(jreal)e.dCpmixT*iCp);
             Jx[ct][ct] = (dNum - fthj*dDen)*iDen;
@@ -1480,6 +1492,8 @@ struct WarpCtx {
     void sync() const {}
     // pressure AT this lane's node given the affine maps (a,b) of the lanes before it; carry advances past the chunk
     double scan_affine(double a, double b, double& carry) const { const double P = carry; carry = a*P + b; return P; }
+    // carry + (sum of x over the lanes before this one); carry advances by the whole chunk's sum
+    double scan_sum(double x, double& carry) const { const double P = carry; carry = P + x; return P; }
 #else
     int lane; enum { NL = 32 };
     __device__ __forceinline__ double sum(double x) const {
@@ -1502,6 +1516,14 @@ struct WarpCtx {
         carry = __shfl_sync(0xffffffffu, a*carry + b, 31);
         return P;
     }
+    __device__ __forceinline__ double scan_sum(double x, double& carry) const {
+        double s = x;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const double s1 = __shfl_up_sync(0xffffffffu, s, off); if (lane >= off) s += s1; }
+        const double P = carry + (s - x);
+        carry += __shfl_sync(0xffffffffu, s, 31);
+        return P;
+    }
 #endif
 };
 
@@ -1513,6 +1535,61 @@ struct N2Ws {            // views into the warp's scratch
     PBR_DEV double* piv() const { return lu() + (long)PBR_NV2*PBR_NV2*zNo; }
     PBR_DEV double* G() const { return piv() + zNo; }
 };
+
+#if PBR_MODEL_M9
+// One node of model M9 (modelEquationM5, pbReactor.py:2419-2575) in the scaled variables y = [C_i/Cmax, (T - T0)/T0] (time in s):
+// given the marched pressure Pz [Pa] and velocity vz [m/s] AT the node, returns f = dy/dt and the two march slopes
+// dPdz [Pa/m] (Ergun, :2456-2461) and dvdz [1/s] (:2531-2533, with the reference's factors of 1000).
+PBR_DEV void pbr_m9_node(const double* yc, const double* yb, bool first, double Pz, double vz, double inv_dzL, const InstPar& p,
+                         double* f, double& dPdz, double& dvdz, double* sub) {
+    const int n = PBR_NC;
+    const double epsc = PBR_EPS*pbr_rcp(p.Cmax);                        // the reference clamps the DIMENSIONAL concentration at 1e-30 (:2424)
+    double c[PBR_NC];
+#pragma unroll
+    for (int i = 0; i < n; ++i) c[i] = fmax(yc[i], epsc);
+    const double T = yc[n]*p.Tf + p.Tf;
+    PointEval e;
+    pbr_point<false>(c, T, Pz, p, e);                                   // C, Ct, x, M, rates at (T, Pz, x, C) (:2466-2470), Cp, dH, Q [kJ]
+    const double GaDe = e.M*e.Ct;                                       // :2453
+    dPdz = -(p.E1*vz + p.E2*GaDe*vz*vz);                                // :2456-2461
+    double OvR = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) OvR += e.ri[i];                         // :2480
+    const double Tb = first ? p.Tf : (yb[n]*p.Tf + p.Tf);               // :2513-2516
+    const double dTdz = (T - Tb)*inv_dzL;                               // :2518
+    const double iT = pbr_rcp(T);
+    dvdz = pbr_rcp(e.Ct*1000.0)*((-vz*pbr_rcp(PBR_R))*(iT*dPdz - (Pz*iT*iT)*dTdz) + OvR*1000.0);   // :2531-2533
+    const double ieps = pbr_rcp(p.eps), iCmax = pbr_rcp(p.Cmax);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        const double Cc = yc[i]*p.Cmax;                                 // unclamped centre (:2546)
+        const double Cb = first ? p.c0[i]*p.Cmax : fmax(yb[i]*p.Cmax, PBR_EPS);      // :2548-2552
+        f[i] = (ieps*(-vz*((Cc - Cb)*inv_dzL) - Cc*dvdz + e.ri[i]))*iCmax;           // :2554-2556
+        if (sub) sub[i] = (first || !(yb[i]*p.Cmax > PBR_EPS)) ? 0.0 : ieps*vz*inv_dzL;
+    }
+    const double cT1 = (e.Ct*vz)*e.Cpmix;                               // :2539
+    const double cT2 = pbr_rcp(e.Ct*e.Cpmix*p.eps + p.tmass);           // :2540
+    f[n] = (cT2*(-cT1*dTdz + (-e.Hsum + e.Q)))*pbr_rcp(p.Tf);           // :2571
+    if (sub) sub[n] = first ? 0.0 : cT2*cT1*inv_dzL;
+}
+
+// d f_z / d y_z of one M9 node at FROZEN marched (Pz, vz), by forward differences (rolled loop: one more copy of the node code).
+// The dependence of (Pz, vz) on the upstream nodes is left out of the Newton matrix exactly as N2's pressure coupling is.
+template <class Store>
+PBR_DEV void pbr_m9_node_jac(const double* yc, const double* yb, bool first, double Pz, double vz, double inv_dzL, const InstPar& p,
+                             const double* f, Store& st) {
+#pragma unroll 1
+    for (int k = 0; k < PBR_NV2; ++k) {
+        double yk[PBR_NV2], fk[PBR_NV2], hk = 0.0, dP, dv;
+#pragma unroll
+        for (int v = 0; v < PBR_NV2; ++v) { const double hv = 1e-7*fmax(fabs(yc[v]), 1e-2); yk[v] = yc[v] + (v == k ? hv : 0.0); if (v == k) hk = hv; }
+        pbr_m9_node(yk, yb, first, Pz, vz, inv_dzL, p, fk, dP, dv, (double*)0);
+        const double ih = pbr_rcp(hk);
+#pragma unroll
+        for (int a = 0; a < PBR_NV2; ++a) st(a, k, (fk[a] - f[a])*ih);
+    }
+}
+#endif
 
 struct Lu2Store {        // Jacobian entries of one node -> I - c*J in the node's strided LU block
     Strided a; double c;
@@ -1528,6 +1605,10 @@ PBR_DEV bool pbr_n2_sweep_eval(const WarpCtx& w, const InstPar& p, const N2Ws& w
     const double dz = 1.0/(double)(zNo - 1), inv_dz = (double)(zNo - 1);        // :3439
     double Pcarry = p.Pf;                                                        // :3848
     double bad = 0.0;
+#if PBR_MODEL_M9
+    const double dzL = p.zf*dz, inv_dzL = pbr_rcp(dzL);                          // pbReactor.py:2058 (metres)
+    double vcarry = p.vs0, sP = 0.0, sv = 0.0;                                   // :2397-2400; slopes at the end of the previous chunk
+#endif
     w.sync();
     for (int z0 = 0; z0 < zNo; z0 += WarpCtx::NL) {
         const int z = z0 + w.lane;
@@ -1538,6 +1619,31 @@ PBR_DEV bool pbr_n2_sweep_eval(const WarpCtx& w, const InstPar& p, const N2Ws& w
             yc[v] = act ? ws.vec(0, v)[z] : 1.0;
             yb[v] = (act && z > 0) ? ws.vec(0, v)[z - 1] : 0.0;
         }
+#if PBR_MODEL_M9
+        // M9 marches pressure AND velocity node by node, with the node's rates inside the chain (pbReactor.py:2456-2470, :2531-2535):
+        //   P_{z+1} = P_z + dz dPdz(y_z, P_z, v_z),  v_{z+1} = v_z + dz dvdz(y_z, y_{z-1}, P_z, v_z).
+        // Within a chunk of 32 nodes this is solved by fixed-point sweeps: every lane evaluates its node at the current guess of
+        // (P_z, v_z), a prefix sum of the slopes gives the next guess.  Lane l is exact after l+1 sweeps (the dependence is strictly
+        // upstream), and because the slopes depend on (P, v) only weakly the sweep converges to rounding in a few passes; the loop
+        // stops when the guess no longer moves.  f, sub are those of the last pass, taken at (Pu, vu).
+        double f[PBR_NV2], sub[PBR_NV2];
+        double Pz = Pcarry + (double)w.lane*dzL*sP, vz = vcarry + (double)w.lane*dzL*sv, Pu = Pz, vu = vz;
+        double dP = 0.0, dv = 0.0, Pc = Pcarry, vc = vcarry;
+#pragma unroll 1
+        for (int it = 0; it < WarpCtx::NL + 2; ++it) {
+            dP = 0.0; dv = 0.0; Pu = Pz; vu = vz;
+            if (act) pbr_m9_node(yc, yb, z == 0, Pz, vz, inv_dzL, p, f, dP, dv, JAC ? sub : (double*)0);
+            Pc = Pcarry; vc = vcarry;
+            const double Pn = w.scan_sum(dzL*dP, Pc), vn = w.scan_sum(dzL*dv, vc);
+            const double chg = w.sum(act ? fabs(Pn - Pz)*pbr_rcp(fabs(Pn)) + fabs(vn - vz)*pbr_rcp(fabs(vn)) : 0.0);
+            Pz = Pn; vz = vn;
+            if (!(chg > 1e-13)) break;                                           // also leaves on NaN; the finite check below reports it
+        }
+        Pcarry = Pc; vcarry = vc;
+        sP = w.bcast(dP, WarpCtx::NL - 1); sv = w.bcast(dv, WarpCtx::NL - 1);
+        if (act) {
+            if (JAC) {
+#else
         double a = 1.0, b = 0.0;
         if (act) {
             double Ct = 0.0, M = 0.0;
@@ -1551,11 +1657,16 @@ PBR_DEV bool pbr_n2_sweep_eval(const WarpCtx& w, const InstPar& p, const N2Ws& w
         if (act) {
             double f[PBR_NV2], sub[PBR_NV2];
             if (JAC) {
+#endif
                 // the node's Newton block is built, factorised and used out of the warp's shared-memory tile (this
                 // lane's column); LU and G go to the global scratch afterwards with coalesced, fire-and-forget stores
                 const Strided blk = {w.tile + w.lane, WarpCtx::NL};
                 Lu2Store st = {blk, c};
+#if PBR_MODEL_M9
+                pbr_m9_node_jac(yc, yb, z == 0, Pu, vu, inv_dzL, p, f, st);
+#else
                 pbr_n2_node<true>(yc, yb, z == 0, Pz, inv_dz, p, f, st, sub);
+#endif
                 unsigned long long piv;
                 if (!pbr_lu_factor<PBR_NV2>(blk, piv)) bad = 1.0;
                 ws.piv()[z] = (double)piv;
@@ -1576,8 +1687,10 @@ PBR_DEV bool pbr_n2_sweep_eval(const WarpCtx& w, const InstPar& p, const N2Ws& w
 #pragma unroll 7
                 for (int e = 0; e < PBR_NV2*PBR_NV2; ++e) lu[(long)e*zNo] = blk[e];
             } else {
+#if !PBR_MODEL_M9
                 NoStore ns;
                 pbr_n2_node<false>(yc, yb, z == 0, Pz, inv_dz, p, f, ns, (double*)0);
+#endif
             }
 #pragma unroll
             for (int v = 0; v < PBR_NV2; ++v) {
@@ -2111,6 +2224,30 @@ extern "C" __global__ void __launch_bounds__(128) pbr_k4_solve_n2(long N, int zN
         __syncwarp();
     }
 }
+
+#if PBR_MODEL_M9
+// ---- K3m: M9 right-hand side only (parity tests and the CPU-vs-GPU RHS comparison): the warp solver's own sweep, one warp per reactor.
+//      Y, dYdt: [N][NV2][zNo] scaled, var-major.
+extern "C" __global__ void __launch_bounds__(128) pbr_k3m_rhs_m9(long N, int zNo, const double* __restrict__ par, const double* __restrict__ Y,
+                                                                 double* __restrict__ dYdt, double* __restrict__ work, int* __restrict__ status) {
+    extern __shared__ double pbr_smem[];
+    const long gw = ((long)blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const long G = ((long)gridDim.x*blockDim.x) >> 5;
+    WarpCtx w; w.lane = threadIdx.x & 31;
+    w.tile = pbr_smem + (long)(threadIdx.x >> 5)*PBR_N2_TILE_ROWS*32;
+    const N2Ws ws = {work + gw*(long)PBR_N2_WS_ROWS*zNo, zNo};
+    for (long inst = gw; inst < N; inst += G) {
+        InstPar p; pbr_load_par(par, N, inst, p);
+        for (int v = 0; v < PBR_NV2; ++v)
+            for (int z = w.lane; z < zNo; z += 32) ws.vec(0, v)[z] = Y[(inst*PBR_NV2 + v)*zNo + z];
+        const bool ok = pbr_n2_sweep_eval<false>(w, p, ws, 0.0, false);
+        for (int v = 0; v < PBR_NV2; ++v)
+            for (int z = w.lane; z < zNo; z += 32) dYdt[(inst*PBR_NV2 + v)*zNo + z] = ws.vec(4, v)[z];
+        if (w.lane == 0 && status) status[inst] = ok ? PBR_OK : PBR_ERR_NONFINITE;
+        __syncwarp();
+    }
+}
+#endif
 
 #endif  // !PBR_HOST (kernels K2, K3, K4)
 

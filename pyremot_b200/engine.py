@@ -155,8 +155,8 @@ class Model:
         self._check(L.pbr_set_species(self._ctx, self.n, self.S.shape[0], p_mw, p_cp, p_vis, p_s, p_dh, p_dc, int(self.iso)))
         # "M7": the dimensional steady-state model (`PyREMOT/docs/rmtCore.py:300-309`), solved through the N1 kernels
         self.variant = (modelInput.get("model") if variant is None else variant)
-        self.variant = self.variant if self.variant in ("M7", "M8") else "N"
-        self._check(L.pbr_set_model_variant(self._ctx, {"N": 0, "M7": 1, "M8": 2}[self.variant]))
+        self.variant = self.variant if self.variant in ("M7", "M8", "M9") else "N"
+        self._check(L.pbr_set_model_variant(self._ctx, {"N": 0, "M7": 1, "M8": 2, "M9": 3}[self.variant]))
         if cache_dir:
             os.makedirs(cache_dir, exist_ok=True)
         log = C.c_char_p()
@@ -226,11 +226,14 @@ class Model:
         t[:, 9:9 + self.n] = np.asarray(sweep.pop("conc", fe["concentration"]), dtype=np.float64)
         for k, name in enumerate(self.params):
             t[:, 9 + self.n + k] = sweep.pop("VARS:" + name, self.rates.param_defaults[k])
-        if self.variant in ("M7", "M8"):  # `pbReactor.py:1238`, `:1545`: both are inputs of those models
+        if self.variant in ("M7", "M8", "M9"):  # `pbReactor.py:1238`, `:1545`, `:2504`: both are inputs of those models
             t[:, 9 + self.n + len(self.params)] = sweep.pop("GaMiVi", fe["mixture-viscosity"])
             t[:, 10 + self.n + len(self.params)] = sweep.pop("EfHeTrAr", eh["EfHeTrAr"])
-        if self.variant == "M8":          # `pbReactor.py:1626`
+        if self.variant in ("M8", "M9"):  # `pbReactor.py:1626`, `:2034`
             t[:, 11 + self.n + len(self.params)] = sweep.pop("SuGaVe0", fe["superficial-velocity"])
+        if self.variant == "M9":          # catalyst heat capacity in the energy balance, `pbReactor.py:2048-2052`, `:2540`
+            t[:, 12 + self.n + len(self.params)] = sweep.pop("CaDe", re_["CaDe"])
+            t[:, 13 + self.n + len(self.params)] = sweep.pop("CaSpHeCa", re_["CaSpHeCa"])
         if sweep:
             raise KeyError(f"unknown sweep keys {sorted(sweep)} (rate parameters must be listed in params=)")
         return t

@@ -41,6 +41,32 @@ void hs_jac_n1(long N, const double* par, const double* y, double* f, double* J)
 struct JS2 { double* J; void operator()(int r, int c, double v) const { J[r*PBR_NV2 + c] = v; } };
 
 void hs_rhs_n2(long N, int zNo, const double* par, const double* Y, double* dY, double* Jd, double* Js) {
+#if PBR_MODEL_M9
+    // M9: the warp solver's own sweep (one scalar "lane"); with Jd also the FD diagonal blocks at the marched (P, v)
+    std::vector<double> work((size_t)PBR_N2_WS_ROWS*zNo), tile(PBR_N2_TILE_ROWS);
+    for (long i = 0; i < N; ++i) {
+        InstPar p; pbr_load_par(par, N, i, p);
+        WarpCtx w; w.lane = 0; w.tile = tile.data();
+        N2Ws ws = {work.data(), zNo};
+        for (int v = 0; v < PBR_NV2; ++v) for (int z = 0; z < zNo; ++z) ws.vec(0, v)[z] = Y[(i*PBR_NV2 + v)*zNo + z];
+        pbr_n2_sweep_eval<false>(w, p, ws, 0.0, false);
+        for (int v = 0; v < PBR_NV2; ++v) for (int z = 0; z < zNo; ++z) dY[(i*PBR_NV2 + v)*zNo + z] = ws.vec(4, v)[z];
+        if (Jd) {
+            const double dzL = p.zf/(zNo - 1), inv_dzL = 1.0/dzL;
+            double Pz = p.Pf, vz = p.vs0;
+            for (int z = 0; z < zNo; ++z) {
+                double yc[PBR_NV2], yb[PBR_NV2], f[PBR_NV2], sub[PBR_NV2], dP, dv;
+                for (int v = 0; v < PBR_NV2; ++v) { yc[v] = Y[(i*PBR_NV2 + v)*zNo + z]; yb[v] = z ? Y[(i*PBR_NV2 + v)*zNo + z - 1] : 0.0; }
+                pbr_m9_node(yc, yb, z == 0, Pz, vz, inv_dzL, p, f, dP, dv, sub);
+                JS2 st = {Jd + ((i*zNo + z)*PBR_NV2*PBR_NV2)};
+                pbr_m9_node_jac(yc, yb, z == 0, Pz, vz, inv_dzL, p, f, st);
+                for (int v = 0; v < PBR_NV2; ++v) Js[(i*zNo + z)*PBR_NV2 + v] = sub[v];
+                Pz += dzL*dP; vz += dzL*dv;
+            }
+        }
+    }
+    return;
+#endif
     const double dz = 1.0/(zNo - 1), inv_dz = (double)(zNo - 1);
     for (long i = 0; i < N; ++i) {
         InstPar p; pbr_load_par(par, N, i, p);

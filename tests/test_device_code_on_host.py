@@ -434,3 +434,57 @@ def test_m8_dimensional_model_with_velocity_vs_reference_golden(golden):
     assert relerr(series, g["conv_series"]) < 1e-6
     assert relerr(series[:7], g["default_dataYs"]) < 2e-3
     assert relerr(O.Ensemble(cases.m8_case()).rhs_m8(Y), F, floor=1e-300) < 1e-12
+
+
+def test_m9_dynamic_dimensional_model_vs_reference_golden(golden):
+    """model "M9" (`rmtCore.py:322-331` -> `pbReactor.py` modelEquationM5 `:2296-2666`) through the warp
+    solver's own sweep: RHS against the reference on random states at two grids (pressure AND velocity marched through the node
+    evaluations, one species below the clamp), the forward-difference diagonal blocks against central differences of the node
+    function, and the BDF interval loop against the reference's converged rmtExe("M9") temperature profiles."""
+    g = golden("m9")
+    mi = cases.m9_case()
+    m = engine.Model(mi, device=None)
+    assert m.variant == "M9" and m.k_in == 9 + 6 + 5 and m.nv2 == 7
+    hs = HostSim(m)
+    for zNo in (12, 40):
+        Y, F = g[f"rhs_y_z{zNo}"], g[f"rhs_f_z{zNo}"]                      # dimensional [C_i ; T] per node
+        par = hs.prolog(m.instance_table(mi, N=len(Y)))
+        Cmax, T0 = par[2][:, None, None], par[0][:, None]
+        y = Y.copy()
+        y[:, :6] /= Cmax
+        y[:, 6] = (Y[:, 6] - T0)/T0
+        f, Jd, Js = hs.rhs_n2(par, y, jac=True)
+        fd = f.copy()
+        fd[:, :6] *= Cmax
+        fd[:, 6] *= T0
+        assert np.max(np.abs(fd - F)/(np.abs(F) + 1e-12*np.abs(F).max())) < 1e-11, zNo
+        # the diagonal blocks: perturb ONE node's state; the marched (P, v) at that node depend on upstream nodes only, so a central
+        # difference of the full RHS restricted to the node's own rows is the block the solver builds by forward differences
+        i, z = 0, zNo//3
+        par1 = np.ascontiguousarray(par[:, i:i + 1])
+        for k in range(7):
+            h = 1e-6*max(abs(y[i, k, z]), 1e-2)
+            yp, ym = y[i:i + 1].copy(), y[i:i + 1].copy()
+            yp[0, k, z] += h
+            ym[0, k, z] -= h
+            col = (hs.rhs_n2(par1, yp)[0, :, z] - hs.rhs_n2(par1, ym)[0, :, z])/(2*h)
+            assert np.max(np.abs(Jd[i, z, :, k] - col))/np.abs(Jd[i, z]).max() < 1e-3, (zNo, k)    # one-sided h = 1e-7 max(|y|, 1e-2): O(h f'') on the trace species
+    for tag, mic, zNo in (("z12", cases.m9_case(period=0.2), 12), ("z20", cases.m9_case(period=0.1, T=540.0, Tm=530.0), 20)):
+        par = hs.prolog(m.instance_table(mic))
+        snaps, st, stats = hs.solve_n2(par, zNo, 2, float(mic["operating-conditions"]["period"]), rtol=1e-9, atol=1e-13)
+        assert st[0] == 0
+        T = snaps[0, :, 6, :]*par[0, 0] + par[0, 0]
+        assert np.max(np.abs(T - g[f"{tag}_conv_T"]))/500 < 1e-10, tag
+        assert np.max(np.abs(T - g[f"{tag}_default_T"]))/500 < 1e-6, tag        # the reference's own LSODA run at rtol 1e-3
+        # sub-diagonal d f_z / d y_{z-1} on the solved (physical) state: at frozen (P_z, v_z) it is diagonal; what the Newton matrix
+        # leaves out -- node z-1 also moves (P_z, v_z) through the march -- is a percent-level effect there
+        ys = np.ascontiguousarray(snaps[:, -1])
+        _, Jd, Js = hs.rhs_n2(par, ys, jac=True)
+        z = zNo//2
+        for k in range(7):
+            h = 1e-6*max(abs(ys[0, k, z - 1]), 1e-2)
+            yp, ym = ys.copy(), ys.copy()
+            yp[0, k, z - 1] += h
+            ym[0, k, z - 1] -= h
+            col = (hs.rhs_n2(par, yp)[0, :, z] - hs.rhs_n2(par, ym)[0, :, z])/(2*h)
+            assert abs(Js[0, z, k] - col[k]) < 2e-2*abs(col[k]), (tag, k, Js[0, z, k], col[k])

@@ -114,3 +114,19 @@ def test_m8_oracle_vs_reference(golden):
     assert np.max(np.abs(f - g["rhs_f"])/(np.abs(g["rhs_f"]) + 1e-300)) < 1e-12
     _, series, _ = O.solve_m8(O.Ensemble(cases.m8_case()), rtol=1e-12, atol=1e-12)
     assert np.max(np.abs(series[0] - g["conv_series"])/np.abs(g["conv_series"])) < 1e-8
+
+
+def test_m9_oracle_vs_reference(golden):
+    """Model M9: the oracle's restatement of modelEquationM5 (`pbReactor.py:2296-2666`: marched pressure AND velocity, the clamps,
+    the catalyst's heat capacity) against the reference's RHS on random states at two grids (one species below the 1e-30 clamp), and
+    its interval loop against the reference's rmtExe("M9") temperature profiles -- converged and at the reference's tolerances."""
+    g = golden("m9")
+    for zNo in (12, 40):
+        Y, F = g[f"rhs_y_z{zNo}"], g[f"rhs_f_z{zNo}"]
+        f = O.Ensemble(cases.m9_case(), N=len(Y)).rhs_m9(Y)
+        assert np.max(np.abs(f - F)/(np.abs(F) + 1e-12*np.abs(F).max())) < 1e-11, zNo
+    for tag, mi, zNo in (("z12", cases.m9_case(period=0.2), 12),):     # (the z20 fixture is checked through the device code on the host)
+        _, T, _ = O.solve_m9(O.Ensemble(mi), zNo=zNo, tNo=2, method="BDF", rtol=1e-10, atol=1e-12, sparse=True)
+        assert np.max(np.abs(T[0] - g[f"{tag}_conv_T"]))/500 < 1e-10, tag
+        _, T, _ = O.solve_m9(O.Ensemble(mi), zNo=zNo, tNo=2)                       # LSODA, rtol 1e-3: the reference's own run
+        assert np.max(np.abs(T[0] - g[f"{tag}_default_T"]))/500 < 1e-9, tag
