@@ -35,6 +35,11 @@ def _work(job):
         ens = O.Ensemble(_mi(kind, theta_as_vars=bool(job["theta"])), sweep)
         _, data, _ = O.solve_n1(ens, method="BDF", rtol=rtol, atol=atol)
         return data if bool(job["profiles"]) else data[:, :, -1]
+    if kind == "M9":
+        from pyremot_b200 import cases
+        ens = O.Ensemble(cases.m9_case(period=float(job["period"])), sweep)
+        Y, _, _ = O.solve_m9(ens, zNo=int(job["zNo"]), tNo=int(job["tNo"]), method="BDF", rtol=rtol, atol=atol, sparse=True)
+        return Y                                               # dimensional [C_i ; T] snapshots
     ens = O.Ensemble(_mi("N2"), sweep)
     ens.period = float(job["period"])
     _, data, _ = O.solve_n2(ens, zNo=int(job["zNo"]), tNo=int(job["tNo"]), method="BDF", rtol=rtol, atol=atol, sparse=True)
@@ -78,6 +83,11 @@ def oracle_n1(sweep, idx, kind="N1", profiles=False, rtol=1e-11, atol=1e-14, the
 def oracle_n2(sweep, idx, zNo, tNo, period, rtol=1e-9, atol=1e-13, timeout=1500):
     """Converged oracle snapshots dataYs [len(idx), tNo, n+1, zNo] of rows ``idx``."""
     return _run_jobs(sweep, idx, timeout, kind="N2", zNo=zNo, tNo=tNo, period=period, rtol=rtol, atol=atol)
+
+
+def oracle_m9(sweep, idx, zNo, tNo, period, rtol=1e-8, atol=1e-11, timeout=1500):
+    """Converged oracle snapshots [len(idx), tNo, n+1, zNo] (dimensional C_i, T) of the dynamic dimensional model M9."""
+    return _run_jobs(sweep, idx, timeout, kind="M9", zNo=zNo, tNo=tNo, period=period, rtol=rtol, atol=atol)
 
 
 def relerr_rows(a, b, floor=0.0):
