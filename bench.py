@@ -417,6 +417,7 @@ def run_gpu(a):
             n2c3["cpu_baseline"] = cpu_n2(cores)
         e2e_prof = bench_e2e_profile(model, tab_h, a.steps)
         cfg5 = bench_config5(model.device)
+        m9 = bench_m9(model.device, world == 1)
         kind = "reference" if reference_available() else "port"
         n_cpu = max(16*cores, 128)                      # ~0.3-0.8 s per solve per core -> 5-15 s of CPU work per leg
         # the CPU path is timed at N = 1 only (at N > 1 the other ranks would sit in the final barrier for its duration)
@@ -444,7 +445,7 @@ def run_gpu(a):
                          "mean_steps": float(stats[0].mean()), "mean_nfev": float(stats[2].mean()), "mean_nlu": float(stats[3].mean()),
                          "max_over_mean_nfev": float(stats[2].max()/stats[2].mean())},
             "rhs_n2_roofline": rhs,
-            "n2_config3": n2c3, "n2_config4_slice": n2c4, "e2e_profile": e2e_prof, "config5_estimation": cfg5,
+            "n2_config3": n2c3, "n2_config4_slice": n2c4, "e2e_profile": e2e_prof, "config5_estimation": cfg5, "m9_dynamic": m9,
             "northstar_1m": northstar,
             "cpu_baseline": None if cpu_v is None else {
                 "value": cpu_v, "unit": "solves/s", "cores": cores, "kind": kind, "port_value": port_v,
@@ -548,6 +549,47 @@ def bench_config5(model_device):
                               "failed": int((rs["status"] != 0).sum().item())},
             "forward_differences": {"kernel": "pbr_k2_solve_n1", "instances": Nb*(p + 1), "rtol": 1e-11, "ms": ms_f,
                                     "jacobians_per_s": Nb/(ms_f*1e-3), "failed": int((rf["status"] != 0).sum().item())}}
+
+
+def bench_m9(model_device, with_cpu):
+    """Widening row f3: the dynamic dimensional model M9 at the reference's own grid (solverSetting['S2']: 100 nodes, 10 intervals),
+    1,184 swept reactors (8 warps per SM) through 2 s of start-up with the wall 10 K below the feed.  Device-resident inputs,
+    CUDA events; the CPU figure beside it is the oracle's RHS rate (the reference's own RHS is a Python loop over nodes with a
+    print per call: one rmtExe("M9") at this grid takes hours, see oracle/make_golden.py g_m9)."""
+    import torch
+    from pyremot_b200 import cases
+    from pyremot_b200.api import get_model
+    N, zNo, tNo, period = 1184, 100, 10, 2.0
+    mi = cases.m9_case(period=period)
+    m = get_model(mi, device=model_device)
+    rows = cases.ensemble_rows(N)
+    sweep = {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"] - 10.0}
+    tab = torch.from_numpy(m.instance_table(mi, dict(sweep))).cuda()
+    par = m.prolog(tab)
+    m.solve_n2(par, zNo, tNo, period, rtol=RTOL, atol=ATOL)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = m.solve_n2(m.prolog(tab), zNo, tNo, period, rtol=RTOL, atol=ATOL)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    st = r["stats"].cpu().numpy()
+    rec = {"workload": "M9 dynamic dimensional model, 100 nodes x 10 intervals (solverSetting['S2']), 1184 swept reactors, 2 s start-up",
+           "kernel": "pbr_k4_solve_n2 (warp per reactor; pressure/velocity march by fixed-point sweeps)", "ms": ms,
+           "solves_per_s": N/(ms*1e-3), "failed": int((r["status"] != 0).sum().item()), "rtol": RTOL,
+           "mean_steps": float(st[0].mean()), "mean_nfev": float(st[2].mean()), "mean_nlu": float(st[3].mean())}
+    if with_cpu:
+        from oracle import pbr_oracle as O
+        ens = O.Ensemble(mi, {k: v[:64] for k, v in sweep.items()})
+        Y = ens.iv_m9(zNo)
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 2.0:
+            ens.rhs_m9(Y)
+            n += 64
+        rec["cpu_rhs_evals_per_s_per_core_port"] = n/(time.perf_counter() - t0)
+        rec["gpu_rhs_evals_per_s_inside_solver"] = float(st[2].sum())/(ms*1e-3)
+    return rec
 
 
 def bench_northstar(model, mi, world, rank):
