@@ -2510,9 +2510,15 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
 // maps compose: (B2, g2) o (B1, g1) = (B2 B1, g2 + B2 g1).  Every warp scans its 32 maps with shuffles (5 levels), the warp
 // totals are chained through shared memory (<= nw small mat-vecs), and every thread applies its prefix map to its warp's
 // incoming x.  All warps work at once instead of one node at a time.
-// Measured (config-3 / config-4 grids, one B200): zNo = 100 (4 warps) serial 190 ms vs scan 209 ms per 4,096 solves;
-// zNo = 400 (13 warps) serial 412 ms vs scan 186 ms per 1,184 solves.  The launcher picks per grid size:
-// pbr_k4b_solve_n2 (serial march) up to PBR_K4B_SCAN_FROM nodes, pbr_k4bs_solve_n2 / pbr_k4c_solve_n2 (scan) above.
+// Measured (one B200, 592 solves per launch, tools/k4b_march_ab.py -> profiles/r2_k4b_march_ab.json), ms serial / scan:
+// zNo 20 12.1 / 16.6, zNo 64 19.7 / 22.2, zNo 100 25.4 / 24.1, zNo 128 42.7 / 32.6, zNo 256 (296 solves) 57.1 / 28.1.  The phase
+// clocks (tools/k4b_phases.py) say why: the serial march costs ~270-310 cycles per node and is 54 % of a step at zNo 100, the scan
+// 94 cycles per node (19 %) -- but it keeps all four warps issuing, which slows the other three resident blocks' phases down.
+// The launcher picks per grid size: pbr_k4b_solve_n2 (serial march) up to PBR_K4B_SCAN_FROM = 96 nodes, pbr_k4bs_solve_n2 /
+// pbr_k4d_solve_n2 / pbr_k4c_solve_n2 (scan) above.
+#ifndef PBR_K4B_PROFILE
+#define PBR_K4B_PROFILE 0             // 1: phase clocks instead of step counters in `stats` (measurement build only)
+#endif
 #ifndef PBR_K4B_MARCH_SCAN
 #define PBR_K4B_MARCH_SCAN 0          // 1: force the scan in pbr_k4b_solve_n2 as well (A/B)
 #endif
@@ -2691,6 +2697,14 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
         int nsteps = 0, nrejf = 0, nfev = 0, nlu = 0;
         int rc = PBR_OK;
         __syncthreads();
+#if PBR_K4B_PROFILE
+        // measurement build (tools/k4b_phases.py): thread 0's clock at the phase boundaries of every step attempt; the sums (units of 64
+        // cycles: bookkeeping | Jacobian blocks + inverses | march | rest of the Newton loop) replace the step counters in `stats`
+        long long ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0, phm = 0;
+#define PBR_K4B_TICK(var) const long long var = clock64();
+#else
+#define PBR_K4B_TICK(var)
+#endif
         double iv_res = 0.0;
         if (act) {
 #pragma unroll
@@ -2791,6 +2805,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
             double t = t0;
             bool active = (rc == PBR_OK);
             while (active) {
+                PBR_K4B_TICK(tk0)
                 // ---- 1. step size, lazy history rescale
                 double hn = h*pend;
                 const bool clip = (t + hn > t1) || (t1 - (t + hn) < 1e-13*span);
@@ -2820,7 +2835,9 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 }
                 // ---- 3./4. Jacobian blocks + inverses at the predictor, Newton (bdf.py:36-68)
                 bool converged = false;
+                PBR_K4B_TICK(tk1)
                 bool running = pbr_k4b_eval<true>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub);
+                PBR_K4B_TICK(tk2)
                 nlu++; nfev++;
                 double cs[PBR_NX2];
 #pragma unroll
@@ -2839,8 +2856,14 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
 #pragma unroll
                                 for (int v = 0; v < NV; ++v) b[v] = c*f[v] - Psm[v*zNo + z] - d[v];
                             }
+#if PBR_K4B_PROFILE
+                            const long long tm0 = clock64();
+#endif
                             if (SCAN) pbr_k4b_march_scan(cx, zNo, act, Asm, Ysm, cs, b);
                             else pbr_k4b_march(cx, zNo, act, Asm, Ysm, cs, b);
+#if PBR_K4B_PROFILE
+                            phm += clock64() - tm0;
+#endif
                             double nrm = 0.0;
                             if (act) {
 #pragma unroll
@@ -2862,6 +2885,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                         }
                     }
                 }
+                PBR_K4B_TICK(tk3)
                 // ---- 5. error test
                 const double safety = pbr_bdf_safety(n_iter);             // 0.9*(2*MAXITER + 1)/(2*MAXITER + n_iter), bdf.py:391
                 double err_norm = 0.0;
@@ -2912,6 +2936,9 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                     }
                     if (!(t < t1)) active = false;
                 }
+#if PBR_K4B_PROFILE
+                { const long long tk4 = clock64(); ph0 += tk1 - tk0; ph1 += tk2 - tk1; ph2 += tk3 - tk2; ph3 += tk4 - tk3; }
+#endif
             }
             __syncthreads();
             if (act) {                                     // snapshot of this interval's end; NaN once the instance has failed
@@ -2927,6 +2954,9 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
         if (threadIdx.x == 0) {
             status[inst] = rc;
             if (stats) { stats[0*N + inst] = nsteps; stats[1*N + inst] = nrejf; stats[2*N + inst] = nfev; stats[3*N + inst] = nlu; }
+#if PBR_K4B_PROFILE
+            if (stats) { stats[0*N + inst] = (int)((ph0 + ph3) >> 6); stats[1*N + inst] = (int)(ph1 >> 6); stats[2*N + inst] = (int)(phm >> 6); stats[3*N + inst] = (int)((ph2 - phm) >> 6); }
+#endif
         }
         __syncthreads();
     }
