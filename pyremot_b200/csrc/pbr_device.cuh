@@ -2510,11 +2510,13 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
 // maps compose: (B2, g2) o (B1, g1) = (B2 B1, g2 + B2 g1).  Every warp scans its 32 maps with shuffles (5 levels), the warp
 // totals are chained through shared memory (<= nw small mat-vecs), and every thread applies its prefix map to its warp's
 // incoming x.  All warps work at once instead of one node at a time.
-// Measured (one B200, 592 solves per launch, tools/k4b_march_ab.py -> profiles/r2_k4b_march_ab.json), ms serial / scan:
-// zNo 20 12.1 / 16.6, zNo 64 19.7 / 22.2, zNo 100 25.4 / 24.1, zNo 128 42.7 / 32.6, zNo 256 (296 solves) 57.1 / 28.1.  The phase
-// clocks (tools/k4b_phases.py) say why: the serial march costs ~270-310 cycles per node and is 54 % of a step at zNo 100, the scan
-// 94 cycles per node (19 %) -- but it keeps all four warps issuing, which slows the other three resident blocks' phases down.
-// The launcher picks per grid size: pbr_k4b_solve_n2 (serial march) up to PBR_K4B_SCAN_FROM = 96 nodes, pbr_k4bs_solve_n2 /
+// Measured (one B200, tools/k4b_march_ab.py -> profiles/r2_k4b_march_ab*.json), ms serial / scan.  One wave of 592 solves (all
+// blocks in phase): zNo 20 12.1 / 16.6, zNo 64 19.7 / 22.2, zNo 100 25.4 / 24.1, zNo 128 42.7 / 32.6, zNo 256 (296 solves)
+// 57.1 / 28.1.  Seven waves (4,096 solves, blocks out of phase -- the production regime): zNo 64 95.2 / 109.1, zNo 100 155.2 / 158.6,
+// zNo 128 206.5 / 176.0.  The phase clocks (tools/k4b_phases.py) say why the scan does not win earlier: the serial march costs
+// ~270-310 cycles per node and is 54 % of a step at zNo 100, the scan 94 cycles per node (19 %) -- but it keeps all four warps
+// issuing, and the issue slots the serial march leaves idle are what the other three resident blocks run their phases on.
+// The launcher picks per grid size: pbr_k4b_solve_n2 (serial march) up to PBR_K4B_SCAN_FROM = 104 nodes, pbr_k4bs_solve_n2 /
 // pbr_k4d_solve_n2 / pbr_k4c_solve_n2 (scan) above.
 #ifndef PBR_K4B_PROFILE
 #define PBR_K4B_PROFILE 0             // 1: phase clocks instead of step counters in `stats` (measurement build only)

@@ -2,7 +2,7 @@
 sizes both can run (the launcher's switch is PBR_K4B_SCAN_FROM, read at every launch): 592 reactors, tNo 5, 0.5 s; device time,
 median of 3, and the worst difference between the two results.
 
-    python tools/k4b_march_ab.py > gpurun_out/r2_k4b_march_ab.json
+    python tools/k4b_march_ab.py [N [zNo,zNo,...]] > gpurun_out/r2_k4b_march_ab.json
 """
 import json
 import os
@@ -18,8 +18,11 @@ from pyremot_b200.api import get_model  # noqa: E402
 mi = cases.readme_case("N2")
 m = get_model(mi)
 out = {}
-for zNo in (10, 20, 33, 64, 100, 128, 200, 256):
-    N = 592 if zNo <= 128 else 296
+# optional arguments: N and a comma list of grid sizes (default: one wave of 592 / 296 reactors over all grid sizes)
+N_arg = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+grids = tuple(int(x) for x in sys.argv[2].split(",")) if len(sys.argv) > 2 else (10, 20, 33, 64, 100, 128, 200, 256)
+for zNo in grids:
+    N = N_arg or (592 if zNo <= 128 else 296)
     rows = cases.ensemble_rows(N)
     par = m.prolog(torch.from_numpy(m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]})).cuda())
     rec = {}
