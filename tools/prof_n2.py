@@ -1,4 +1,4 @@
-"""Short N2 solve for ncu: python tools/prof_n2.py [N] [zNo] [tNo] [period]"""
+"""Short N2 solve for ncu: python tools/prof_n2.py [N] [zNo] [tNo] [period]      (PBR_PROF_MODEL=M9: the dynamic dimensional model)"""
 import os
 import sys
 
@@ -12,10 +12,11 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
 zNo = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 tNo = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 period = float(sys.argv[4]) if len(sys.argv) > 4 else 0.1
-mi = cases.readme_case("N2")
+m9 = os.environ.get("PBR_PROF_MODEL") == "M9"
+mi = cases.m9_case(period=period) if m9 else cases.readme_case("N2")
 m = get_model(mi)
 rows = cases.ensemble_rows(N)
-tab = torch.from_numpy(m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"]})).cuda()
+tab = torch.from_numpy(m.instance_table(mi, {"T": rows["T"], "P": rows["P"], "conc": rows["conc"], "Tm": rows["T"] - (10.0 if m9 else 0.0)})).cuda()
 par = m.prolog(tab)
 for _ in range(2):
     r = m.solve_n2(par, zNo, tNo, period)
