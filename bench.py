@@ -576,7 +576,7 @@ def bench_m9(model_device, with_cpu):
     ms = e0.elapsed_time(e1)
     st = r["stats"].cpu().numpy()
     rec = {"workload": "M9 dynamic dimensional model, 100 nodes x 10 intervals (solverSetting['S2']), 1184 swept reactors, 2 s start-up",
-           "kernel": "pbr_k4_solve_n2 (warp per reactor; pressure/velocity march by fixed-point sweeps)", "ms": ms,
+           "kernel": "pbr_k4b_solve_n2 (block per reactor, full coordinates; pressure/velocity march by block-wide fixed-point sweeps)", "ms": ms,
            "solves_per_s": N/(ms*1e-3), "failed": int((r["status"] != 0).sum().item()), "rtol": RTOL,
            "mean_steps": float(st[0].mean()), "mean_nfev": float(st[2].mean()), "mean_nlu": float(st[3].mean())}
     if with_cpu:

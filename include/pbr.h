@@ -73,7 +73,7 @@ int pbr_set_species(pbr_ctx* ctx, int n_comp, int n_rxn, const double* MW, const
  * superficial velocity [m/s] (feed['superficial-velocity']), and its state / profiles have one more row (nv1 = n_comp + 3: v).
  * 3 = the dynamic dimensional model "M9" (rmtCore.py:322-331 -> runM5 :1997, modelEquationM5 :2296-2666: pressure AND velocity
  * marched along the bed inside every evaluation, catalyst heat capacity in the energy balance); it runs through the N2 entry
- * points (pbr_rhs_n2, pbr_solve_n2*, warp-per-reactor kernel, state y = [C_i/Cmax ; (T - T0)/T0] per node) and appends five
+ * points (pbr_rhs_n2, pbr_solve_n2*; state y = [C_i/Cmax ; (T - T0)/T0] per node) and appends five
  * columns to inst_in: the three of variant 2, then reactor['CaDe'] [kg/m3] and reactor['CaSpHeCa']. */
 int pbr_set_model_variant(pbr_ctx* ctx, int variant);
 

@@ -2433,6 +2433,22 @@ struct BlkCtx {
         for (int k = 0; k < wid; ++k) Pin = red[k]*Pin + red[16 + k];
         return ae*Pin + be;
     }
+    // block-wide EXCLUSIVE prefix sums of two values at once (model M9's pressure and velocity march): x1, x2 <- sum over earlier threads
+    __device__ __forceinline__ void scan_sum2(double& x1, double& x2) const {
+        double s1 = x1, s2 = x2;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double a1 = __shfl_up_sync(0xffffffffu, s1, off);
+            const double a2 = __shfl_up_sync(0xffffffffu, s2, off);
+            if (lane >= off) { s1 += a1; s2 += a2; }
+        }
+        __syncthreads();
+        if (lane == 31) { red[wid] = s1; red[16 + wid] = s2; }
+        __syncthreads();
+        double c1 = 0.0, c2 = 0.0;
+        for (int k = 0; k < wid; ++k) { c1 += red[k]; c2 += red[16 + k]; }
+        x1 = c1 + (s1 - x1); x2 = c2 + (s2 - x2);
+    }
 };
 
 // Measured and rejected in round 2 (profiles/r2_ab_instruction_level.md): an odd row stride for the inverse blocks (removes every
@@ -2458,9 +2474,10 @@ struct SmStore {         // Jacobian entries of this thread's node -> I - c*J in
 
 // f(Y) at this thread's node from the iterate y[] (registers); with JAC also leaves Ainv in shared memory and sub[].
 // Returns false (block-uniform) if any node produced a non-finite value or a singular block.
+// Model M9: `pv` carries this thread's marched (P_z, v_z) from one evaluation to the next as the first guess of the fixed-point sweeps.
 template <bool JAC>
 __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p, int zNo, bool act, const double* y, double c,
-                                             double* Ysm, double* Asm, double* f, double* sub) {
+                                             double* Ysm, double* Asm, double* f, double* sub, double* pv = 0) {
     const int z = cx.tid;
     const double dz = 1.0/(double)(zNo - 1), inv_dz = (double)(zNo - 1);
     __syncthreads();
@@ -2472,6 +2489,41 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
     double yb[PBR_NX2];
 #pragma unroll
     for (int v = 0; v < PBR_NX2; ++v) yb[v] = (act && z > 0) ? Ysm[v*zNo + z - 1] : 0.0;
+#if PBR_MODEL_M9
+    {
+        // pressure AND velocity are marched through the node evaluations (pbReactor.py:2456-2470, :2531-2535): block-wide fixed-point
+        // sweeps -- every thread evaluates its node at the current guess of (P_z, v_z), two block-wide prefix sums of the slopes give
+        // the next guess -- until the guess stops moving (thread z is exact after z+1 sweeps; with the previous evaluation's march as
+        // the first guess 2-3 sweeps do).  f, sub are those of the last sweep, taken at (Pu, vu).
+        const double dzL = p.zf*dz, inv_dzL = pbr_rcp(dzL);
+        double Pz = pv[0], vz = pv[1], Pu = Pz, vu = vz;
+#pragma unroll 1
+        for (int it = 0; it < zNo + 2; ++it) {
+            double dP = 0.0, dv = 0.0;
+            Pu = Pz; vu = vz;
+            if (act) pbr_m9_node(y, yb, z == 0, Pz, vz, inv_dzL, p, f, dP, dv, JAC ? sub : (double*)0);
+            cx.scan_sum2(dP, dv);
+            const double Pn = p.Pf + dzL*dP, vn = p.vs0 + dzL*dv;
+            const double chg = cx.sum(act ? fabs(Pn - Pz)*pbr_rcp(fabs(Pn)) + fabs(vn - vz)*pbr_rcp(fabs(vn)) : 0.0);
+            Pz = Pn; vz = vn;
+            if (!(chg > 1e-13)) break;                      // block-uniform; also leaves on NaN (reported by the finite check below)
+        }
+        pv[0] = Pz; pv[1] = vz;
+        double bad = 0.0;
+        if (act) {
+            if (JAC) {
+                const Strided blk = {Asm + z, PBR_K4B_ASTRIDE(zNo)};
+                SmStore st = {blk, c};
+                pbr_m9_node_jac(y, yb, z == 0, Pu, vu, inv_dzL, p, f, st);
+                if (!pbr_invert<PBR_NX2>(blk)) bad = 1.0;
+            }
+#pragma unroll
+            for (int v = 0; v < PBR_NX2; ++v) if (!(fabs(f[v]) < 1e300)) bad = 1.0;
+            if (!(fabs(Pz) < 1e300) || !(fabs(vz) < 1e300)) { bad = 1.0; pv[0] = p.Pf; pv[1] = p.vs0; }
+        }
+        return cx.sum(bad) == 0.0;
+    }
+#endif
     double a = 1.0, b = 0.0;
     if (act) {
         double Ct = 0.0, M = 0.0, yf[PBR_NV2];
@@ -2750,6 +2802,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
         double sub[PBR_NX2];
 #pragma unroll
         for (int v = 0; v < NV; ++v) sub[v] = 0.0;
+        double pv[2] = {p.Pf, p.vs0};                          // model M9: last marched (P_z, v_z) of this thread's node
         for (int kint = k_first; kint < tNo; ++kint) {
             const double t0 = (kint == 0) ? 0.0 : period*((double)kint/(double)tNo);  // np.linspace(0, opT, tNo+1)
             const double t1 = (kint == tNo - 1) ? period : period*((double)(kint + 1)/(double)tNo);
@@ -2760,7 +2813,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 double h0 = 0.0, d1 = 0.0, f0[PBR_NX2];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) { y[v] = act ? D[0*NV + v] : 1.0; sub[v] = 0.0; f[v] = 0.0; f0[v] = 0.0; }
-                bool ok = pbr_k4b_eval<false>(cx, p, zNo, act, y, 0.0, Ysm, Asm, f, sub); nfev++;
+                bool ok = pbr_k4b_eval<false>(cx, p, zNo, act, y, 0.0, Ysm, Asm, f, sub, pv); nfev++;
                 double a0 = 0.0, a1 = 0.0;
                 if (act) {
                     double yf[PBR_NV2];
@@ -2782,7 +2835,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 double y1[PBR_NX2];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) y1[v] = y[v] + h0*f0[v];
-                ok = pbr_k4b_eval<false>(cx, p, zNo, act, y1, 0.0, Ysm, Asm, f, sub) && ok; nfev++;
+                ok = pbr_k4b_eval<false>(cx, p, zNo, act, y1, 0.0, Ysm, Asm, f, sub, pv) && ok; nfev++;
                 a0 = 0.0;
                 if (act) {
                     double df[PBR_NX2];
@@ -2838,7 +2891,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                 // ---- 3./4. Jacobian blocks + inverses at the predictor, Newton (bdf.py:36-68)
                 bool converged = false;
                 PBR_K4B_TICK(tk1)
-                bool running = pbr_k4b_eval<true>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub);
+                bool running = pbr_k4b_eval<true>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub, pv);
                 PBR_K4B_TICK(tk2)
                 nlu++; nfev++;
                 double cs[PBR_NX2];
@@ -2851,7 +2904,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
                     if (running) {
                         n_iter = k + 1;
                         bool fin = true;
-                        if (k > 0) { fin = pbr_k4b_eval<false>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub); nfev++; }
+                        if (k > 0) { fin = pbr_k4b_eval<false>(cx, p, zNo, act, y, c, Ysm, Asm, f, sub, pv); nfev++; }
                         if (!fin) running = false;
                         else {
                             if (act) {

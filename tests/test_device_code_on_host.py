@@ -488,3 +488,24 @@ def test_m9_dynamic_dimensional_model_vs_reference_golden(golden):
             ym[0, k, z - 1] -= h
             col = (hs.rhs_n2(par, yp)[0, :, z] - hs.rhs_n2(par, ym)[0, :, z])/(2*h)
             assert abs(Js[0, z, k] - col[k]) < 2e-2*abs(col[k]), (tag, k, Js[0, z, k], col[k])
+
+
+def test_m9_on_the_block_per_reactor_kernels(golden):
+    """Model M9 through the block-per-reactor N2 solver on the SIMT emulator: the march of pressure and velocity is solved by
+    block-wide fixed-point sweeps (pbr_k4b_eval), full coordinates (7 variables per node).  One warp (12 nodes) against the
+    reference's converged rmtExe("M9") profiles; two warps (40 nodes), serial and scan march, against the scalar warp solver."""
+    from hostsim import SimtSim
+    g = golden("m9")
+    mi = cases.m9_case(period=0.2)
+    m = engine.Model(mi, device=None)
+    hs, sim = HostSim(m), SimtSim(m)
+    par = hs.prolog(m.instance_table(mi))
+    snaps, st, stats = sim.solve_n2("pbr_k4b_solve_n2", par, 12, 2, 0.2, rtol=1e-9, atol=1e-13)
+    assert st[0] == 0
+    T = snaps[0, :, 6, :]*par[0, 0] + par[0, 0]
+    assert np.max(np.abs(T - g["z12_conv_T"]))/500 < 1e-10
+    ref, st0, stats0 = hs.solve_n2(par, 40, 2, 0.2, rtol=1e-9, atol=1e-13)
+    for kernel in ("pbr_k4b_solve_n2", "pbr_k4bs_solve_n2"):
+        snaps, st, stats = sim.solve_n2(kernel, par, 40, 2, 0.2, rtol=1e-9, atol=1e-13)
+        assert st[0] == 0 and stats[0, 0] == stats0[0, 0]
+        assert np.max(np.abs(snaps - ref)) < 1e-12, kernel
