@@ -1573,11 +1573,16 @@ PBR_DEV void pbr_m9_node(const double* yc, const double* yb, bool first, double 
     if (sub) sub[n] = first ? 0.0 : cT2*cT1*inv_dzL;
 }
 
-// d f_z / d y_z of one M9 node at FROZEN marched (Pz, vz), by forward differences (rolled loop: one more copy of the node code).
-// The dependence of (Pz, vz) on the upstream nodes is left out of the Newton matrix exactly as N2's pressure coupling is.
+// d f_z / d y_z of one M9 node at FROZEN marched (Pz, vz): analytic, from the rate partials of the compiled kinetics (the same
+// pbr_point<true> the N-models use).  The dependence of (Pz, vz) on the upstream nodes is left out of the Newton matrix exactly as
+// N2's pressure coupling is.  PBR_M9_FD_JAC=1 restores the forward-difference blocks (7 more node evaluations) for A/B.
+#ifndef PBR_M9_FD_JAC
+#define PBR_M9_FD_JAC 0
+#endif
 template <class Store>
 PBR_DEV void pbr_m9_node_jac(const double* yc, const double* yb, bool first, double Pz, double vz, double inv_dzL, const InstPar& p,
                              const double* f, Store& st) {
+#if PBR_M9_FD_JAC
 #pragma unroll 1
     for (int k = 0; k < PBR_NV2; ++k) {
         double yk[PBR_NV2], fk[PBR_NV2], hk = 0.0, dP, dv;
@@ -1588,6 +1593,68 @@ PBR_DEV void pbr_m9_node_jac(const double* yc, const double* yb, bool first, dou
 #pragma unroll
         for (int a = 0; a < PBR_NV2; ++a) st(a, k, (fk[a] - f[a])*ih);
     }
+#else
+    const int n = PBR_NC;
+    const double epsc = PBR_EPS*pbr_rcp(p.Cmax);
+    double c[PBR_NC], mask[PBR_NC];
+#pragma unroll
+    for (int i = 0; i < n; ++i) { mask[i] = (yc[i] > epsc) ? 1.0 : 0.0; c[i] = fmax(yc[i], epsc); }
+    const double T = yc[n]*p.Tf + p.Tf;
+    PointEval e;
+    pbr_point<true>(c, T, Pz, p, e);
+    const double iT = pbr_rcp(T), iCt = e.invCt, iR = pbr_rcp(PBR_R), ieps = pbr_rcp(p.eps), iCmax = pbr_rcp(p.Cmax), iTf = pbr_rcp(p.Tf);
+    const double dPdz = -(p.E1*vz + p.E2*(e.M*e.Ct)*vz*vz);
+    double OvR = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) OvR += e.ri[i];
+    const double Tb = first ? p.Tf : (yb[n]*p.Tf + p.Tf);
+    const double dTdz = (T - Tb)*inv_dzL;
+    const double k1000 = iCt*1e-3;                                      // 1/(Ct*1000)
+    const double dvdz = k1000*((-vz*iR)*(iT*dPdz - (Pz*iT*iT)*dTdz) + OvR*1000.0);
+    const double CtCp = e.Ct*e.Cpmix;
+    const double cT1 = CtCp*vz, cT2 = pbr_rcp(CtCp*p.eps + p.tmass);
+    const double Nn = -cT1*dTdz + (-e.Hsum + e.Q);
+    double drk[PBR_NR], dri[PBR_NC];
+    // ---- species columns: C_k = Cmax c_k (clamped where the rates / Ct / density see it, unclamped in the balance's own terms)
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+        pbr_dr_dc(e, p, k, mask[k], drk);
+        pbr_dri(drk, dri);
+        const double dCt = p.Cmax*mask[k];
+        const double ddP = -p.E2*vz*vz*(p.Cmax*PBR_MWK[k]*mask[k]);
+        double dOvR = 0.0, dH = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) dOvR += dri[i];
+#pragma unroll
+        for (int j = 0; j < PBR_NR; ++j) dH += drk[j]*e.dH[j];
+        const double ddv = -dvdz*dCt*iCt + k1000*((-vz*iR)*(iT*ddP) + dOvR*1000.0);
+#pragma unroll
+        for (int i = 0; i < n; ++i)
+            st(i, k, (ieps*((i == k ? -(vz*inv_dzL + dvdz)*p.Cmax : 0.0) - (yc[i]*p.Cmax)*ddv + dri[i]))*iCmax);
+        const double dCtCp = dCt*e.cpm[k];
+        const double dN = -(dCtCp*vz)*dTdz - dH;
+        st(n, k, ((-cT2*cT2*dCtCp*p.eps)*Nn + cT2*dN)*iTf);
+    }
+    // ---- temperature column
+    {
+#pragma unroll
+        for (int j = 0; j < PBR_NR; ++j) drk[j] = p.Tf*(double)e.drT[j];
+        pbr_dri(drk, dri);
+        double dOvR = 0.0, dH = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) dOvR += dri[i];
+#pragma unroll
+        for (int j = 0; j < PBR_NR; ++j) dH += drk[j]*e.dH[j] + p.Tf*e.r[j]*e.dHdT[j];
+        const double ddTdz = p.Tf*inv_dzL;
+        const double ddv = k1000*((-vz*iR)*(-dPdz*p.Tf*iT*iT - Pz*iT*iT*ddTdz + 2.0*Pz*dTdz*p.Tf*iT*iT*iT) + dOvR*1000.0);
+#pragma unroll
+        for (int i = 0; i < n; ++i) st(i, n, (ieps*(-(yc[i]*p.Cmax)*ddv + dri[i]))*iCmax);
+        const double dCtCp = e.Ct*e.dCpmixT*p.Tf;
+        const double dQ = (p.Tm == 0.0) ? 0.0 : -p.Ua*p.Tf;
+        const double dN = -(dCtCp*vz)*dTdz - cT1*ddTdz - dH + dQ;
+        st(n, n, ((-cT2*cT2*dCtCp*p.eps)*Nn + cT2*dN)*iTf);
+    }
+#endif
 }
 #endif
 
