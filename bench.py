@@ -155,6 +155,38 @@ def ref_rhs_n2_rate(ref, zNo, n):
     return n/(time.perf_counter() - t0)
 
 
+def ref_rhs_m9_rate(ref, zNo, n):
+    """Evaluations per second of the reference's modelEquationM5 (model M9) at the case's initial state, one core."""
+    from pyremot_b200 import cases
+    PyREMOT, H, setting = ref.load()
+    import PyREMOT.docs.pbReactor as R
+    cls = R.PackedBedReactorClass
+    orig = cls.modelEquationM5
+    cap = {}
+
+    def spy(t, y, a, b, c):
+        cap["y"], cap["args"] = np.array(y), (a, b, c)
+        raise RuntimeError("captured")
+
+    old = dict(setting["S2"])
+    cls.modelEquationM5 = spy
+    setting["S2"]["zNo"] = zNo
+    try:
+        with ref.quiet():
+            PyREMOT.rmtExe(cases.m9_case())
+    except BaseException:
+        pass
+    finally:
+        cls.modelEquationM5 = orig
+        setting["S2"].update(old)
+    with ref.quiet():
+        orig(0.05, cap["y"], *cap["args"])
+        t0 = time.perf_counter()
+        for _ in range(n):
+            orig(0.05, cap["y"], *cap["args"])
+    return n/(time.perf_counter() - t0)
+
+
 def cpu_rhs_rates():
     """RHS evaluations per second of the CPU path, one core, called the way the reference calls its callbacks
     (one reactor per call): modelEquationN1 and modelEquationN2 at zNo = 100 (oracle port)."""
@@ -589,6 +621,15 @@ def bench_m9(model_device, with_cpu):
             n += 64
         rec["cpu_rhs_evals_per_s_per_core_port"] = n/(time.perf_counter() - t0)
         rec["gpu_rhs_evals_per_s_inside_solver"] = float(st[2].sum())/(ms*1e-3)
+        if reference_available():
+            from oracle import ref_driver as ref
+            r = ref_rhs_m9_rate(ref, zNo, 10)                  # the reference's own modelEquationM5 (a Python loop over the nodes)
+            rec["cpu_rhs_evals_per_s_per_core_reference"] = r
+            # derived, not timed: one reference solve at this grid = RHS evaluations of LSODA with a dense finite-difference Jacobian
+            # (700 columns) -- hours; cores x evals/s / (the evaluations SciPy's BDF on the port needs per solve: ~2,900)
+            rec["cpu_solves_per_s_reference_derived"] = {"value": (os.cpu_count() or 1)*r/2900.0, "unit": "solves/s",
+                                                         "note": "derived: cores x reference RHS evals/s / 2,900 RHS evaluations per solve "
+                                                                 "(oracle BDF with grouped finite-difference Jacobian, zNo 100, 10 intervals)"}
     return rec
 
 
