@@ -3084,10 +3084,13 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
     }
 }
 
+#ifndef PBR_K4B_MAXTHREADS
+#define PBR_K4B_MAXTHREADS 256   // A/B knob: 128 with PBR_K4B_MINBLOCKS = 3 gives the <= 128-node grids 168 registers at three blocks per SM
+#endif
 #ifndef PBR_K4B_MINBLOCKS
 #define PBR_K4B_MINBLOCKS 2      // caps the kernel at 128 registers/thread: 512 threads per SM (measured 258 -> 191 ms on config 3)
 #endif
-extern "C" __global__ void __launch_bounds__(256, PBR_K4B_MINBLOCKS) pbr_k4b_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+extern "C" __global__ void __launch_bounds__(PBR_K4B_MAXTHREADS, PBR_K4B_MINBLOCKS) pbr_k4b_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                    double rtol, double atol, int max_steps,
                                                                    double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
                                                             const double* __restrict__ iv, int k_first, int flags) {
@@ -3095,7 +3098,7 @@ extern "C" __global__ void __launch_bounds__(256, PBR_K4B_MINBLOCKS) pbr_k4b_sol
 }
 
 // the same kernel with the log-depth march: grids of more than PBR_K4B_SCAN_FROM nodes (chosen by the launcher)
-extern "C" __global__ void __launch_bounds__(256, PBR_K4B_MINBLOCKS) pbr_k4bs_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+extern "C" __global__ void __launch_bounds__(PBR_K4B_MAXTHREADS, PBR_K4B_MINBLOCKS) pbr_k4bs_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                     double rtol, double atol, int max_steps,
                                                                     double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
                                                             const double* __restrict__ iv, int k_first, int flags) {
