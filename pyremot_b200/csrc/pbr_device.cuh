@@ -3084,6 +3084,9 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
     }
 }
 
+#ifndef PBR_K4D_MAXTHREADS
+#define PBR_K4D_MAXTHREADS 512   // A/B knob: 416 lets the 400-node grid of config 4 use 152 instead of 128 registers per thread
+#endif
 #ifndef PBR_K4B_MAXTHREADS
 #define PBR_K4B_MAXTHREADS 256   // A/B knob: 128 with PBR_K4B_MINBLOCKS = 3 gives the <= 128-node grids 168 registers at three blocks per SM
 #endif
@@ -3107,7 +3110,7 @@ extern "C" __global__ void __launch_bounds__(PBR_K4B_MAXTHREADS, PBR_K4B_MINBLOC
 
 // K4d: the whole state on chip for grids of 257..512 nodes (59*zNo doubles = 189 KB at zNo = 400), scan march, one block per SM.
 // The launcher prefers it to pbr_k4c_solve_n2 whenever the state fits (170 vs 190 ms per 1,184 solves at zNo = 400).
-extern "C" __global__ void __launch_bounds__(512) pbr_k4d_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+extern "C" __global__ void __launch_bounds__(PBR_K4D_MAXTHREADS) pbr_k4d_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                                                    double rtol, double atol, int max_steps,
                                                                    double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
                                                             const double* __restrict__ iv, int k_first, int flags) {
