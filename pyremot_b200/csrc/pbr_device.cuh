@@ -2635,10 +2635,15 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
 // zNo 128 206.5 / 176.0.  The phase clocks (tools/k4b_phases.py) say why the scan does not win earlier: the serial march costs
 // ~270-310 cycles per node and is 54 % of a step at zNo 100, the scan 94 cycles per node (19 %) -- but it keeps all four warps
 // issuing, and the issue slots the serial march leaves idle are what the other three resident blocks run their phases on.
-// The launcher picks per grid size: pbr_k4b_solve_n2 (serial march) up to PBR_K4B_SCAN_FROM = 104 nodes, pbr_k4bs_solve_n2 /
-// pbr_k4d_solve_n2 / pbr_k4c_solve_n2 (scan) above.
+// With the five scan levels ROLLED (see pbr_k4b_march_scan: the out-of-phase blocks are bound by instruction fetch) the scan wins from
+// ~56 nodes up: zNo 48 84.3 / 86.2, 64 94.6 / 91.7, 80 130.7 / 121.5, 100 156.5 / 140.0 ms per 4,096 solves.
+// The launcher picks per grid size: pbr_k4b_solve_n2 (serial march) up to PBR_K4B_SCAN_FROM nodes (56 in extent coordinates, 128 with
+// 7 full variables per node), pbr_k4bs_solve_n2 / pbr_k4d_solve_n2 / pbr_k4c_solve_n2 (scan) above.
 #ifndef PBR_K4B_PROFILE
 #define PBR_K4B_PROFILE 0             // 1: phase clocks instead of step counters in `stats` (measurement build only)
+#endif
+#ifndef PBR_K4B_SCAN_ROLL
+#define PBR_K4B_SCAN_ROLL 1           // pbr_k4bs_solve_n2: the five levels of the scan march as a rolled loop (0: unrolled, A/B)
 #endif
 #ifndef PBR_K4B_MARCH_SCAN
 #define PBR_K4B_MARCH_SCAN 0          // 1: force the scan in pbr_k4b_solve_n2 as well (A/B)
@@ -2647,6 +2652,7 @@ __device__ __forceinline__ bool pbr_k4b_eval(const BlkCtx& cx, const InstPar& p,
 #define PBR_K4C_MARCH_SCAN 1          // 0: serial march in pbr_k4c_solve_n2 (A/B)
 #endif
 
+template <bool ROLL>
 __device__ __forceinline__ void pbr_k4b_march_scan(const BlkCtx& cx, int zNo, bool act, const double* Asm, double* gsm,
                                                    const double* cs, double* b) {
     const int NXm = PBR_NX2;
@@ -2663,7 +2669,10 @@ __device__ __forceinline__ void pbr_k4b_march_scan(const BlkCtx& cx, int zNo, bo
         }
         g[i] = act ? acc : 0.0;
     }
-#pragma unroll
+    // ROLL: the five levels as a rolled loop -- a fifth of the code.  With four blocks per SM in different phases the kernel is bound by
+    // instruction fetch (ncu at config 3's size: no_instruction 2.75 stall cycles per issue with the unrolled scan); rolling it took
+    // 4,096 x 100 nodes from 156.7 to 140.3 ms.  One block per SM (K4d / K4c: all warps in the same code) keeps the unrolled form.
+#pragma unroll (ROLL ? 1 : 5)
     for (int off = 1; off < 32; off <<= 1) {
         double Bp[PBR_NX2*PBR_NX2], gp[PBR_NX2];
 #pragma unroll
@@ -2793,7 +2802,7 @@ __device__ __forceinline__ void pbr_k4b_march(const BlkCtx& cx, int zNo, bool ac
 // (<= 512 threads, scan march, BDF history in a global scratch slab per block that stays L2-resident, for states that do not fit).
 // The Jacobian blocks and their inverses are rebuilt at every step attempt: keeping them while c = h/alpha is unchanged (SciPy's
 // policy) was measured and rejected -- a stale Jacobian needs two Newton iterations, i.e. two marches per step.
-template <bool D_GLOBAL, bool SCAN>
+template <bool D_GLOBAL, bool SCAN, bool ROLL = false>
 __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double period, const double* __restrict__ par,
                                              double rtol, double atol, int max_steps, double* __restrict__ gwork,
                                              double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
@@ -2981,7 +2990,7 @@ __device__ __forceinline__ void pbr_k4b_body(long N, int zNo, int tNo, double pe
 #if PBR_K4B_PROFILE
                             const long long tm0 = clock64();
 #endif
-                            if (SCAN) pbr_k4b_march_scan(cx, zNo, act, Asm, Ysm, cs, b);
+                            if (SCAN) pbr_k4b_march_scan<ROLL>(cx, zNo, act, Asm, Ysm, cs, b);
                             else pbr_k4b_march(cx, zNo, act, Asm, Ysm, cs, b);
 #if PBR_K4B_PROFILE
                             phm += clock64() - tm0;
@@ -3105,7 +3114,7 @@ extern "C" __global__ void __launch_bounds__(PBR_K4B_MAXTHREADS, PBR_K4B_MINBLOC
                                                                     double rtol, double atol, int max_steps,
                                                                     double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
                                                             const double* __restrict__ iv, int k_first, int flags) {
-    pbr_k4b_body<false, true>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats, iv, k_first, flags);
+    pbr_k4b_body<false, true, PBR_K4B_SCAN_ROLL != 0>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats, iv, k_first, flags);
 }
 
 // K4d: the whole state on chip for grids of 257..512 nodes (59*zNo doubles = 189 KB at zNo = 400), scan march, one block per SM.

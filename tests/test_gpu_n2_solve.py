@@ -146,7 +146,7 @@ def test_n2_both_kernels_agree_and_large_grid():
 
 
 def test_n2_scan_march_matches_serial_march_and_oracle():
-    """Grids above 104 nodes use the log-depth scan of the per-node affine maps (pbr_k4bs_solve_n2) instead of the serial
+    """Grids above 56 nodes use the log-depth scan of the per-node affine maps (pbr_k4bs_solve_n2) instead of the serial
     node march (pbr_k4b_solve_n2): both solve the same block-bidiagonal Newton systems, so the snapshots must agree to
     integration tolerance, and with the oracle to 1e-6.  zNo = 160 is ragged (5 warps of nodes)."""
     import os
