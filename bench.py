@@ -442,7 +442,7 @@ def run_gpu(a):
         cores = os.cpu_count() or 1
         # dynamic model under the same clock: BASELINE configs[2] whole, and one GPU's worth of 8 waves of the configs[3] grid
         n2c3 = bench_n2(model, 4096, 100, "N2 dynamic model, 100 nodes, 4096 instances, start-up transient (BASELINE configs[2])",
-                        "pbr_k4bs_solve_n2", fp64_peak)
+                        "pbr_k4bs128_solve_n2", fp64_peak)
         n2c4 = bench_n2(model, 1184, 400, "N2 dynamic model, 400 nodes, 1184-instance slice (8 per SM) of BASELINE configs[3]",
                         "pbr_k4d_solve_n2", fp64_peak)
         if world == 1:

@@ -3117,6 +3117,19 @@ extern "C" __global__ void __launch_bounds__(PBR_K4B_MAXTHREADS, PBR_K4B_MINBLOC
     pbr_k4b_body<false, true, PBR_K4B_SCAN_ROLL != 0>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats, iv, k_first, flags);
 }
 
+// the scan-march kernel for grids of up to 128 nodes (one to four warps): 168 registers, three blocks per SM.  Measured at config 3's
+// production size with the rolled scan (profiles/r2_k4b_regs_ab_rolled.txt): 128 registers x 4 blocks 142.9 ms, 168 x 3 133.3 ms,
+// 255 x 2 145.9 ms -- fewer spills buy more than the fourth block.
+#ifndef PBR_K4BS128_MINBLOCKS
+#define PBR_K4BS128_MINBLOCKS 3
+#endif
+extern "C" __global__ void __launch_bounds__(128, PBR_K4BS128_MINBLOCKS) pbr_k4bs128_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,
+                                                                    double rtol, double atol, int max_steps,
+                                                                    double* __restrict__ snaps, int* __restrict__ status, int* __restrict__ stats,
+                                                                    const double* __restrict__ iv, int k_first, int flags) {
+    pbr_k4b_body<false, true, PBR_K4B_SCAN_ROLL != 0>(N, zNo, tNo, period, par, rtol, atol, max_steps, (double*)0, snaps, status, stats, iv, k_first, flags);
+}
+
 // K4d: the whole state on chip for grids of 257..512 nodes (59*zNo doubles = 189 KB at zNo = 400), scan march, one block per SM.
 // The launcher prefers it to pbr_k4c_solve_n2 whenever the state fits (170 vs 190 ms per 1,184 solves at zNo = 400).
 extern "C" __global__ void __launch_bounds__(PBR_K4D_MAXTHREADS) pbr_k4d_solve_n2(long N, int zNo, int tNo, double period, const double* __restrict__ par,

@@ -33,7 +33,7 @@ st = r["stats"].cpu().numpy()
 if os.environ.get("PBR_BENCH_SAVE"):      # first 64 reactors' snapshots, for A/B comparisons between kernel variants
     import numpy as np
     np.save(os.environ["PBR_BENCH_SAVE"], r["snaps_y"][:64].cpu().numpy())
-kname = "pbr_k4b_solve_n2" if zNo <= 56 else "pbr_k4bs_solve_n2" if zNo <= 256 else "pbr_k4d_solve_n2 / pbr_k4c_solve_n2" if zNo <= 512 else "pbr_k4_solve_n2"
+kname = "pbr_k4b_solve_n2" if zNo <= 56 else "pbr_k4bs128_solve_n2" if zNo <= 128 else "pbr_k4bs_solve_n2" if zNo <= 256 else "pbr_k4d_solve_n2 / pbr_k4c_solve_n2" if zNo <= 512 else "pbr_k4_solve_n2"
 print(json.dumps({"kernel": kname + " (launcher's default for this grid)", "N": N, "zNo": zNo, "tNo": tNo, "period": period, "rtol": rtol, "ms": ms,
                   "solves_per_s": N/(ms*1e-3), "failed": int((r["status"] != 0).sum()), "mean_steps": float(st[0].mean()),
                   "mean_nfev": float(st[2].mean()), "mean_nlu": float(st[3].mean()),
