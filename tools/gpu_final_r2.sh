@@ -10,4 +10,7 @@ NCU="ncu --set full --clock-control none --import-source on -c 1"
 PBR_PROF_MODEL=M9 timeout 200 python tools/prof_n2.py 1184 100 1 0.2 > gpurun_out/prof_m9.log 2>&1 && \
   PBR_PROF_MODEL=M9 timeout 900 $NCU -k regex:pbr_k4b_solve -o gpurun_out/k4b_m9 -f python tools/prof_n2.py 1184 100 1 0.2 > gpurun_out/ncu_k4b_m9.log 2>&1; echo "k4b m9 rc $?"
 python tools/ncu_summary.py gpurun_out/k4b_m9.ncu-rep > gpurun_out/r2_k4b_m9_N1184_z100.txt 2>&1
-cat gpurun_out/prof_m9.log; head -30 gpurun_out/r2_k4b_m9_N1184_z100.txt
+timeout 200 python tools/prof_n2.py 4096 100 5 0.5 > gpurun_out/prof_c3.log 2>&1 && \
+  timeout 900 $NCU -k regex:pbr_k4bs128_solve -o gpurun_out/k4bs128_c3 -f python tools/prof_n2.py 4096 100 5 0.5 > gpurun_out/ncu_k4bs128.log 2>&1; echo "k4bs128 rc $?"
+python tools/ncu_summary.py gpurun_out/k4bs128_c3.ncu-rep > gpurun_out/r2_k4bs128_N4096_z100.txt 2>&1
+cat gpurun_out/prof_m9.log; head -34 gpurun_out/r2_k4bs128_N4096_z100.txt
